@@ -1,0 +1,133 @@
+"""Pin the numpy oracle to vectors produced by the unmodified reference
+(oracle/make_golden.py).  CPU only."""
+
+import numpy as np
+import pytest
+
+from oracle import fdiff_oracle as O
+from ffd_testutil import load_golden
+
+TINY = dict(L=16, C=2, H=2)
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+@pytest.mark.parametrize("L", [24, 100, 101, 187, 251, 252, 365])
+def test_fourier_matrix_form(L):
+    g = load_golden("fourier.npz")
+    x = g[f"x_{L}"].astype(np.float64)
+    assert rel(O.dft(x), g[f"dft_{L}"]) < 2e-6
+    assert rel(O.idft(x), g[f"idft_{L}"]) < 2e-6
+    # reference tests/test_utils.py:36-51 -- mutual inverses
+    assert np.abs(O.idft(O.dft(x)) - x).max() < 1e-10
+    assert np.abs(O.dft(O.idft(x)) - x).max() < 1e-10
+
+
+def _sampler(weights, L, C, H, kind, fns, dtype, use_cache, K=2, R=100, sigma_max=50.0):
+    w = O.ModelWeights.from_state_dict(weights, H, dtype=np.float32)
+    model = O.OracleScoreModel(w, L, C, dtype=dtype)
+    sde = O.SDEConfig(kind=kind, fourier_noise_scaling=fns, sigma_max=sigma_max)
+    return O.OracleSampler(model, sde, use_cache=use_cache, K=K, R=R)
+
+
+CASES = [("vp_freq", "vp", True, 50.0), ("ve_freq", "ve", True, 2.0), ("vp_time", "vp", False, 50.0)]
+
+
+@pytest.mark.parametrize("tag,kind,fns,smax", CASES)
+@pytest.mark.parametrize("cache", [False, True])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_tiny_sampler_trace(tiny_weights, tag, kind, fns, smax, cache, dtype):
+    g = load_golden(f"tiny_{tag}_{'cache' if cache else 'nocache'}.npz")
+    s = _sampler(tiny_weights, TINY["L"], TINY["C"], TINY["H"], kind, fns, dtype, cache, sigma_max=smax)
+    n = int(g["n_steps"])
+    tr = O.OracleTrace()
+    out = s.sample_batches(list(g["prior_z"]), [list(z) for z in g["step_z"]], n, trace=tr,
+                           ts=g["timesteps"])
+    # recompute decisions match exactly
+    nS = [-1 if S is None else len(S) for S in tr.recompute]
+    assert nS == list(g["nS"])
+    for i, st in enumerate(g["keep_steps"]):
+        assert rel(tr.states[st], g["keep_X"][i]) < 2e-4, st
+        assert rel(tr.scores[st], g["keep_score"][i]) < 2e-3, st
+    assert rel(out, g["final"]) < 5e-4
+    if cache:
+        assert rel(s.store.k, g["k_cache"]) < 1e-3
+        assert rel(s.store.v, g["v_cache"]) < 1e-3
+        assert rel(s.crf, g["crf"]) < 1e-3
+        st = O.cache_stats(s.store, n - 1)
+        ref = dict(zip(g["stats_keys"], g["stats_vals"]))
+        for k in ("recompute_count", "cache_hit_count", "cache_hit_ratio", "cache_ratio"):
+            assert st[k] == pytest.approx(ref[k], rel=1e-9), k
+
+
+def test_tiny_teacher_forced_steps(tiny_weights):
+    """Per-step (well-conditioned) parity: feed the reference's X_t, z_t."""
+    g = load_golden("tiny_vp_freq_cache.npz")
+    s = _sampler(tiny_weights, 16, 2, 2, "vp", True, np.float32, True)
+    n = int(g["n_steps"])
+    ts = g["timesteps"]
+    dt = np.float32(ts[0] - ts[1])
+    assert dt == g["step_size"]
+    # replay batch 0 fully so the cache state is right, checking kept steps teacher-forced
+    X = O.prior_sample(s.sde, s.G, g["prior_z"][0])
+    keep = {int(k): i for i, k in enumerate(g["keep_steps"])}
+    for i in range(n):
+        S = O.determine_recompute_set(i, 2, 100, 16)
+        if i in keep:
+            Xin = g["keep_X"][keep[i]]
+            assert float(g["keep_t"][keep[i]]) == pytest.approx(float(ts[i]), abs=0)
+            Xn, sc = s.step(Xin, float(ts[i]), g["step_z"][0][i], dt, S, i)
+            assert rel(sc, g["keep_score"][keep[i]]) < 5e-5
+            assert rel(Xn, g["keep_Xn"][keep[i]]) < 2e-6
+            X = Xn
+        else:
+            X, _ = s.step(X, float(ts[i]), g["step_z"][0][i], dt, S, i)
+
+
+def test_tiny_model_level_sets(tiny_weights):
+    g = load_golden("tiny_model_level.npz")
+    w = O.ModelWeights.from_state_dict(tiny_weights, 2)
+    model = O.OracleScoreModel(w, 16, 2, dtype=np.float32)
+    store = O.KVStore(2, 16)
+    for i, s in enumerate(g["sets"]):
+        S = [int(v) for v in str(s).split(",") if v != ""]
+        score, crf = model.forward_cached(g["X"] + np.float32(0.01 * i), float(g["t"]), S, store)
+        assert rel(score, g["scores"][i]) < 5e-5, i
+        assert rel(crf, g["crf"][i]) < 5e-5, i
+    assert rel(store.k, g["k_cache"]) < 1e-5
+    assert rel(store.v, g["v_cache"]) < 1e-5
+
+
+def test_tiny_cold_cache_is_zero_kv(tiny_weights):
+    g = load_golden("tiny_cold_cache.npz")
+    w = O.ModelWeights.from_state_dict(tiny_weights, 2)
+    model = O.OracleScoreModel(w, 16, 2, dtype=np.float32)
+    score, crf = model.forward_cached(g["X"], float(g["t"]), [], O.KVStore(2, 16))
+    assert rel(score, g["score"]) < 5e-5
+    assert rel(crf, g["crf"]) < 5e-5
+
+
+def test_pos_embedding_renorm(tiny_weights):
+    g = load_golden("tiny_vp_freq_nocache.npz")
+    got = O.posemb_renorm(tiny_weights["pos_encoder.embedding.weight"], np.sqrt(12.0), iters=8)
+    assert np.abs(got - g["pos_after"]).max() < 1e-6
+
+
+def test_linspace_close_to_torch():
+    import torch
+
+    for n in (2, 3, 10, 103, 1000):
+        a, b = O.linspace_f32(1.0, 1e-5, n), torch.linspace(1.0, 1e-5, n).numpy()
+        assert np.abs(a - b).max() <= 1.2e-7 and a[0] == b[0] and a[-1] == b[-1]
+
+
+def test_schedule_closed_form():
+    # caching.py:131-181
+    assert O.determine_recompute_set(0, 5, 10, 187) == list(range(187))
+    assert O.determine_recompute_set(500, 5, 10, 187) == list(range(10))
+    assert O.determine_recompute_set(10, 5, 10, 187) == []
+    assert O.determine_recompute_set(150, 1, 150, 187) == [0, 1]
+    assert O.determine_recompute_set(500, 0, 10, 187) == []
+    assert O.determine_recompute_set(500, 200, 10, 187) == list(range(187))
