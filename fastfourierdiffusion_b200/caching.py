@@ -1,0 +1,152 @@
+"""E2-CRF cache -- host mirror of ``fdiff.utils.caching.E2CRFCache``.
+
+What the reference's cache does on the sampling path is:
+a recompute schedule that is a pure function of the step index
+(caching.py:131-181), a sample-0 K/V store of shape (num_layers, nhead,
+max_len, head_dim) (caching.py:251-396), a CRF store written when
+``current_step % R == 0`` (caching.py:459-480) and counters
+(caching.py:599-636).  The K/V and CRF tensors live on the device and are
+written by the kernels; the schedule and the counters are deterministic, so
+they stay on the host and the step loop never synchronises.
+
+FreqCa / event-intensity code of the reference is never reached from the
+sampler and is not mirrored; the corresponding constructor
+arguments are accepted and stored so that ``cache_kwargs`` keep working.
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Set
+
+import torch
+
+
+class E2CRFCache:
+    def __init__(self, num_layers: int, max_len: int, device: torch.device, K: int = 5, R: int = 10,
+                 tau_0: float = 0.1, tau_warn: float = 0.5, use_freqca: bool = False, freq_decomp: str = "dct",
+                 low_freq_ratio: float = 0.3, max_history: int = 10, hermite_order: int = 3,
+                 freq_decomp_interval: int = 10, use_fresca_in_cache: bool = False,
+                 fresca_adaptive_threshold: bool = False):
+        if use_freqca:
+            raise NotImplementedError("FreqCa is off the sampling path of the reference and is not built")
+        self.num_layers = num_layers
+        self.max_len = max_len
+        self.device = device
+        self.K = K
+        self.R = R
+        self.tau_0 = tau_0
+        self.tau_warn = tau_warn
+        self.use_freqca = use_freqca
+        self.freq_decomp = freq_decomp
+        self.low_freq_ratio = low_freq_ratio
+        self.max_history = max_history
+        self.hermite_order = hermite_order
+        self.freq_decomp_interval = freq_decomp_interval
+        self.use_fresca_in_cache = use_fresca_in_cache
+        self.fresca_adaptive_threshold = fresca_adaptive_threshold
+        # device stores, attached by ScoreModule.enable_caching (shape needs nhead/head_dim)
+        self._k_store: Optional[torch.Tensor] = None  # [NL, H, L, hd], zero = never stored
+        self._v_store: Optional[torch.Tensor] = None
+        self._crf_store: Optional[torch.Tensor] = None  # [NL, L, d]
+        self._populated = False  # reference: k_cache_tensor is None until the first store
+        self._crf_valid = False
+        self._valid = torch.zeros(num_layers, max_len, dtype=torch.bool)  # host copy of cache_valid
+        self.stats = {"recompute_count": 0, "cache_hit_count": 0}
+        self.current_step = 0
+
+    # -- device stores ---------------------------------------------------------
+    def attach_stores(self, n_head: int, head_dim: int, d_model: int) -> None:
+        dev = self.device
+        self._k_store = torch.zeros(self.num_layers, n_head, self.max_len, head_dim, device=dev)
+        self._v_store = torch.zeros_like(self._k_store)
+        self._crf_store = torch.zeros(self.num_layers, self.max_len, d_model, device=dev)
+
+    @property
+    def k_cache_tensor(self) -> Optional[torch.Tensor]:
+        return self._k_store if self._populated else None
+
+    @property
+    def v_cache_tensor(self) -> Optional[torch.Tensor]:
+        return self._v_store if self._populated else None
+
+    @property
+    def cache_valid(self) -> Optional[torch.Tensor]:
+        return self._valid.to(self.device) if self._populated else None
+
+    @property
+    def crf_cache(self) -> Optional[torch.Tensor]:
+        return self._crf_store if self._crf_valid else None
+
+    def reset(self) -> None:
+        """caching.py:115-129 (tensors dropped there; zeroed here, which reads the same)."""
+        if self._k_store is not None:
+            self._k_store.zero_()
+            self._v_store.zero_()
+        self._populated = False
+        self._crf_valid = False
+        self._valid.zero_()
+        self.stats = {"recompute_count": 0, "cache_hit_count": 0}
+        self.current_step = 0
+
+    # -- schedule ------------------------------------------------------------------
+    def determine_recompute_set(self, x_tilde: Optional[torch.Tensor], event_intensity: float,
+                                step: int) -> Set[int]:
+        """caching.py:131-181: all tokens at step 0, the first min(2K, L) tokens every
+        ``500 if R < 100 else R`` steps, nothing otherwise.  ``x_tilde`` and
+        ``event_intensity`` are ignored, as in the reference."""
+        if step == 0:
+            return set(range(self.max_len))
+        interval = 500 if self.R < 100 else self.R
+        if step % interval == 0:
+            return set(range(min(2 * min(self.K, self.max_len), self.max_len)))
+        return set()
+
+    def crf_stored_at(self, step: int) -> bool:
+        """update_crf keeps the CRF iff current_step % R == 0 (caching.py:474); R == 0
+        raises ZeroDivisionError exactly like the reference."""
+        return step % self.R == 0
+
+    # -- host-side bookkeeping of what the kernels did --------------------------
+    def account_forward(self, n_own: int, own_idx=None) -> None:
+        """Counter / validity updates of one cached-mode forward over all layers
+        (caching.py:283,299,389-396; branch rules cached_transformer.py:142-305)."""
+        L, NL = self.max_len, self.num_layers
+        if n_own == L:
+            self.stats["recompute_count"] += NL * L
+            self._valid[:] = True
+            self._populated = True
+        elif n_own > 0.8 * L:
+            return
+        elif n_own == 0:
+            if self._populated:
+                self.stats["cache_hit_count"] += NL * L
+        else:
+            for _ in range(NL):
+                if self._populated and L - n_own > 0:
+                    self.stats["cache_hit_count"] += L - n_own
+                self.stats["recompute_count"] += n_own
+                self._populated = True
+            idx = list(range(n_own)) if own_idx is None else list(own_idx)
+            self._valid[:, idx] = True
+
+    def update_crf(self, crf: Optional[torch.Tensor], timestep: Optional[float] = None) -> None:
+        """caching.py:459-480.  On the fused path the kernel has already written the
+        CRF rows into the device store; a tensor passed here is copied in."""
+        if self.crf_stored_at(self.current_step):
+            if crf is not None and self._crf_store is not None and crf.data_ptr() != self._crf_store.data_ptr():
+                self._crf_store.copy_(crf)
+            self._crf_valid = True
+
+    def get_cache_stats(self) -> dict:
+        """caching.py:599-636."""
+        total = self.stats["recompute_count"] + self.stats["cache_hit_count"]
+        ratio = float(self._valid.float().mean().item()) if self._populated else 0.0
+        if ratio >= 1.0:
+            ratio = 0.99  # the reference caps a fully valid cache at 99 % (caching.py:623-628)
+        return {
+            "cache_hit_ratio": self.stats["cache_hit_count"] / total if total > 0 else 0.0,
+            "cache_ratio": ratio,
+            "recompute_count": self.stats["recompute_count"],
+            "cache_hit_count": self.stats["cache_hit_count"],
+            "current_step": self.current_step,
+        }

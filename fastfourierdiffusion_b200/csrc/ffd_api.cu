@@ -1,0 +1,309 @@
+// C ABI (include/ffd_b200.h) and the per-step orchestration of the score model.
+#include <stdarg.h>
+#include <string.h>
+
+#include "ffd_internal.h"
+
+namespace ffd {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED); }
+
+static int check_dims(const ffd_dims& m) {
+  FFD_CHECK_ARG(m.max_len > 0 && m.n_channels > 0 && m.d_model > 0 && m.n_head > 0 && m.d_ff > 0 && m.n_layers > 0,
+                "non-positive model dimension");
+  FFD_CHECK_ARG(m.d_model % m.n_head == 0, "d_model %d not divisible by n_head %d", m.d_model, m.n_head);
+  FFD_CHECK_ARG(m.d_model <= 128, "d_model %d > 128 unsupported", m.d_model);
+  FFD_CHECK_ARG(m.d_model / m.n_head <= 64, "head_dim %d > 64 unsupported", m.d_model / m.n_head);
+  return FFD_OK;
+}
+
+// one encoder layer, fp32 arithmetic (FFD_PREC_BF16 swaps in the tcgen05 FFN)
+//   x = LN1(x + MHA(x));  x = LN2(x + FFN(x))      cached_transformer.py:123-134 / :309-327
+static int run_layer(const ffd_forward_args& a, const Arena& ar, const Workspace& ws, int layer, int branch,
+                     cudaStream_t s) {
+  const ffd_dims& m = a.dims;
+  const int L = m.max_len, d = m.d_model, H = m.n_head, hd = d / H, F = m.d_ff;
+  const int64_t M = a.B * L;
+  const float* w = a.weights + ar.layer0 + (int64_t)layer * ar.layer_stride;
+  float* kc = a.k_cache ? a.k_cache + (int64_t)layer * H * L * hd : nullptr;
+  float* vc = a.v_cache ? a.v_cache + (int64_t)layer * H * L * hd : nullptr;
+  int rc;
+  // branch: 0 = stock attention (all K/V own), 1 = pure cache, 2 = mixed
+  const int nq = (branch == 1) ? d : 3 * d;  // pure cache projects Q only (cached_transformer.py:229)
+  if ((rc = launch_linear(ws.h, d, w + ar.in_w, d, w + ar.in_b, ws.qkv, 3 * d, M, nq, d, 0, s))) return rc;
+  if (branch == 2) {
+    // store sample 0's recomputed rows BEFORE attention reads the cache? No: the mixed branch
+    // reads cached rows only for tokens outside S and writes only rows inside S
+    // (cached_transformer.py:275-276,295-296,304), so the order is immaterial.
+    if ((rc = launch_scatter_kv(ws.qkv, 3 * d, d, 2 * d, a.own_mask, a.n_own, kc, vc, L, H, hd, s))) return rc;
+  }
+  const int n_prefix = (branch == 0) ? L : (branch == 1 ? 0 : a.n_own);
+  const int32_t* mask = (branch == 2) ? a.own_mask : nullptr;
+  if ((rc = launch_attention(ws.qkv, 3 * d, kc, vc, mask, n_prefix, ws.attn, a.B, L, d, H, s))) return rc;
+  if ((rc = launch_linear(ws.attn, d, w + ar.out_w, d, w + ar.out_b, ws.tmp, d, M, d, d, 0, s))) return rc;
+  if ((rc = launch_add_ln(ws.h, ws.tmp, w + ar.n1w, w + ar.n1b, ws.h, M, d, s))) return rc;
+  if (a.precision == FFD_PREC_BF16) {
+    if ((rc = tc_ffn_ln(m, a.packed, a.weights, layer, ws.h, ws.h, M, s))) return rc;
+  } else {
+    if ((rc = launch_ffn(ws.h, w + ar.w1, w + ar.b1, w + ar.w2, w + ar.b2, ws.tmp, M, d, F, s))) return rc;
+    if ((rc = launch_add_ln(ws.h, ws.tmp, w + ar.n2w, w + ar.n2b, ws.h, M, d, s))) return rc;
+  }
+  return FFD_OK;
+}
+
+// Which branch of CachedTransformerEncoderLayer.forward runs (cached_transformer.py:106-329).
+//   returns 0 stock, 1 pure cache, 2 mixed; *populate = 1 when the full-recompute branch stores K/V.
+static int pick_branch(const ffd_forward_args& a, int* populate) {
+  *populate = 0;
+  if (a.mode == FFD_MODE_STOCK) return 0;
+  const int L = a.dims.max_len;
+  if (a.n_own == L) {
+    *populate = 1;
+    return 0;
+  }
+  if ((double)a.n_own > 0.8 * (double)L) return 0;
+  return a.n_own == 0 ? 1 : 2;
+}
+
+static int forward_hidden(const ffd_forward_args& a, const Arena& ar, const Workspace& ws, cudaStream_t s) {
+  const ffd_dims& m = a.dims;
+  const int L = m.max_len, C = m.n_channels, d = m.d_model, H = m.n_head, hd = d / H;
+  const int64_t M = a.B * L;
+  int rc;
+  if ((rc = launch_embed(a.X, a.weights + ar.emb_w, a.weights + ar.emb_b, a.weights + ar.pos, a.time_emb, ws.h, M,
+                         L, C, d, s)))
+    return rc;
+  int populate = 0;
+  const int branch = pick_branch(a, &populate);
+  for (int l = 0; l < m.n_layers; ++l) {
+    if ((rc = run_layer(a, ar, ws, l, branch, s))) return rc;
+    if (populate) {
+      // K/V of the layer OUTPUT of sample 0, all rows (cached_transformer.py:142-168)
+      const float* w = a.weights + ar.layer0 + (int64_t)l * ar.layer_stride;
+      if ((rc = launch_linear(ws.h, d, w + ar.in_w + (int64_t)d * d, d, w + ar.in_b + d, ws.kvtmp, 2 * d, L, 2 * d,
+                              d, 0, s)))
+        return rc;
+      if ((rc = launch_scatter_kv(ws.kvtmp, 2 * d, 0, d, nullptr, L, a.k_cache + (int64_t)l * H * L * hd,
+                                  a.v_cache + (int64_t)l * H * L * hd, L, H, hd, s)))
+        return rc;
+    }
+    if (a.crf_out && a.mode == FFD_MODE_CACHED) {
+      // crf[l] = h[0]  (score_models.py:151,188)
+      FFD_CHECK_CUDA(cudaMemcpyAsync(a.crf_out + (int64_t)l * L * d, ws.h, sizeof(float) * L * d,
+                                     cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  return FFD_OK;
+}
+
+static int check_forward(const ffd_forward_args& a) {
+  int rc = check_dims(a.dims);
+  if (rc) return rc;
+  FFD_CHECK_ARG(a.B >= 0, "negative batch");
+  FFD_CHECK_ARG(a.weights && a.workspace && a.X && a.time_emb, "null pointer in ffd_forward_args");
+  FFD_CHECK_ARG(a.precision == FFD_PREC_FP32 || a.precision == FFD_PREC_BF16, "unknown precision %d", a.precision);
+  if (a.precision == FFD_PREC_BF16) {
+    FFD_CHECK_ARG(a.packed != nullptr, "FFD_PREC_BF16 needs the packed weight image");
+    if (!tc_supported(a.dims)) {
+      set_error("tensor-core path unsupported for these dims (needs d_model <= 80, d_ff %% 128 == 0)");
+      return FFD_ERR_UNSUPPORTED;
+    }
+  }
+  FFD_CHECK_ARG(a.mode == FFD_MODE_STOCK || a.mode == FFD_MODE_CACHED, "unknown mode %d", a.mode);
+  if (a.mode == FFD_MODE_CACHED) {
+    FFD_CHECK_ARG(a.k_cache && a.v_cache, "cached mode needs k_cache/v_cache");
+    FFD_CHECK_ARG(a.n_own >= 0 && a.n_own <= a.dims.max_len, "n_own %d out of range", a.n_own);
+  }
+  const int64_t need = ffd_workspace_bytes(&a.dims, a.B, a.precision);
+  if (a.workspace_bytes < need) {
+    set_error("workspace too small: %lld < %lld", (long long)a.workspace_bytes, (long long)need);
+    return FFD_ERR_WORKSPACE;
+  }
+  return FFD_OK;
+}
+
+}  // namespace ffd
+
+using namespace ffd;
+
+extern "C" {
+
+int ffd_version(void) { return 1; }
+uint64_t ffd_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+const char* ffd_last_error(void) { return g_err; }
+
+int64_t ffd_weights_count(const ffd_dims* dims) { return dims ? arena_of(*dims).total : -1; }
+int64_t ffd_layer_stride(const ffd_dims* dims) { return dims ? arena_of(*dims).layer_stride : -1; }
+int64_t ffd_layer0_offset(const ffd_dims* dims) { return dims ? arena_of(*dims).layer0 : -1; }
+
+int64_t ffd_packed_bytes(const ffd_dims* dims) { return dims ? tc_packed_bytes(*dims) : -1; }
+
+int ffd_pack_weights(const ffd_dims* dims, const float* weights, void* packed, ffd_stream_t stream) {
+  FFD_CHECK_ARG(dims && weights && packed, "null pointer");
+  int rc = check_dims(*dims);
+  if (rc) return rc;
+  if (!tc_supported(*dims)) {
+    set_error("tensor-core path unsupported for these dims");
+    return FFD_ERR_UNSUPPORTED;
+  }
+  return tc_pack_weights(*dims, weights, packed, (cudaStream_t)stream);
+}
+
+int64_t ffd_workspace_bytes(const ffd_dims* dims, int64_t B, int precision) {
+  (void)precision;
+  if (!dims || B < 0) return -1;
+  return carve(*dims, B, nullptr).bytes;
+}
+
+int ffd_has_tensor_path(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+int ffd_dft_matrix(float* out, int L, int inverse, ffd_stream_t stream) {
+  FFD_CHECK_ARG(out && L > 0 && L <= 8192, "bad ffd_dft_matrix arguments");
+  return launch_dft_matrix(out, L, inverse, (cudaStream_t)stream);
+}
+
+int ffd_dft_apply(const float* T, const float* x, const float* scale, const float* shift, float* y, int64_t B,
+                  int L, int C, ffd_stream_t stream) {
+  FFD_CHECK_ARG(T && x && y && B >= 0 && L > 0 && C > 0, "bad ffd_dft_apply arguments");
+  FFD_CHECK_ARG(x != y, "ffd_dft_apply cannot run in place");
+  return launch_dft_apply(T, x, scale, shift, y, B, L, C, (cudaStream_t)stream);
+}
+
+int ffd_posemb_renorm(float* table, int L, int d, float max_norm, ffd_stream_t stream) {
+  FFD_CHECK_ARG(table && L > 0 && d > 0, "bad ffd_posemb_renorm arguments");
+  return launch_posemb_renorm(table, L, d, max_norm, (cudaStream_t)stream);
+}
+
+int ffd_time_embedding(const float* t, int n, const float* W, const float* dense_w, const float* dense_b, int d,
+                       float* out, ffd_stream_t stream) {
+  FFD_CHECK_ARG(t && W && dense_w && dense_b && out && n >= 0 && d > 0 && d <= 4096, "bad ffd_time_embedding arguments");
+  return launch_time_embedding(t, n, W, dense_w, dense_b, d, out, (cudaStream_t)stream);
+}
+
+int ffd_score_forward(const ffd_forward_args* a, ffd_stream_t stream) {
+  FFD_CHECK_ARG(a != nullptr, "null args");
+  int rc = check_forward(*a);
+  if (rc) return rc;
+  FFD_CHECK_ARG(a->score != nullptr, "score output is null");
+  if (a->B == 0) return FFD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const Arena ar = arena_of(a->dims);
+  const Workspace ws = carve(a->dims, a->B, a->workspace);
+  if ((rc = forward_hidden(*a, ar, ws, s))) return rc;
+  const ffd_dims& m = a->dims;
+  return launch_unembed_step(ws.h, a->weights + ar.unemb_w, a->weights + ar.unemb_b, a->score, 0, nullptr, nullptr,
+                             nullptr, nullptr, 0, 0, nullptr, a->B * m.max_len, m.max_len, m.n_channels, m.d_model,
+                             s);
+}
+
+int ffd_ffn_ln(const ffd_dims* dims, int precision, const float* weights, const void* packed, int layer,
+               const float* x, float* y, float* scratch, int64_t M, ffd_stream_t stream) {
+  FFD_CHECK_ARG(dims && weights && x && y && M >= 0, "bad ffd_ffn_ln arguments");
+  int rc = check_dims(*dims);
+  if (rc) return rc;
+  FFD_CHECK_ARG(layer >= 0 && layer < dims->n_layers, "layer %d out of range", layer);
+  if (M == 0) return FFD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (precision == FFD_PREC_BF16) {
+    FFD_CHECK_ARG(packed != nullptr, "FFD_PREC_BF16 needs the packed weight image");
+    if (!tc_supported(*dims)) {
+      set_error("tensor-core path unsupported for these dims");
+      return FFD_ERR_UNSUPPORTED;
+    }
+    return tc_ffn_ln(*dims, packed, weights, layer, x, y, M, s);
+  }
+  FFD_CHECK_ARG(precision == FFD_PREC_FP32, "unknown precision %d", precision);
+  FFD_CHECK_ARG(scratch != nullptr, "fp32 path needs an [M, d] scratch buffer");
+  const Arena ar = arena_of(*dims);
+  const float* w = weights + ar.layer0 + (int64_t)layer * ar.layer_stride;
+  const int d = dims->d_model;
+  if ((rc = launch_ffn(x, w + ar.w1, w + ar.b1, w + ar.w2, w + ar.b2, scratch, M, d, dims->d_ff, s))) return rc;
+  return launch_add_ln(x, scratch, w + ar.n2w, w + ar.n2b, y, M, d, s);
+}
+
+int ffd_sde_step(const ffd_step_coef* c, const float* G, const float* x, const float* score, const float* z,
+                 uint64_t seed, uint64_t stream_id, float* x_out, int64_t B, int L, int C, ffd_stream_t stream) {
+  FFD_CHECK_ARG(c && G && x && score && x_out && B >= 0 && L > 0 && C > 0, "bad ffd_sde_step arguments");
+  FFD_CHECK_ARG(c->kind == FFD_SDE_VP || c->kind == FFD_SDE_VE, "unknown SDE kind %d", c->kind);
+  FFD_CHECK_ARG(c->dt > 0.f, "step_size must be positive (sde.py:158,239)");
+  return launch_sde_step(c, G, x, score, z, seed, stream_id, x_out, B, L, C, (cudaStream_t)stream);
+}
+
+int ffd_prior(const float* G, const float* z, uint64_t seed, uint64_t stream_id, float scale, float* x_out,
+              int64_t B, int L, int C, ffd_stream_t stream) {
+  FFD_CHECK_ARG(G && x_out && B >= 0 && L > 0 && C > 0, "bad ffd_prior arguments");
+  return launch_prior(G, z, seed, stream_id, scale, x_out, B, L, C, (cudaStream_t)stream);
+}
+
+int ffd_philox_normal(uint64_t seed, uint64_t stream_id, float* out, int64_t n, ffd_stream_t stream) {
+  FFD_CHECK_ARG(out && n >= 0, "bad ffd_philox_normal arguments");
+  return launch_philox_normal(seed, stream_id, out, n, (cudaStream_t)stream);
+}
+
+int ffd_sample_steps(const ffd_sample_args* a, ffd_stream_t stream) {
+  FFD_CHECK_ARG(a != nullptr, "null args");
+  FFD_CHECK_ARG(a->G && a->time_emb_table && a->coef_host && a->n_own_host && a->x && a->x_tmp,
+                "null pointer in ffd_sample_args");
+  FFD_CHECK_ARG(a->step_begin >= 0 && a->step_end >= a->step_begin, "bad step range");
+  FFD_CHECK_ARG(!a->noise || a->noise_step0 <= a->step_begin, "noise_step0 beyond step_begin");
+  ffd_forward_args f = a->fwd;
+  f.X = a->x;
+  f.time_emb = a->time_emb_table;  // placeholder for the null check
+  int rc = check_forward(f);
+  if (rc) return rc;
+  if (f.B == 0) return FFD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const ffd_dims& m = f.dims;
+  const Arena ar = arena_of(m);
+  const Workspace ws = carve(m, f.B, f.workspace);
+  const int64_t n_elem = f.B * m.max_len * m.n_channels;
+  float* cur = a->x;
+  float* nxt = a->x_tmp;
+  for (int i = a->step_begin; i < a->step_end; ++i) {
+    const ffd_step_coef& c = a->coef_host[i];
+    FFD_CHECK_ARG(c.dt > 0.f, "step_size must be positive (sde.py:158,239)");
+    ffd_forward_args fi = f;
+    fi.X = cur;
+    fi.time_emb = a->time_emb_table + (int64_t)i * m.d_model;
+    const int n_own = a->n_own_host[i];
+    if (n_own < 0) {
+      fi.mode = FFD_MODE_STOCK;
+      fi.n_own = 0;
+    } else {
+      fi.mode = FFD_MODE_CACHED;
+      fi.n_own = n_own;
+      fi.own_mask = nullptr;  // the sampler's sets are prefixes (caching.py:164-181)
+      FFD_CHECK_ARG(n_own <= m.max_len && fi.k_cache && fi.v_cache, "bad cached step %d", i);
+    }
+    if (!(a->store_crf_host && a->store_crf_host[i])) fi.crf_out = nullptr;
+    if ((rc = forward_hidden(fi, ar, ws, s))) return rc;
+    const float* z = a->noise ? a->noise + (int64_t)(i - a->noise_step0) * n_elem : nullptr;
+    if ((rc = launch_unembed_step(ws.h, f.weights + ar.unemb_w, f.weights + ar.unemb_b, f.score, 1, &c, a->G, cur, z,
+                                  a->seed, a->stream_base + (uint64_t)i, nxt, f.B * m.max_len, m.max_len,
+                                  m.n_channels, m.d_model, s)))
+      return rc;
+    float* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  if (cur != a->x)
+    FFD_CHECK_CUDA(cudaMemcpyAsync(a->x, cur, sizeof(float) * n_elem, cudaMemcpyDeviceToDevice, s));
+  return FFD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// Shared helpers for the ffd_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "ffd_b200.h"
+
+namespace ffd {
+
+void set_error(const char* fmt, ...);
+void count_launch();
+
+#define FFD_CHECK_ARG(cond, ...)          \
+  do {                                    \
+    if (!(cond)) {                        \
+      ffd::set_error(__VA_ARGS__);        \
+      return FFD_ERR_ARG;                 \
+    }                                     \
+  } while (0)
+
+#define FFD_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ffd::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return FFD_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define FFD_CHECK_LAUNCH(name)                                                            \
+  do {                                                                                    \
+    ffd::count_launch();                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      ffd::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));            \
+      return FFD_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// ---- weight arena offsets (ffd_b200.h) ---------------------------------------
+struct Arena {
+  int64_t pos, emb_w, emb_b, unemb_w, unemb_b, layer0, layer_stride, total;
+  // within a layer block
+  int64_t in_w, in_b, out_w, out_b, w1, b1, w2, b2, n1w, n1b, n2w, n2b;
+};
+
+static inline Arena arena_of(const ffd_dims& m) {
+  Arena a;
+  const int64_t L = m.max_len, C = m.n_channels, d = m.d_model, F = m.d_ff;
+  int64_t o = 0;
+  a.pos = o; o += L * d;
+  a.emb_w = o; o += d * C;
+  a.emb_b = o; o += d;
+  a.unemb_w = o; o += C * d;
+  a.unemb_b = o; o += C;
+  a.layer0 = o;
+  int64_t q = 0;
+  a.in_w = q; q += 3 * d * d;
+  a.in_b = q; q += 3 * d;
+  a.out_w = q; q += d * d;
+  a.out_b = q; q += d;
+  a.w1 = q; q += F * d;
+  a.b1 = q; q += F;
+  a.w2 = q; q += d * F;
+  a.b2 = q; q += d;
+  a.n1w = q; q += d;
+  a.n1b = q; q += d;
+  a.n2w = q; q += d;
+  a.n2b = q; q += d;
+  a.layer_stride = q;
+  a.total = o + q * m.n_layers;
+  return a;
+}
+
+// ---- workspace carve-up --------------------------------------------------------
+struct Workspace {
+  float* h;     // [M, d] residual stream
+  float* tmp;   // [M, d] pre-LN sums
+  float* attn;  // [M, d] attention output (heads merged)
+  float* qkv;   // [M, 3d]
+  float* kvtmp; // [L, 2d] sample-0 K/V of a full step
+  int64_t bytes;
+};
+
+static inline Workspace carve(const ffd_dims& m, int64_t B, void* base) {
+  Workspace w;
+  const int64_t M = B * m.max_len, d = m.d_model;
+  char* p = (char*)base;
+  int64_t o = 0;
+  auto take = [&](int64_t nfloat) {
+    float* r = (float*)(p + o);
+    o += align_up(nfloat * 4, 1024);
+    return r;
+  };
+  w.h = take(M * d);
+  w.tmp = take(M * d);
+  w.attn = take(M * d);
+  w.qkv = take(M * 3 * d);
+  w.kvtmp = take((int64_t)m.max_len * 2 * d);
+  w.bytes = o;
+  return w;
+}
+
+// ---- device helpers --------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Philox-4x32-10 (Salmon et al. 2011); restated in oracle/fdiff_oracle.py:philox4x32_10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// four N(0,1) draws for element quad q of stream `stream_id`
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t stream_id, uint64_t q) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)stream_id,
+                                           (uint32_t)(stream_id >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = ((float)r.x + 0.5f) * k, u1 = ((float)r.y + 0.5f) * k;
+  const float u2 = ((float)r.z + 0.5f) * k, u3 = ((float)r.w + 0.5f) * k;
+  const float rad0 = sqrtf(-2.0f * logf(u0));
+  const float rad1 = sqrtf(-2.0f * logf(u2));
+  float s0, c0, s1, c1;
+  sincospif(2.0f * u1, &s0, &c0);
+  sincospif(2.0f * u3, &s1, &c1);
+  return make_float4(rad0 * c0, rad0 * s0, rad1 * c1, rad1 * s1);
+}
+
+}  // namespace ffd

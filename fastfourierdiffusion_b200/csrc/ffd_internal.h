@@ -1,0 +1,43 @@
+// Internal launch wrappers shared between translation units.
+#pragma once
+#include "ffd_common.cuh"
+
+namespace ffd {
+
+// ffd_simt.cu
+int launch_embed(const float* X, const float* We, const float* be, const float* pos, const float* te, float* h,
+                 int64_t M, int L, int C, int d, cudaStream_t s);
+int launch_linear(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy,
+                  int64_t M, int N, int K, int relu, cudaStream_t s);
+int launch_attention(const float* qkv, int ldq, const float* kc, const float* vc, const int32_t* own_mask,
+                     int n_prefix_own, float* out, int64_t B, int L, int d, int H, cudaStream_t s);
+int launch_add_ln(const float* res, const float* x, const float* w, const float* b, float* y, int64_t M, int d,
+                  cudaStream_t s);
+int launch_ffn(const float* X, const float* W1, const float* b1, const float* W2, const float* b2, float* out,
+               int64_t M, int d, int F, cudaStream_t s);
+int launch_scatter_kv(const float* src, int lds, int k_off, int v_off, const int32_t* own_mask, int n_prefix_own,
+                      float* kc, float* vc, int L, int H, int hd, cudaStream_t s);
+int launch_unembed_step(const float* h, const float* Wu, const float* bu, float* score_out, int do_step,
+                        const ffd_step_coef* coef, const float* G, const float* x, const float* z, uint64_t seed,
+                        uint64_t stream_id, float* x_out, int64_t M, int L, int C, int d, cudaStream_t s);
+int launch_sde_step(const ffd_step_coef* c, const float* G, const float* x, const float* score, const float* z,
+                    uint64_t seed, uint64_t stream_id, float* x_out, int64_t B, int L, int C, cudaStream_t s);
+int launch_prior(const float* G, const float* z, uint64_t seed, uint64_t stream_id, float scale, float* x_out,
+                 int64_t B, int L, int C, cudaStream_t s);
+int launch_philox_normal(uint64_t seed, uint64_t stream_id, float* out, int64_t n, cudaStream_t s);
+int launch_posemb_renorm(float* table, int L, int d, float max_norm, cudaStream_t s);
+int launch_time_embedding(const float* t, int n, const float* W, const float* dense_w, const float* dense_b, int d,
+                          float* out, cudaStream_t s);
+int launch_dft_matrix(float* out, int L, int inverse, cudaStream_t s);
+int launch_dft_apply(const float* T, const float* x, const float* scale, const float* shift, float* y, int64_t B,
+                     int L, int C, cudaStream_t s);
+
+// ffd_tc.cu (tcgen05 path)
+int64_t tc_packed_bytes(const ffd_dims& m);
+int tc_pack_weights(const ffd_dims& m, const float* weights, void* packed, cudaStream_t s);
+bool tc_supported(const ffd_dims& m);
+// out = LN2(x + W2 relu(W1 x + b1) + b2) for layer `layer`, rows [0, M)
+int tc_ffn_ln(const ffd_dims& m, const void* packed, const float* weights, int layer, const float* x, float* y,
+              int64_t M, cudaStream_t s);
+
+}  // namespace ffd

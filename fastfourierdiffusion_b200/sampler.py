@@ -1,0 +1,193 @@
+"""Reverse-SDE sampler -- host mirror of ``fdiff.sampling.sampler.DiffusionSampler``.
+
+Same constructor and ``sample`` / ``reverse_diffusion_step`` / ``sample_prior``
+contract as the reference (sampler.py:14-228).  The step loop itself
+(sampler.py:157-210) is one ``ffd_sample_steps`` call per noise chunk: the
+recompute schedule, the per-step SDE scalars and the time-embedding table are
+precomputed (they depend on the step index only), so the device runs all steps
+back to back with no host synchronisation, where the reference synchronises
+three times per step.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Literal, Optional, Set
+
+import torch
+
+from . import _lib
+from .batch import DiffusableBatch
+from .score_model import ScoreModule
+from .sde import SDE
+
+
+class DiffusionSampler:
+    def __init__(self, score_model: ScoreModule, sample_batch_size: int, use_cache: bool = False,
+                 cache_kwargs: Optional[dict] = None, use_fresca: bool = False, fresca_low_scale: float = 1.0,
+                 fresca_high_scale: float = 1.5, fresca_cutoff_ratio: float = 0.5,
+                 fresca_cutoff_strategy: Literal["spatial", "energy"] = "energy",
+                 noise: Literal["torch", "philox"] = "torch", seed: int = 0) -> None:
+        self.score_model = score_model
+        self.noise_scheduler = score_model.noise_scheduler
+        self.sample_batch_size = sample_batch_size
+        self.n_channels = score_model.n_channels
+        self.max_len = score_model.max_len
+        self.use_cache = use_cache
+        if use_cache:
+            self.score_model.enable_caching(**(cache_kwargs or {}))
+        if use_fresca:
+            raise NotImplementedError("FreSca score filtering (fresca.py) is a 'next' row (SURVEY 8f), not built yet")
+        self.use_fresca = use_fresca
+        self.fresca_low_scale = fresca_low_scale
+        self.fresca_high_scale = fresca_high_scale
+        self.fresca_cutoff_ratio = fresca_cutoff_ratio
+        self.fresca_cutoff_strategy = fresca_cutoff_strategy
+        # "torch": z from torch.randn / randn_like on the same generators the reference uses
+        # (CPU for the prior, device for the steps: sde.py:85,157,238); "philox": drawn inside
+        # the step kernel, keyed (seed, batch, step).
+        assert noise in ("torch", "philox")
+        self.noise = noise
+        self.seed = seed
+        self.noise_chunk_steps = 8  # steps of torch noise generated per ffd_sample_steps call
+
+    # -- single step (API parity; the fused loop below does not go through here) --------
+    def reverse_diffusion_step(self, batch: DiffusableBatch, step: int = 0,
+                               recompute_tokens: Optional[Set[int]] = None) -> torch.Tensor:
+        """sampler.py:48-103."""
+        X, timesteps = batch.X, batch.timesteps
+        assert timesteps is not None and timesteps.size(0) == len(batch)
+        assert torch.min(timesteps) == torch.max(timesteps)
+        model = self.score_model
+        if self.use_cache and recompute_tokens is not None:
+            score, crf = model(batch, recompute_tokens=recompute_tokens, step=step, return_crf=True)
+            if model.cache is not None:
+                model.cache.update_crf(crf, timestep=timesteps[0].item())
+                model.cache.current_step = step
+        else:
+            score = model(batch)
+        out = self.noise_scheduler.step(model_output=score, timestep=timesteps[0].item(), sample=X)
+        return out.prev_sample
+
+    # -- the loop ---------------------------------------------------------------------------
+    def sample(self, num_samples: int, num_diffusion_steps: Optional[int] = None) -> torch.Tensor:
+        """sampler.py:105-215: returns a CPU fp32 tensor [floor(N/bs)*bs, L, C] (one batch of N if N < bs)."""
+        if num_diffusion_steps is not None:
+            self._num_diffusion_steps = num_diffusion_steps
+        model = self.score_model
+        model.eval()
+        n_steps = model.num_training_steps if num_diffusion_steps is None else num_diffusion_steps
+        self.noise_scheduler.set_timesteps(n_steps)
+        all_samples: List[torch.Tensor] = []
+        num_batches = max(1, num_samples // self.sample_batch_size)
+        global_step = 0
+        with torch.no_grad():
+            for batch_idx in range(num_batches):
+                batch_size = min(num_samples - batch_idx * self.sample_batch_size, self.sample_batch_size)
+                X = self.sample_prior(batch_size, batch_idx)
+                if self.use_cache and model.cache is not None and batch_idx == 0:
+                    model.cache.reset()
+                    global_step = 0
+                X = self.run_steps(X, global_step, batch_idx=batch_idx)
+                global_step += n_steps
+                all_samples.append(X.cpu())
+        return torch.cat(all_samples, dim=0)
+
+    def sample_prior(self, batch_size: int, batch_idx: int = 0) -> torch.Tensor:
+        """sampler.py:217-228."""
+        if not isinstance(self.noise_scheduler, SDE):
+            raise NotImplementedError("Scheduler not recognized.")
+        shape = (batch_size, self.max_len, self.n_channels)
+        if self.noise == "torch":
+            return self.noise_scheduler.prior_sampling(shape).to(device=self.score_model.device)
+        return self.noise_scheduler.prior_from_noise(None, shape, seed=self.seed,
+                                                     stream_id=self._stream_base(batch_idx))
+
+    def _stream_base(self, batch_idx: int) -> int:
+        # one Philox stream per (batch, step): stream 0 of a batch is its prior
+        return batch_idx * (1 << 32)
+
+    def step_tables(self, global_step0: int):
+        """Per-step host tables for one batch: SDE scalars, |recompute set|, CRF-store flag."""
+        sched = self.noise_scheduler
+        model = self.score_model
+        ts = [float(t) for t in sched.timesteps.tolist()]
+        n = len(ts)
+        coef = (_lib.StepCoef * n)(*[sched.step_coef(t) for t in ts])
+        n_own = (C.c_int32 * n)()
+        crf = (C.c_int32 * n)()
+        cache = model.cache if (self.use_cache and model.cache is not None) else None
+        for i in range(n):
+            if cache is None:
+                n_own[i] = -1
+            else:
+                gs = global_step0 + i
+                # x_tilde / event_intensity are ignored by the reference's schedule
+                n_own[i] = len(cache.determine_recompute_set(None, 0.1, gs))
+                crf[i] = 1 if cache.crf_stored_at(gs) else 0
+        return coef, n_own, crf
+
+    def run_steps(self, X: torch.Tensor, global_step0: int = 0, batch_idx: int = 0,
+                  noise: Optional[torch.Tensor] = None, step_begin: int = 0,
+                  step_end: Optional[int] = None, noise_step0: int = 0) -> torch.Tensor:
+        """Diffusion steps [step_begin, step_end) of one batch on the device.  ``noise``
+        ([k, B, L, C], holding steps noise_step0 .. noise_step0+k) injects the per-step z
+        (parity runs); otherwise z follows ``self.noise``."""
+        model = self.score_model
+        sched = self.noise_scheduler
+        dev = model.device
+        lib = _lib.load()
+        X = X.to(device=dev, dtype=torch.float32).contiguous().clone()
+        B = X.shape[0]
+        n = sched.timesteps.numel()
+        step_end = n if step_end is None else step_end
+        coef, n_own, crf_flags = self.step_tables(global_step0)
+        te_table = model.time_embedding(sched.timesteps)
+        a = _lib.SampleArgs()
+        a.fwd = model.forward_args(B)
+        cache = model.cache if (self.use_cache and model.cache is not None) else None
+        if cache is not None:
+            a.fwd.crf_out = _lib.ptr(cache._crf_store)
+        a.G = _lib.ptr(sched.G_device(dev))
+        a.time_emb_table = _lib.ptr(te_table)
+        a.coef_host = coef
+        a.n_own_host = n_own
+        a.store_crf_host = crf_flags
+        a.seed = self.seed
+        a.stream_base = self._stream_base(batch_idx) + 1
+        x_tmp = torch.empty_like(X)
+        a.x = _lib.ptr(X)
+        a.x_tmp = _lib.ptr(x_tmp)
+        st = _lib.stream_handle(dev)
+        if noise is not None:
+            noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+            assert tuple(noise.shape[1:]) == tuple(X.shape)
+            assert noise_step0 <= step_begin and step_end - noise_step0 <= noise.shape[0]
+            a.noise = _lib.ptr(noise)
+            a.noise_step0 = noise_step0
+            a.step_begin, a.step_end = step_begin, step_end
+            _lib.check(lib.ffd_sample_steps(a, st))
+        elif self.noise == "philox":
+            a.noise = None
+            a.step_begin, a.step_end = step_begin, step_end
+            _lib.check(lib.ffd_sample_steps(a, st))
+        else:
+            # torch noise: same generator stream as the reference's randn_like per step
+            chunk = max(1, self.noise_chunk_steps)
+            buf = torch.empty((chunk,) + tuple(X.shape), device=dev, dtype=torch.float32)
+            for s0 in range(step_begin, step_end, chunk):
+                s1 = min(step_end, s0 + chunk)
+                for j in range(s1 - s0):
+                    buf[j].normal_()
+                a.noise = _lib.ptr(buf)
+                a.noise_step0 = s0
+                a.step_begin, a.step_end = s0, s1
+                _lib.check(lib.ffd_sample_steps(a, st))
+        if cache is not None:
+            owner = model._kv_owner
+            for i in range(step_begin, step_end):
+                owner.account_forward(int(n_own[i]))
+                if crf_flags[i]:
+                    cache._crf_valid = True
+            cache.current_step = step_end - 1 if step_end > step_begin else cache.current_step
+        return X

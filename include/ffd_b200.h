@@ -1,0 +1,172 @@
+/*
+ * ffd_b200.h -- C ABI of the B200-native reverse-SDE sampling path.
+ *
+ * The reference (NoakLiu/FastFourierDiffusion) has no FFI: its hot path is a
+ * Python class API over stock ATen ops.  Each entry point below replaces the
+ * ATen op sequence of one reference function and is what a maintainer would
+ * bind (ctypes) underneath that function:
+ *
+ *   ffd_dft_matrix / ffd_dft_apply   src/fdiff/utils/fourier.py:8-52 (dft), :55-94 (idft)
+ *   ffd_posemb_renorm                src/fdiff/models/transformer.py:13-15,26-28 (Embedding max_norm)
+ *   ffd_time_embedding               src/fdiff/models/transformer.py:77-91 (GaussianFourierProjection)
+ *   ffd_score_forward                src/fdiff/models/score_models.py:79-194 (ScoreModule.forward,
+ *                                    _forward_with_cache) and
+ *                                    src/fdiff/models/cached_transformer.py:106-329 (all five branches),
+ *                                    src/fdiff/utils/caching.py:251-396 (KV store), :459-480 (CRF store)
+ *   ffd_sde_step                     src/fdiff/schedulers/sde.py:129-165 (VE), :215-246 (VP)
+ *   ffd_prior                        src/fdiff/schedulers/sde.py:79-87, :125-127
+ *   ffd_philox_normal                torch.randn / randn_like call sites sde.py:85,157,238
+ *   ffd_sample_steps                 src/fdiff/sampling/sampler.py:157-210 (the step loop)
+ *
+ * Conventions: plain pointers and sizes only; all pointers are DEVICE pointers
+ * unless the name ends in _host; the library never allocates, never frees and
+ * never synchronises -- every call only enqueues work on `stream`.  Return
+ * value 0 = ok, negative = error (ffd_last_error() gives the message for the
+ * calling thread).  Tensors are contiguous row-major fp32 in the reference's
+ * own layouts: X[B, L, C], weights as in ScoreModule.state_dict().
+ */
+#ifndef FFD_B200_H
+#define FFD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFD_OK 0
+#define FFD_ERR_ARG (-1)       /* bad argument (shape, null pointer, unsupported size) */
+#define FFD_ERR_CUDA (-2)      /* a CUDA call or launch failed */
+#define FFD_ERR_WORKSPACE (-3) /* workspace too small */
+#define FFD_ERR_UNSUPPORTED (-4)
+
+/* arithmetic of the score-model GEMMs */
+#define FFD_PREC_FP32 0 /* CUDA-core fp32 FMA everywhere */
+#define FFD_PREC_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate in TMEM; fp32 residual stream */
+
+#define FFD_SDE_VP 0
+#define FFD_SDE_VE 1
+
+/* score-model call mode (cached_transformer.py:106-329 picks the branch from n_own) */
+#define FFD_MODE_STOCK 0  /* cache is None: nn.TransformerEncoder */
+#define FFD_MODE_CACHED 1 /* cached layers: branch on the recompute set */
+
+typedef void* ffd_stream_t; /* cudaStream_t */
+
+typedef struct ffd_dims {
+  int32_t max_len;    /* L */
+  int32_t n_channels; /* C */
+  int32_t d_model;    /* d */
+  int32_t n_head;     /* H  (d % H == 0) */
+  int32_t d_ff;       /* F  (2048 in the reference: score_models.py:61-63) */
+  int32_t n_layers;   /* NL */
+} ffd_dims;
+
+/* Flat fp32 weight arena, element offsets (see ffd_weights_layout):
+ *   pos[L*d] emb_w[d*C] emb_b[d] unemb_w[C*d] unemb_b[C]
+ *   per layer: in_w[3d*d] in_b[3d] out_w[d*d] out_b[d] w1[F*d] b1[F] w2[d*F] b2[d]
+ *              n1w[d] n1b[d] n2w[d] n2b[d]
+ * (state_dict order of score_models.py:55-66; q/k/v are rows 0:d/d:2d/2d:3d of in_w,
+ *  cached_transformer.py:94-100).  `pos` must already be max-norm renormed. */
+int64_t ffd_weights_count(const ffd_dims* dims);
+int64_t ffd_layer_stride(const ffd_dims* dims);      /* floats per layer block */
+int64_t ffd_layer0_offset(const ffd_dims* dims);     /* offset of layer 0's in_w */
+
+/* bf16 tensor-core image of the arena (UMMA canonical K-major core-matrix tiles) */
+int64_t ffd_packed_bytes(const ffd_dims* dims);
+int ffd_pack_weights(const ffd_dims* dims, const float* weights, void* packed, ffd_stream_t stream);
+
+/* workspace for a batch of B samples */
+int64_t ffd_workspace_bytes(const ffd_dims* dims, int64_t B, int precision);
+
+const char* ffd_last_error(void);
+int ffd_version(void);
+/* kernels launched by this library in this process so far (bench.py's gpu_launches) */
+uint64_t ffd_launch_count(void);
+/* 1 if the tcgen05 path was compiled in and the current device is sm_100 */
+int ffd_has_tensor_path(void);
+
+/* ---- boundary transforms (fourier.py) ---------------------------------- */
+/* U[L,L] (inverse=0) or V=U^-1[L,L] (inverse=1), fp32, entries evaluated in fp64 */
+int ffd_dft_matrix(float* out, int L, int inverse, ffd_stream_t stream);
+/* y[b,k,c] = sum_n T[k,n] * (x[b,n,c]*scale[n,c] + shift[n,c]); scale/shift may be NULL
+ * (cmd/sample.py:107-113 de-standardise + idft fused) */
+int ffd_dft_apply(const float* T, const float* x, const float* scale, const float* shift, float* y,
+                  int64_t B, int L, int C, ffd_stream_t stream);
+
+/* ---- embeddings (transformer.py) ---------------------------------------- */
+int ffd_posemb_renorm(float* table, int L, int d, float max_norm, ffd_stream_t stream);
+/* out[i, :] = dense_w @ [sin(2*pi*t_i*W), cos(...)][:d] + dense_b   for i < n */
+int ffd_time_embedding(const float* t, int n, const float* W, const float* dense_w, const float* dense_b,
+                       int d, float* out, ffd_stream_t stream);
+
+/* ---- score model --------------------------------------------------------- */
+typedef struct ffd_forward_args {
+  ffd_dims dims;
+  int32_t precision;      /* FFD_PREC_* */
+  int32_t mode;           /* FFD_MODE_* */
+  int64_t B;
+  const float* weights;   /* fp32 arena */
+  const void* packed;     /* bf16 image (FFD_PREC_BF16 only) */
+  void* workspace;
+  int64_t workspace_bytes;
+  const float* X;         /* [B, L, C] */
+  const float* time_emb;  /* [d]  (one shared t per batch: sampler.py:59-60) */
+  /* cached mode */
+  int32_t n_own;          /* |S| */
+  const int32_t* own_mask;/* [L] 1 = token in S; may be NULL when n_own is 0 or L */
+  float* k_cache;         /* [NL, H, L, hd] sample-0 K  (caching.py:364-377) */
+  float* v_cache;
+  float* crf_out;         /* [NL, L, d] or NULL  (score_models.py:151,188) */
+  float* score;           /* [B, L, C] out; may be NULL if fused_step != NULL */
+} ffd_forward_args;
+
+int ffd_score_forward(const ffd_forward_args* a, ffd_stream_t stream);
+
+/* y = LayerNorm2(x + linear2(relu(linear1(x)))) of one encoder layer on M token rows
+ * (cached_transformer.py:130-132,325-327): the kernel that carries 86 % of the path's FLOPs.
+ * x, y: [M, d] fp32 (y may alias x); scratch: [M, d] fp32, used by FFD_PREC_FP32 only. */
+int ffd_ffn_ln(const ffd_dims* dims, int precision, const float* weights, const void* packed, int layer,
+               const float* x, float* y, float* scratch, int64_t M, ffd_stream_t stream);
+
+/* ---- SDE ------------------------------------------------------------------ */
+typedef struct ffd_step_coef {
+  int32_t kind;     /* FFD_SDE_* */
+  float c_x;        /* VP: fp32(-0.5*beta)   VE: unused */
+  float coef;       /* VP: fp32(sqrt(beta))  VE: fp32(sqrt_derivative) */
+  float dt;         /* step_size (sde.py:64) */
+  float sqrt_dt;    /* fp32 sqrt(dt) */
+} ffd_step_coef;
+
+/* x_out = x - drift*dt + sqrt_dt*(coef*G)*z, same rounding order as sde.py:228-244 / :143-163.
+ * z == NULL: z is drawn in-kernel, Philox-4x32-10 keyed (seed, stream_id), element index = counter. */
+int ffd_sde_step(const ffd_step_coef* c, const float* G, const float* x, const float* score, const float* z,
+                 uint64_t seed, uint64_t stream_id, float* x_out, int64_t B, int L, int C, ffd_stream_t stream);
+int ffd_prior(const float* G, const float* z, uint64_t seed, uint64_t stream_id, float scale, float* x_out,
+              int64_t B, int L, int C, ffd_stream_t stream);
+int ffd_philox_normal(uint64_t seed, uint64_t stream_id, float* out, int64_t n, ffd_stream_t stream);
+
+/* ---- the step loop -------------------------------------------------------- */
+typedef struct ffd_sample_args {
+  ffd_forward_args fwd;        /* X is updated in place; score may be NULL */
+  const float* G;              /* [L] */
+  const float* time_emb_table; /* [n_steps, d] */
+  const ffd_step_coef* coef_host;   /* [n_steps] HOST array */
+  const int32_t* n_own_host;   /* [n_steps] HOST array, -1 = no cache (stock) */
+  const int32_t* store_crf_host; /* [n_steps] HOST array: 1 = write crf_out this step (caching.py:474) */
+  const float* noise;          /* injected z for steps noise_step0.., [*, B, L, C]; NULL = Philox in-kernel */
+  int32_t noise_step0;         /* absolute step index of noise[0] */
+  uint64_t seed;
+  uint64_t stream_base;        /* Philox stream id of step 0 */
+  float* x;                    /* [B, L, C] state, in/out */
+  float* x_tmp;                /* [B, L, C] scratch */
+  int32_t step_begin, step_end;
+} ffd_sample_args;
+
+int ffd_sample_steps(const ffd_sample_args* a, ffd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFD_B200_H */

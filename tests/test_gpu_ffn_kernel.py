@@ -1,0 +1,63 @@
+"""The fused FFN + residual + LayerNorm kernel on its own (ffd_ffn_ln), fp32 CUDA-core path against
+a float64 restatement, tcgen05 bf16 path against the fp32 path, ragged row counts included."""
+
+import numpy as np
+import pytest
+import torch
+
+from ffd_testutil import ECG, TINY, build_seeded_model, build_tiny_model, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@torch.no_grad()
+def _ffn_ref(model, layer, x):
+    lyr = model.backbone.layers[layer]
+    w1, b1 = lyr.linear1.weight.double(), lyr.linear1.bias.double()
+    w2, b2 = lyr.linear2.weight.double(), lyr.linear2.bias.double()
+    xd = x.double()
+    h = torch.relu(xd @ w1.T + b1) @ w2.T + b2 + xd
+    return torch.nn.functional.layer_norm(h, (x.shape[1],), lyr.norm2.weight.double(), lyr.norm2.bias.double(), 1e-5)
+
+
+def _run(model, layer, x, precision):
+    from fastfourierdiffusion_b200 import _lib
+
+    model.set_precision(precision)
+    arena, packed = model.device_weights()
+    y = torch.empty_like(x)
+    scratch = torch.empty_like(x)
+    _lib.check(_lib.load().ffd_ffn_ln(model.dims, 1 if precision == "bf16" else 0, _lib.ptr(arena), _lib.ptr(packed),
+                                      layer, _lib.ptr(x), _lib.ptr(y), _lib.ptr(scratch), x.shape[0],
+                                      _lib.stream_handle()))
+    torch.cuda.synchronize()
+    return y
+
+
+@pytest.mark.parametrize("which", ["tiny", "ecg"])
+@pytest.mark.parametrize("M", [1, 100, 256, 300, 5000, 187 * 64])
+def test_ffn_ln_fp32_and_tensor_path(which, M):
+    from fastfourierdiffusion_b200 import _lib
+
+    model = build_tiny_model() if which == "tiny" else build_seeded_model(ECG, 42).to("cuda").eval()
+    d = model.d_model
+    layer = len(model.backbone.layers) - 1
+    torch.manual_seed(M)
+    x = torch.randn(M, d, device="cuda") * 1.3
+    want = _ffn_ref(model, layer, x)
+    got32 = _run(model, layer, x, "fp32")
+    assert rel(got32.cpu().numpy(), want.cpu().numpy()) < 5e-6
+    if not _lib.load().ffd_has_tensor_path() or not model._tc_ok():
+        pytest.skip("tensor path not available")
+    got16 = _run(model, layer, x, "bf16")
+    assert torch.isfinite(got16).all()
+    # bf16 operands (8-bit mantissa), fp32 accumulate, fp32 residual and LayerNorm
+    assert rel(got16.cpu().numpy(), want.cpu().numpy()) < 1e-2
+    err = (got16.double() - want).abs()
+    assert float(err.mean() / want.abs().mean()) < 2e-3
+    # in place
+    xin = x.clone()
+    arena, packed = model.device_weights()
+    _lib.check(_lib.load().ffd_ffn_ln(model.dims, 1, _lib.ptr(arena), _lib.ptr(packed), layer, _lib.ptr(xin),
+                                      _lib.ptr(xin), None, M, _lib.stream_handle()))
+    assert torch.equal(xin, got16)

@@ -1,0 +1,399 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the numpy oracle and the
+golden vectors produced by the unmodified reference.  Tolerances: fp32 arithmetic
+1e-5-class (stated per check), bf16 tensor-core arithmetic 1e-3-class on per-step states."""
+
+import numpy as np
+import pytest
+import torch
+
+from ffd_testutil import (ECG, TINY, build_seeded_model, build_tiny_model, load_golden, rel, state_dict_checksums,
+                          tiny_state_dict)
+from oracle import fdiff_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _precisions():
+    out = ["fp32"]
+    try:
+        from fastfourierdiffusion_b200 import _lib
+
+        if torch.cuda.is_available() and _lib.load().ffd_has_tensor_path():
+            out.append("bf16")
+    except Exception:
+        pass
+    return out
+
+
+PRECS = ["fp32", "bf16"]
+# per-precision tolerances: (score rel, one-step state rel, multi-step state rel)
+TOL = {"fp32": dict(score=2e-5, step=2e-6, traj=5e-4), "bf16": dict(score=3e-2, step=1e-3, traj=5e-2)}
+
+
+def _skip_unless(prec, model=None):
+    if prec not in _precisions():
+        pytest.skip("tensor path not available")
+    if prec == "bf16" and model is not None and not model._tc_ok():
+        pytest.skip("model shape not supported by the tcgen05 kernels")
+
+
+def test_native_library_is_loaded():
+    from fastfourierdiffusion_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.ffd_version() >= 1
+    maps = open("/proc/self/maps").read()
+    assert "libffd_b200.so" in maps
+
+
+# ---- boundary transforms -------------------------------------------------------------------
+@pytest.mark.parametrize("L", [24, 100, 101, 187, 251, 252, 365])
+def test_dft_idft_against_reference_vectors(L):
+    import fastfourierdiffusion_b200 as F
+
+    g = load_golden("fourier.npz")
+    x = torch.from_numpy(g[f"x_{L}"])
+    assert rel(F.dft(x).numpy(), g[f"dft_{L}"]) < 2e-6
+    assert rel(F.idft(x).numpy(), g[f"idft_{L}"]) < 2e-6
+    # reference tests/test_utils.py:36-51 (atol 1e-5)
+    xc = x.cuda()
+    assert torch.allclose(F.idft(F.dft(xc)), xc, atol=1e-5)
+    assert torch.allclose(F.dft(F.idft(xc)), xc, atol=1e-5)
+
+
+def test_dft_full_size_round_trip_and_parseval():
+    import fastfourierdiffusion_b200 as F
+
+    x = torch.randn(16384, 187, 1, device="cuda")
+    y = F.dft(x)
+    assert torch.allclose(F.idft(y), x, atol=2e-5)
+    # orthonormal up to the packing: energy = re0^2 + 2*sum(others)
+    w = torch.full((187,), 2.0, device="cuda")
+    w[0] = 1.0
+    e = (y[:, :, 0] ** 2 * w).sum(1)
+    assert torch.allclose(e, (x[:, :, 0] ** 2).sum(1), rtol=1e-4)
+
+
+def test_idft_fused_destandardise():
+    import fastfourierdiffusion_b200 as F
+
+    x = torch.randn(5, 24, 3, device="cuda")
+    std, mean = torch.rand(24, 3, device="cuda") + 0.5, torch.randn(24, 3, device="cuda")
+    assert torch.allclose(F.idft(x, std, mean), F.idft(x * std + mean), atol=1e-6)
+
+
+# ---- small ops ------------------------------------------------------------------------------------
+def test_sde_step_bit_exact_vs_oracle():
+    import fastfourierdiffusion_b200 as F
+
+    rng = np.random.default_rng(0)
+    for kind, kw in (("vp", {}), ("ve", {"sigma_max": 2.0})):
+        for L, C in ((187, 1), (24, 5)):
+            s = (F.VPScheduler if kind == "vp" else F.VEScheduler)(fourier_noise_scaling=True, **kw)
+            s.set_noise_scaling(L)
+            s.set_timesteps(50)
+            x, sc, z = (rng.standard_normal((7, L, C)).astype(np.float32) for _ in range(3))
+            t = float(s.timesteps[13])
+            got = s.step(torch.from_numpy(sc).cuda(), t, torch.from_numpy(x).cuda(),
+                         noise=torch.from_numpy(z).cuda()).prev_sample.cpu().numpy()
+            cfg = O.SDEConfig(kind=kind, fourier_noise_scaling=True, **kw)
+            want = O.sde_step(cfg, O.noise_scaling(L, True), sc, t, x, z, np.float32(s.step_size.item()))
+            assert np.array_equal(got, want)
+
+
+def test_prior_bit_exact_and_philox_stream():
+    import fastfourierdiffusion_b200 as F
+    from fastfourierdiffusion_b200 import _lib
+
+    s = F.VEScheduler(sigma_max=2.0, fourier_noise_scaling=True)
+    s.set_noise_scaling(24)
+    z = np.random.default_rng(1).standard_normal((3, 24, 2)).astype(np.float32)
+    got = s.prior_from_noise(torch.from_numpy(z)).cpu().numpy()
+    want = O.prior_sample(O.SDEConfig("ve", sigma_max=2.0, fourier_noise_scaling=True), O.noise_scaling(24, True), z)
+    assert np.array_equal(got, want)
+    out = torch.empty(10001, device="cuda")
+    _lib.check(_lib.load().ffd_philox_normal(1234567890123, 77, _lib.ptr(out), out.numel(), _lib.stream_handle()))
+    want = O.philox_normal(1234567890123, 77, 10001)
+    assert np.abs(out.cpu().numpy() - want).max() < 1e-3  # fp32 Box-Muller vs the fp64 restatement
+    big = torch.empty(1 << 22, device="cuda")
+    _lib.check(_lib.load().ffd_philox_normal(5, 1, _lib.ptr(big), big.numel(), _lib.stream_handle()))
+    assert abs(big.mean().item()) < 3e-3 and abs(big.std().item() - 1) < 3e-3
+
+
+def test_time_embedding_and_posemb_renorm():
+    m = build_tiny_model()
+    sd = tiny_state_dict()
+    ts = torch.linspace(1.0, 1e-5, 9)
+    got = m.time_embedding(ts).cpu().numpy()
+    for i, t in enumerate(ts.tolist()):
+        want = O.time_embedding(t, sd["time_encoder.W"], sd["time_encoder.dense.weight"],
+                                sd["time_encoder.dense.bias"], 12)
+        assert np.abs(got[i] - want).max() < 2e-5  # |2 pi t W| ~ 1e2 rad: sin/cos differ by ulps of the argument
+    m.device_weights()
+    g = load_golden("tiny_vp_freq_nocache.npz")
+    assert np.abs(m.pos_encoder.embedding.weight.detach().cpu().numpy() - g["pos_after"]).max() < 1e-6
+
+
+# ---- score model ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", PRECS)
+def test_tiny_model_level_sets(prec):
+    """Every branch of the cached layer incl. non-prefix sets, against the reference's outputs."""
+    import fastfourierdiffusion_b200 as F
+
+    m = build_tiny_model(precision=prec)
+    _skip_unless(prec, m)
+    g = load_golden("tiny_model_level.npz")
+    m.enable_caching(K=5, R=10)
+    m.cache.reset()
+    X = torch.from_numpy(g["X"]).cuda()
+    ts = torch.full((3,), float(g["t"]), dtype=torch.float32, device="cuda")
+    tol = TOL[prec]["score"]
+    for i, s in enumerate(g["sets"]):
+        S = {int(v) for v in str(s).split(",") if v != ""}
+        m.cache.current_step = i
+        score, crf = m(F.DiffusableBatch(X=X + 0.01 * i, timesteps=ts), recompute_tokens=S, step=i, return_crf=True)
+        assert rel(score.cpu().numpy(), g["scores"][i]) < tol, i
+        assert rel(crf.cpu().numpy(), g["crf"][i]) < tol, i
+    assert rel(m.cache.k_cache_tensor.cpu().numpy(), g["k_cache"]) < tol
+    assert rel(m.cache.v_cache_tensor.cpu().numpy(), g["v_cache"]) < tol
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_tiny_cold_cache_and_stock(prec):
+    import fastfourierdiffusion_b200 as F
+
+    m = build_tiny_model(precision=prec)
+    _skip_unless(prec, m)
+    g = load_golden("tiny_cold_cache.npz")
+    X = torch.from_numpy(g["X"]).cuda()
+    ts = torch.full((3,), float(g["t"]), dtype=torch.float32, device="cuda")
+    # stock path (no cache) vs the oracle
+    w = O.ModelWeights.from_state_dict(tiny_state_dict(), 2)
+    want = O.OracleScoreModel(w, 16, 2).forward(g["X"], float(g["t"]))
+    got = m(F.DiffusableBatch(X=X, timesteps=ts))
+    assert rel(got.cpu().numpy(), want) < TOL[prec]["score"]
+    m.enable_caching()
+    m.cache.reset()
+    score, crf = m(F.DiffusableBatch(X=X, timesteps=ts), recompute_tokens=set(), step=3, return_crf=True)
+    assert rel(score.cpu().numpy(), g["score"]) < TOL[prec]["score"]
+    assert rel(crf.cpu().numpy(), g["crf"]) < TOL[prec]["score"]
+    assert m.cache.k_cache_tensor is None  # nothing stored yet, as in the reference
+
+
+def _run_trace(model, g, use_cache, cache_kwargs, noise_steps=None):
+    import fastfourierdiffusion_b200 as F
+
+    n = int(g["n_steps"])
+    B = int(g["batch"])
+    sampler = F.DiffusionSampler(model, B, use_cache=use_cache, cache_kwargs=cache_kwargs)
+    model.noise_scheduler.set_timesteps(n)
+    assert np.array_equal(model.noise_scheduler.timesteps.numpy(), g["timesteps"])
+    outs, gs = [], 0
+    for b in range(int(g["n_batches"])):
+        X = model.noise_scheduler.prior_from_noise(torch.from_numpy(g["prior_z"][b]))
+        if use_cache and b == 0:
+            model.cache.reset()
+            gs = 0
+        X = sampler.run_steps(X, gs, batch_idx=b, noise=torch.from_numpy(g["step_z"][b]))
+        gs += n
+        outs.append(X.cpu().numpy())
+    return sampler, np.concatenate(outs)
+
+
+CASES = [("vp_freq", "vp", True, {}), ("ve_freq", "ve", True, {"sigma_max": 2.0}), ("vp_time", "vp", False, {})]
+
+
+@pytest.mark.parametrize("tag,kind,fns,skw", CASES)
+@pytest.mark.parametrize("cache", [False, True])
+@pytest.mark.parametrize("prec", PRECS)
+def test_tiny_sampler_trace(tag, kind, fns, skw, cache, prec):
+    """Whole sampling runs (two sampler batches with the cache on) with the reference's noise."""
+    m = build_tiny_model(kind, fns, precision=prec, **skw)
+    _skip_unless(prec, m)
+    g = load_golden(f"tiny_{tag}_{'cache' if cache else 'nocache'}.npz")
+    sampler, out = _run_trace(m, g, cache, dict(K=2, R=100))
+    assert rel(out, g["final"]) < TOL[prec]["traj"]
+    if cache:
+        c = m.cache
+        assert rel(c.k_cache_tensor.cpu().numpy(), g["k_cache"]) < TOL[prec]["traj"] * 4
+        assert rel(c.v_cache_tensor.cpu().numpy(), g["v_cache"]) < TOL[prec]["traj"] * 4
+        assert rel(c.crf_cache.cpu().numpy(), g["crf"]) < TOL[prec]["traj"] * 4
+        st = c.get_cache_stats()
+        ref = dict(zip(g["stats_keys"], g["stats_vals"]))
+        for k in ref:  # decisions and counters match exactly
+            assert st[k] == pytest.approx(ref[k], rel=1e-12), k
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_tiny_teacher_forced_steps(prec):
+    """Per-step parity (well conditioned): feed the reference's X_t and z_t, compare X_{t-1}."""
+    import fastfourierdiffusion_b200 as F
+
+    m = build_tiny_model(precision=prec)
+    _skip_unless(prec, m)
+    g = load_golden("tiny_vp_freq_cache.npz")
+    n = int(g["n_steps"])
+    sampler = F.DiffusionSampler(m, 3, use_cache=True, cache_kwargs=dict(K=2, R=100))
+    m.noise_scheduler.set_timesteps(n)
+    m.cache.reset()
+    keep = {int(k): i for i, k in enumerate(g["keep_steps"]) if k < n}
+    z = torch.from_numpy(g["step_z"][0])
+    X = m.noise_scheduler.prior_from_noise(torch.from_numpy(g["prior_z"][0]))
+    for i in range(n):
+        if i in keep:
+            X = torch.from_numpy(g["keep_X"][keep[i]]).cuda()
+        X = sampler.run_steps(X, 0, noise=z, step_begin=i, step_end=i + 1)
+        if i in keep:
+            assert rel(X.cpu().numpy(), g["keep_Xn"][keep[i]]) < TOL[prec]["step"], i
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_ecg_default_model_cached_trace(prec):
+    """Hydra-default model (d=72, 10 layers, 12 heads, L=187): full / pure-cache / mixed steps."""
+    import fastfourierdiffusion_b200 as F
+
+    g = load_golden("ecg_cache.npz")
+    m = build_seeded_model(ECG, 42, precision=prec)
+    _skip_unless(prec, m)
+    keys, cs = state_dict_checksums(m)
+    np.testing.assert_allclose(cs, g["ck_vals"], rtol=1e-12)
+    m = m.to("cuda").eval()
+    n = int(g["n_steps"])
+    sampler = F.DiffusionSampler(m, 2, use_cache=True, cache_kwargs=dict(K=5, R=100))
+    m.noise_scheduler.set_timesteps(n)
+    m.cache.reset()
+    z = torch.from_numpy(g["step_z"][0])
+    # teacher-forced at the kept steps (0 full, 1,2,50,99 pure, 100 mixed, 101,102 pure)
+    keep = {int(k): i for i, k in enumerate(g["keep_steps"])}
+    X = m.noise_scheduler.prior_from_noise(torch.from_numpy(g["prior_z"][0]))
+    assert np.array_equal(X.cpu().numpy(), g["keep_X"][0])
+    for i in range(n):
+        if i in keep:
+            X = torch.from_numpy(g["keep_X"][keep[i]]).cuda()
+        X = sampler.run_steps(X, 0, noise=z, step_begin=i, step_end=i + 1)
+        if i in keep:
+            assert rel(X.cpu().numpy(), g["keep_Xn"][keep[i]]) < TOL[prec]["step"], i
+    assert rel(X.cpu().numpy(), g["final"]) < TOL[prec]["step"]
+    c = m.cache
+    tol = 1e-4 if prec == "fp32" else 5e-2
+    assert rel(c.k_cache_tensor[[0, 9]].cpu().numpy(), g["k_cache"]) < tol
+    assert rel(c.v_cache_tensor[[0, 9]].cpu().numpy(), g["v_cache"]) < tol
+    assert rel(c.crf_cache[[0, 9]].cpu().numpy(), g["crf"]) < tol
+    st = c.get_cache_stats()
+    ref = dict(zip(g["stats_keys"], g["stats_vals"]))
+    for k in ref:
+        assert st[k] == pytest.approx(ref[k], rel=1e-12), k
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_ecg_default_model_scores_and_free_run(prec):
+    import fastfourierdiffusion_b200 as F
+
+    g = load_golden("ecg_nocache.npz")
+    m = build_seeded_model(ECG, 42, precision=prec)
+    _skip_unless(prec, m)
+    m = m.to("cuda").eval()
+    m.noise_scheduler.set_timesteps(int(g["n_steps"]))
+    for i, st in enumerate(g["keep_steps"]):
+        X = torch.from_numpy(g["keep_X"][i]).cuda()
+        ts = torch.full((2,), float(g["keep_t"][i]), dtype=torch.float32, device="cuda")
+        score = m(F.DiffusableBatch(X=X, timesteps=ts))
+        assert rel(score.cpu().numpy(), g["keep_score"][i]) < TOL[prec]["score"], st
+    sampler, out = _run_trace(m, g, False, None)
+    assert rel(out, g["final"]) < TOL[prec]["traj"]
+
+
+# ---- the public sampler API ---------------------------------------------------------------------------------
+def test_sampler_public_api_shapes_and_rng_parity():
+    """reference tests/test_sampling.py:21-40 (shape contract) + same torch RNG consumption as
+    the reference: CPU generator for the prior, device generator per step."""
+    import fastfourierdiffusion_b200 as F
+
+    for kind in ("vp", "ve"):
+        torch.manual_seed(42)
+        sched = (F.VPScheduler if kind == "vp" else F.VEScheduler)(fourier_noise_scaling=True)
+        m = F.ScoreModule(n_channels=3, max_len=50, noise_scheduler=sched, precision="fp32").cuda()
+        sched.set_noise_scaling(50)
+        sampler = F.DiffusionSampler(score_model=m, sample_batch_size=12)
+        samples = sampler.sample(num_samples=48, num_diffusion_steps=10)
+        assert samples.shape == (48, 50, 3) and samples.device.type == "cpu" and samples.dtype == torch.float32
+        assert torch.isfinite(samples).all()
+    # remainder dropped / single short batch (sampler.py:127,143-146)
+    assert sampler.sample(num_samples=30, num_diffusion_steps=3).shape == (24, 50, 3)
+    assert sampler.sample(num_samples=5, num_diffusion_steps=3).shape == (5, 50, 3)
+    # torch-noise mode reproduces a manual loop that draws randn_like per step
+    torch.manual_seed(7)
+    a = sampler.sample(12, 6)
+    torch.manual_seed(7)
+    sched.set_timesteps(6)
+    X = sched.prior_sampling((12, 50, 3))
+    for t in sched.timesteps:
+        ts = torch.full((12,), t.item(), dtype=torch.float32, device="cuda")
+        X = sampler.reverse_diffusion_step(F.DiffusableBatch(X=X, timesteps=ts))
+    assert torch.allclose(a, X.cpu(), rtol=1e-5, atol=1e-5)
+
+
+def test_philox_sampler_is_deterministic_and_batch_invariant():
+    import fastfourierdiffusion_b200 as F
+
+    m = build_tiny_model()
+    s = F.DiffusionSampler(m, 64, use_cache=True, cache_kwargs=dict(K=2, R=100), noise="philox", seed=3)
+    a = s.sample(64, 20)
+    b = s.sample(64, 20)
+    assert torch.equal(a, b)
+    assert torch.isfinite(a).all() and a.std() > 0
+    s2 = F.DiffusionSampler(m, 64, use_cache=True, cache_kwargs=dict(K=2, R=100), noise="philox", seed=4)
+    assert not torch.equal(a, s2.sample(64, 20))
+
+
+def test_error_conventions():
+    import fastfourierdiffusion_b200 as F
+
+    m = build_tiny_model()
+    ts = torch.full((3,), 0.5, device="cuda")
+    with pytest.raises(AssertionError):  # score_models.py:87-90
+        m(F.DiffusableBatch(X=torch.zeros(3, 15, 2, device="cuda"), timesteps=ts))
+    with pytest.raises(AssertionError):  # score_models.py:93
+        m(F.DiffusableBatch(X=torch.zeros(3, 16, 2, device="cuda"), timesteps=ts[:2]))
+    s = F.DiffusionSampler(m, 3)
+    with pytest.raises(AssertionError):  # sampler.py:59-60
+        s.reverse_diffusion_step(F.DiffusableBatch(X=torch.zeros(3, 16, 2, device="cuda"),
+                                                   timesteps=torch.tensor([0.1, 0.2, 0.3], device="cuda")))
+    with pytest.raises(IndexError):  # one step has no step size (sde.py:64)
+        s.sample(3, 1)
+    with pytest.raises(TypeError):  # README's random_probe_ratio is not a cache kwarg (caching.py:28-47)
+        F.DiffusionSampler(m, 3, use_cache=True, cache_kwargs={"random_probe_ratio": 0.1})
+
+
+# ---- full-size properties (BASELINE config 2 shapes) ---------------------------------------------------------
+@pytest.mark.parametrize("prec", PRECS)
+def test_full_batch_properties(prec):
+    """B=16384 x L=187: (1) no-cache outputs are per-sample functions (a permuted batch gives the
+    permuted result), (2) with the cache on every sample sees sample 0's K/V: replicating sample 0
+    through the batch reproduces sample 0's trajectory everywhere."""
+    import fastfourierdiffusion_b200 as F
+
+    m = build_seeded_model(ECG, 42, precision=prec)
+    _skip_unless(prec, m)
+    m = m.to("cuda").eval()
+    B = 16384
+    sched = m.noise_scheduler
+    sched.set_timesteps(1000)
+    torch.manual_seed(0)
+    X = sched.prior_from_noise(torch.randn(B, 187, 1))
+    ts = torch.full((B,), float(sched.timesteps[3]), device="cuda")
+    s1 = m(F.DiffusableBatch(X=X, timesteps=ts))
+    perm = torch.randperm(B, device="cuda")
+    s2 = m(F.DiffusableBatch(X=X[perm].contiguous(), timesteps=ts))
+    assert torch.isfinite(s1).all()
+    assert torch.allclose(s1[perm], s2, rtol=0, atol=0 if prec == "fp32" else 1e-6 * float(s1.abs().max()) + 1e-6)
+    small = m(F.DiffusableBatch(X=X[:4].contiguous(), timesteps=ts[:4]))
+    assert rel(s1[:4].cpu().numpy(), small.cpu().numpy()) < 1e-6
+    sampler = F.DiffusionSampler(m, B, use_cache=True, noise="philox")
+    m.cache.reset()
+    Xc = X[:1].expand(B, -1, -1).contiguous()
+    # three steps (full, pure, pure) with identical per-sample noise
+    nz = torch.randn(3, 1, 187, 1, device="cuda").expand(3, B, 187, 1).contiguous()
+    Xc = sampler.run_steps(Xc, 0, noise=nz, step_begin=0, step_end=3)
+    assert torch.isfinite(Xc).all()
+    assert rel(Xc.cpu().numpy(), Xc[:1].expand(B, -1, -1).cpu().numpy()) < (1e-6 if prec == "fp32" else 1e-5)
