@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- samples/sec of ECG frequency-domain reverse-SDE sampling with E2-CRF caching.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): ECG (L=187, C=1), Hydra-default transformer score model
+(d=72, 12 heads, 10 layers, FFN 2048, random init under seed 42), VP-SDE Euler-Maruyama on the
+1000-step time grid, E2-CRF cache with benchmark_cache.py's default kwargs (K=5, R=10), batch 16384
+per GPU, synthetic prior, Philox noise drawn in-kernel.
+
+A bench "step" is ONE reverse-diffusion step (score-model forward + SDE update) over the whole
+batch; the timed region runs schedule steps 0..K-1 (step 0 is the full-recompute step, step 500
+the refresh step, the rest pure-cache steps).  value = samples/sec for a 1000-step run
+= batch / (1000 * mean step time); with K = 1000 that is the exact wall time of a full run.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+N_DIFFUSION_STEPS = 1000
+ECG = dict(max_len=187, n_channels=1, d_model=72, num_layers=10, n_head=12)
+D_FF = 2048
+METRIC = "samples/sec (ECG freq-domain, 1000 steps, E2-CRF)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], hbm=d["hbm_gbs"], src="measured")
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+def flops_per_sample_step(n_own: int, L=187, C=1, d=72, F=D_FF, NL=10) -> float:
+    """NL*L*(8d^2 + 4Ld + 4dF) + 4LCd for a full step; the pure-cache step skips K/V (4d^2);
+    a mixed step recomputes K/V for n_own rows."""
+    if n_own < 0 or n_own == L or n_own > 0.8 * L:
+        return NL * L * (8 * d * d + 4 * L * d + 4 * d * F) + 4 * L * C * d
+    return NL * (L * (4 * d * d + 4 * L * d + 4 * d * F) + 4 * n_own * d * d) + 4 * L * C * d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) == 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def build_model(precision: str):
+    import torch
+
+    import fastfourierdiffusion_b200 as F
+
+    torch.manual_seed(42)
+    sched = F.VPScheduler(fourier_noise_scaling=True)
+    model = F.ScoreModule(noise_scheduler=sched, fourier_noise_scaling=True, precision=precision, **ECG)
+    sched.set_noise_scaling(ECG["max_len"])
+    return model
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_throughput(state_dict, budget_s: float, n_threads: int, steps=None, warmup=0):
+    """samples/sec of the torch-CPU port on a bounded sample; returns (value, sample description, ms/step)."""
+    import torch
+
+    from oracle.torch_port import TorchPort, time_cached_steps
+
+    torch.set_num_threads(n_threads)
+    port = TorchPort(state_dict, ECG["max_len"], ECG["n_channels"], ECG["n_head"], "vp", True)
+    # calibrate the batch so the run fits the budget
+    probe, _ = time_cached_steps(port, 4, [0, 1], N_DIFFUSION_STEPS)
+    per_sample = max(probe[1], 1e-4) / 4
+    if steps is None:  # cpu_baseline leg: full + 3 pure + refresh step, extrapolated over the schedule
+        b = int(max(4, min(64, budget_s / (6 * per_sample))))
+        port.k_cache = port.v_cache = None
+        t, _ = time_cached_steps(port, b, [0, 1, 2, 3, 500], N_DIFFUSION_STEPS)
+        pure = (t[1] + t[2] + t[3]) / 3
+        total = t[0] + t[500] + (N_DIFFUSION_STEPS - 2) * pure
+        return b / total, (f"batch {b}: schedule steps 0 (full), 1-3 (pure cache), 500 (refresh) timed, "
+                           f"1000-step run = full + refresh + 998 x mean pure step"), total / N_DIFFUSION_STEPS * 1e3
+    k = len(steps)
+    b = int(max(1, min(64, budget_s / ((k + warmup) * per_sample))))
+    port.k_cache = port.v_cache = None
+    if warmup:
+        time_cached_steps(port, b, list(range(1, 1 + warmup)), N_DIFFUSION_STEPS)
+        port.k_cache = port.v_cache = None
+    t, _ = time_cached_steps(port, b, steps, N_DIFFUSION_STEPS)
+    mean = sum(t.values()) / k
+    return b / (mean * N_DIFFUSION_STEPS), f"batch {b}: schedule steps 0..{k - 1} of the 1000-step grid", mean * 1e3
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path.  The upstream package is pure
+    Python and absent on the GPU box, so the torch-CPU port of oracle/ stands in (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    cores = os.cpu_count() or 1
+    model = build_model("fp32")
+    sd = {k: v for k, v in model.state_dict().items()}
+    value, sample, ms = cpu_port_throughput(sd, budget_s=150.0, n_threads=cores, steps=list(range(args.steps)),
+                                            warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ECG L=187 C=1, d=72 H=12 NL=10 F=2048, VP-SDE, E2-CRF K=5 R=10, CPU torch port",
+                   "torch_threads": torch.get_num_threads()},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        entry.build()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    import fastfourierdiffusion_b200 as F
+    from fastfourierdiffusion_b200 import _lib
+
+    lib = _lib.load()
+    dev = torch.device("cuda", local)
+    B = args.batch
+    K, W = args.steps, args.warmup
+    model = build_model(args.precision).to(dev).eval()
+    cpu_state = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    sampler = F.DiffusionSampler(model, B, use_cache=True, cache_kwargs={}, noise="philox", seed=42 + rank)
+    sched = model.noise_scheduler
+    sched.set_timesteps(N_DIFFUSION_STEPS)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident run -------------------------------------------------------------------
+    X0 = sampler.sample_prior(B)
+    model.cache.reset()
+    sampler.run_steps(X0, 0, step_begin=0, step_end=max(W, 1))  # warm-up: full step + pure steps
+    model.cache.reset()
+    barrier()
+    n0 = lib.ffd_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        X = sampler.run_steps(X0, 0, step_begin=0, step_end=K)
+        ev1.record()
+        barrier()
+    launches = int(lib.ffd_launch_count() - n0)
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    assert torch.isfinite(X).all()
+    ms_per_step = ms_total / K
+    value = world * B / (ms_per_step * 1e-3 * N_DIFFUSION_STEPS)
+
+    # ---- end to end through the public API with host buffers ------------------------------------
+    # DiffusionSampler.sample(): prior noise drawn on the host, copied to the device, K steps with
+    # per-step torch noise, final samples copied back to the host (sampler.py:105-215).
+    e2e_sampler = F.DiffusionSampler(model, B, use_cache=True, cache_kwargs={}, noise="torch")
+    Ke = min(K, args.e2e_steps) if args.e2e_steps > 0 else K
+    barrier()
+    t0 = time.perf_counter()
+    out = e2e_sampler.sample(B, num_diffusion_steps=Ke)
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    assert out.shape == (B, ECG["max_len"], ECG["n_channels"]) and out.device.type == "cpu"
+    e2e_value = world * B / (float(t_e2e.item()) / Ke * N_DIFFUSION_STEPS)
+    bytes_io = B * ECG["max_len"] * ECG["n_channels"] * 4
+
+    # ---- final gather of the samples over NCCL (the path's only collective) -------------
+    gather_ms = None
+    if world > 1:
+        parts = [torch.empty_like(X) for _ in range(world)]
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.all_gather(parts, X)
+        g1.record()
+        barrier()
+        gather_ms = g0.elapsed_time(g1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused FFN + LN), timed alone with CUDA events -------------
+    pk = peaks()
+    M = B * ECG["max_len"]
+    arena, packed = model.device_weights()
+    xbuf = torch.randn(M, ECG["d_model"], device=dev)
+    ybuf = torch.empty_like(xbuf)
+    scratch = torch.empty_like(xbuf) if args.precision == "fp32" else None
+    prec = 1 if args.precision == "bf16" else 0
+    st = _lib.stream_handle(dev)
+
+    def ffn():
+        _lib.check(lib.ffd_ffn_ln(model.dims, prec, _lib.ptr(arena), _lib.ptr(packed), 3, _lib.ptr(xbuf),
+                                  _lib.ptr(ybuf), _lib.ptr(scratch), M, st))
+
+    for _ in range(3):
+        ffn()
+    torch.cuda.synchronize()
+    reps = 10
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(reps):
+        ffn()
+    r1.record()
+    torch.cuda.synchronize()
+    ffn_ms = r0.elapsed_time(r1) / reps
+    ffn_flops = 4.0 * M * ECG["d_model"] * D_FF
+    achieved = ffn_flops / (ffn_ms * 1e-3) / 1e12
+    peak = pk["bf16"] if args.precision == "bf16" else 72.0  # fp32 FMA peak: 148 SMs x 128 lanes x 2 x 1.9 GHz
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ffn_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    # whole-step figure: algorithmic FLOPs of the timed steps over the measured time
+    n_own = [int(v) for v in sampler.step_tables(0)[1]][:K]
+    step_flops = sum(flops_per_sample_step(n) for n in n_own) * B
+    step_tflops = step_flops / (ms_total * 1e-3) / 1e12
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, sample, _ = cpu_port_throughput(cpu_state, budget_s=20.0, n_threads=cores)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
+        "config": {"workload": "ECG L=187 C=1 freq-domain, d=72 H=12 NL=10 F=2048 random init (seed 42), VP-SDE "
+                               "1000-step grid, E2-CRF K=5 R=10, Philox noise in-kernel",
+                   "batch_per_gpu": B, "global_batch": world * B, "schedule_steps_timed": f"0..{K - 1}",
+                   "value_definition": "global_batch / (1000 x mean step time over the timed steps)",
+                   "l2": "per-step activations [B*L, 72] fp32 = %.0f MB >> 126 MB L2 (inputs larger than L2)" % (
+                       M * 72 * 4 / 1e6),
+                   "parallelism": f"batch-sharded x{world}, no per-step collective",
+                   "final_gather_ms": gather_ms, "step_tflops_algorithmic": step_tflops,
+                   "step_frac_of_sustained_bf16_peak": step_tflops / pk["bf16_sustained"]},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": bytes_io / Ke,
+                "d2h_bytes_per_step": bytes_io / Ke, "steps": Ke,
+                "api": "DiffusionSampler.sample(): host prior noise -> H2D -> steps (torch device noise) -> D2H"},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "ffn_ln_tc_kernel<80>" if args.precision == "bf16" else "ffn_kernel+add_ln_kernel",
+                     "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": pk["src"] + " (burst)",
+                     "flops_per_launch": ffn_flops, "ms_per_launch": ffn_ms,
+                     "how": f"{reps} back-to-back launches over M={M} rows between CUDA events on the launch stream"},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16384, help="samples per GPU")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--e2e-steps", type=int, default=0, help="cap the steps of the e2e leg (0 = same as --steps)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -131,3 +131,23 @@ def test_schedule_closed_form():
     assert O.determine_recompute_set(150, 1, 150, 187) == [0, 1]
     assert O.determine_recompute_set(500, 0, 10, 187) == []
     assert O.determine_recompute_set(500, 200, 10, 187) == list(range(187))
+
+
+def test_torch_port_matches_reference_vectors(tiny_weights):
+    """The timed CPU baseline (oracle/torch_port.py) computes the same thing as the reference."""
+    import torch
+
+    from oracle.torch_port import TorchPort, recompute_set
+
+    g = load_golden("tiny_vp_freq_cache.npz")
+    port = TorchPort({k: torch.from_numpy(np.array(v)) for k, v in tiny_weights.items()}, 16, 2, 2, "vp", True)
+    ts = torch.from_numpy(g["timesteps"])
+    dt = ts[0] - ts[1]
+    X = port.G[None, :, None] * torch.from_numpy(g["prior_z"][0])
+    keep = {int(k): i for i, k in enumerate(g["keep_steps"])}
+    with torch.no_grad():
+        for i in range(int(g["n_steps"])):
+            if i in keep:
+                assert rel(X.numpy(), g["keep_X"][keep[i]]) < 2e-4, i
+            X = port.step(X, float(ts[i]), torch.from_numpy(g["step_z"][0][i]), dt, recompute_set(i, 2, 100, 16))
+    assert port.k_cache is not None and rel(X.numpy(), g["final"][:3]) < 5e-4
