@@ -39,6 +39,12 @@ static int run_layer(const ffd_forward_args& a, const Arena& ar, const Workspace
   float* vc = a.v_cache ? a.v_cache + (int64_t)layer * H * L * hd : nullptr;
   int rc;
   // branch: 0 = stock attention (all K/V own), 1 = pure cache, 2 = mixed
+  if (branch == 1 && a.precision == FFD_PREC_BF16 && tc_attn_supported(m)) {
+    // pure-cache layer on tensor cores: attention block and FFN block, two launches
+    if ((rc = tc_attn_cached(m, tc_attn_image(m, a.packed, layer), ws.kvimg, a.weights, layer, ws.h, ws.h, M, s)))
+      return rc;
+    return tc_ffn_ln(m, a.packed, a.weights, layer, ws.h, ws.h, M, s);
+  }
   const int nq = (branch == 1) ? d : 3 * d;  // pure cache projects Q only (cached_transformer.py:229)
   if ((rc = launch_linear(ws.h, d, w + ar.in_w, d, w + ar.in_b, ws.qkv, 3 * d, M, nq, d, 0, s))) return rc;
   if (branch == 2) {
@@ -85,6 +91,11 @@ static int forward_hidden(const ffd_forward_args& a, const Arena& ar, const Work
     return rc;
   int populate = 0;
   const int branch = pick_branch(a, &populate);
+  if (branch == 1 && a.precision == FFD_PREC_BF16 && tc_attn_supported(m)) {
+    // the fp32 cache is the source of truth (it may have been reset or refreshed since the last
+    // call); its bf16 operand images are 1.5 MB, so they are simply rebuilt every pure-cache step
+    if ((rc = tc_pack_kv(m, a.k_cache, a.v_cache, ws.kvimg, s))) return rc;
+  }
   for (int l = 0; l < m.n_layers; ++l) {
     if ((rc = run_layer(a, ar, ws, l, branch, s))) return rc;
     if (populate) {

@@ -83,6 +83,7 @@ struct Workspace {
   float* attn;  // [M, d] attention output (heads merged)
   float* qkv;   // [M, 3d]
   float* kvtmp; // [L, 2d] sample-0 K/V of a full step
+  void* kvimg;  // bf16 K/V operand images of the cache for the tcgen05 attention kernel
   int64_t bytes;
 };
 
@@ -101,6 +102,8 @@ static inline Workspace carve(const ffd_dims& m, int64_t B, void* base) {
   w.attn = take(M * d);
   w.qkv = take(M * 3 * d);
   w.kvtmp = take((int64_t)m.max_len * 2 * d);
+  // [NL, H] x (K image [NKV x 16] + V image [16 x NKV]) bf16, NKV = ceil16(L)
+  w.kvimg = take((int64_t)m.n_layers * m.n_head * ((m.max_len + 15) / 16 * 16) * 16);
   w.bytes = o;
   return w;
 }

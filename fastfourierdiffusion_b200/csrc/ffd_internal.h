@@ -40,4 +40,18 @@ bool tc_supported(const ffd_dims& m);
 int tc_ffn_ln(const ffd_dims& m, const void* packed, const float* weights, int layer, const float* x, float* y,
               int64_t M, cudaStream_t s);
 
+// ffd_tc_attn.cu (tcgen05 pure-cache attention block)
+bool tc_attn_supported(const ffd_dims& m);
+int64_t tc_attn_image_bytes(const ffd_dims& m);
+int64_t tc_kv_image_bytes(const ffd_dims& m);
+int64_t tc_ffn_image_bytes(const ffd_dims& m);
+const void* tc_attn_image(const ffd_dims& m, const void* packed, int layer);
+int tc_pack_attn(const ffd_dims& m, const float* weights, void* img_base, int64_t layer_stride_bytes,
+                 int64_t attn_off_bytes, cudaStream_t s);
+// bf16 K/V operand images of all layers/heads from the fp32 sample-0 cache [NL, H, L, hd]
+int tc_pack_kv(const ffd_dims& m, const float* kc, const float* vc, void* kvimg, cudaStream_t s);
+// y = LN1(x + out_proj(softmax(q K_c^T / sqrt(hd)) V_c)) for layer `layer`, rows [0, M); y may alias x
+int tc_attn_cached(const ffd_dims& m, const void* attn_img, const void* kvimg, const float* weights, int layer,
+                   const float* x, float* y, int64_t M, cudaStream_t s);
+
 }  // namespace ffd

@@ -2,148 +2,57 @@
 //   y = LN2(x + W2 relu(W1 x + b1) + b2)          cached_transformer.py:130-132,325-327
 // which carries 86 % of the sampling path's FLOPs.
 //
-// One persistent CTA per SM walks over pairs of 128-token tiles (A, B).  Per 128-wide slice j of
-// the F hidden units:
-//   GEMM1  H_s = X_s[128 x KP] . W1_j^T          tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM)
-//   epilogue warps: tcgen05.ld H_s -> relu -> bf16 -> shared (canonical K-major tile P_s)
-//   GEMM2  Y_s += P_s[128 x 128] . W2_j^T        accumulates in TMEM over all slices
-// so the [tokens x F] hidden activation never leaves the SM.  W1_j / W2_j are pre-packed (ffd_pack_weights)
-// as ready-to-use UMMA core-matrix images and arrive by 1-D bulk async copies (cp.async.bulk, mbarrier
-// completion) through a 2-stage ring each; both token tiles reuse every weight slice.  b1 rides in two spare
-// K columns of W1 (hi + lo bf16 parts against constant-1 columns of X), so the epilogue is relu + convert only.
-// The last epilogue adds b2 and the fp32 residual, applies LayerNorm per row (one thread owns a row) and
-// stores fp32.
+// One persistent CTA per SM walks over pairs of 128-token tiles (A, B).  The fp32 token tiles move between
+// HBM and shared memory as single bulk async copies (a tile of 128 rows is contiguous), so no thread touches
+// global memory.  Per 128-wide slice j of the F hidden units:
+//   GEMM1  H_s = X_s[128 x DP] . W1_j^T          tcgen05.mma kind::f16, A operand (bf16 X_s) read from TMEM,
+//                                                 B operand from shared memory, fp32 accumulate in TMEM
+//   epilogue warps: tcgen05.ld H_s -> relu -> bf16 -> tcgen05.st, in place over H_s
+//   GEMM2  Y_s += relu(H_s)[128 x 128] . W2_j^T   A operand again from TMEM; accumulates over all slices
+// so the [tokens x F] hidden activation never leaves the SM and only the weight slices stream through shared
+// memory (pre-packed UMMA core-matrix images, one bulk copy each, 3-stage rings, shared by both token tiles).
+// b1 rides in two spare K columns of W1 (hi + lo bf16 parts against constant-1 columns of X), so the slice
+// epilogue is relu + convert only.  The last epilogue adds b2 and the fp32 residual, applies LayerNorm per row
+// (one thread owns a row) into the tile buffer, which one bulk copy stores back.
 //
 // Warp roles (10 warps): 0 = bulk-copy producer, 1 = TMEM allocator + MMA issuer,
 // 2..5 = epilogue of tile A, 6..9 = epilogue of tile B.
-#include <cuda_bf16.h>
-
-#include "ffd_internal.h"
+#include "ffd_tc_ptx.cuh"
 
 namespace ffd {
 
 namespace tc {
 
-constexpr int TILE_M = 128;   // rows per token tile (UMMA M)
 constexpr int CHUNK = 128;    // hidden units per slice (UMMA N of GEMM1, K extent of GEMM2)
-constexpr int STAGES = 2;     // weight ring depth
+constexpr int STAGES = 3;     // weight ring depth
 constexpr int NUM_THREADS = 320;
 
-__host__ __device__ constexpr int dp_of(int d) { return (d + 2 + 15) / 16 * 16; }
-
-// ---- PTX wrappers --------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// 1-D bulk async copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
-               "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-
-// shared-memory matrix descriptor, K-major, no swizzle: 8x(16 B) core matrices; LBO = byte step
-// between the two K halves of one MMA (k-groups), SBO = byte step between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-// instruction descriptor: D fp32, A/B bf16, both K-major, M x N
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// arrive on an mbarrier once every MMA issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-#define FFD_TMEM_LD16(taddr, r)                                                                                     \
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),     \
-                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) \
-               : "r"(taddr))
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// relu + round-to-nearest bf16 of two floats in one instruction; lo -> low half (lower k index)
-__device__ __forceinline__ uint32_t relu_pack_bf16(uint32_t lo_bits, uint32_t hi_bits) {
-  uint32_t r;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi_bits)), "f"(__uint_as_float(lo_bits)));
-  return r;
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-
 // ---- shared-memory plan ------------------------------------------------------------------------
-template <int DP>
-struct Smem {
-  static constexpr int X_BYTES = TILE_M * DP * 2;     // bf16 [128 x DP]
-  static constexpr int P_BYTES = TILE_M * CHUNK * 2;  // bf16 [128 x 128]
-  static constexpr int W1_BYTES = CHUNK * DP * 2;     // bf16 [128 n x DP k]
-  static constexpr int W2_BYTES = DP * CHUNK * 2;     // bf16 [DP n x 128 k]
-  static constexpr int OFF_X = 0;
-  static constexpr int OFF_P = OFF_X + 2 * X_BYTES;
-  static constexpr int OFF_W1 = OFF_P + 2 * P_BYTES;
-  static constexpr int OFF_W2 = OFF_W1 + STAGES * W1_BYTES;
-  static constexpr int OFF_BAR = OFF_W2 + STAGES * W2_BYTES;
-  static constexpr int NUM_BARS = 4 * STAGES + 12;
-  static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
-  static constexpr int TOTAL = OFF_TMEM + 16;
+struct FfnSmem {
+  int x32, w1, w2, consts, bars, tmem, total;
+  int tile_bytes, w1_bytes, w2_bytes;
 };
+
+__host__ __device__ inline FfnSmem ffn_smem(int DP, int d) {
+  FfnSmem s;
+  int o = 0;
+  auto take = [&](int bytes) {
+    int r = o;
+    o += (bytes + 127) / 128 * 128;
+    return r;
+  };
+  s.tile_bytes = TILE_M * d * 4;  // fp32 [128 x d], row-contiguous exactly as in HBM
+  s.w1_bytes = CHUNK * DP * 2;    // bf16 [128 n x DP k]
+  s.w2_bytes = DP * CHUNK * 2;    // bf16 [DP n x 128 k]
+  s.x32 = take(2 * ((s.tile_bytes + 127) / 128 * 128));
+  s.w1 = take(STAGES * s.w1_bytes);
+  s.w2 = take(STAGES * s.w2_bytes);
+  s.consts = take(3 * DP * 4);    // b2, ln weight, ln bias
+  s.bars = take(32 * 8);
+  s.tmem = take(16);
+  s.total = o;
+  return s;
+}
 
 // ---- the kernel ------------------------------------------------------------------------------------
 template <int DP>
@@ -151,22 +60,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t* __restrict__ w1img,
                  const uint8_t* __restrict__ w2img, const float* __restrict__ b2, const float* __restrict__ lnw,
                  const float* __restrict__ lnb, int64_t M, int d, int n_chunks, int64_t n_pairs, float eps) {
-  using S = Smem<DP>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
-  uint64_t* w1_full = bars;                 // [STAGES]
-  uint64_t* w1_empty = bars + STAGES;       // [STAGES]
-  uint64_t* w2_full = bars + 2 * STAGES;    // [STAGES]
-  uint64_t* w2_empty = bars + 3 * STAGES;   // [STAGES]
-  uint64_t* x_full = bars + 4 * STAGES;     // [2] 128 arrivals (epilogue threads)
+  const FfnSmem sm = ffn_smem(DP, d);
+  const int tile_stride = (sm.tile_bytes + 127) / 128 * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);
+  uint64_t* w1_full = bars;                 // [STAGES] tx
+  uint64_t* w1_empty = bars + STAGES;       // [STAGES] commit
+  uint64_t* w2_full = bars + 2 * STAGES;    // [STAGES] tx
+  uint64_t* w2_empty = bars + 3 * STAGES;   // [STAGES] commit
+  uint64_t* t_full = bars + 4 * STAGES;     // [2] tx: fp32 tile landed in shared memory
+  uint64_t* t_empty = t_full + 2;           // [2] 1 arrival: tile buffer stored back and reusable
+  uint64_t* x_full = t_empty + 2;           // [2] 128 arrivals: bf16 X_s written to TMEM
   uint64_t* h_full = x_full + 2;            // [2] commit
   uint64_t* p_full = h_full + 2;            // [2] 128 arrivals
-  uint64_t* p_empty = p_full + 2;           // [2] commit
-  uint64_t* y_full = p_empty + 2;           // [2] commit
+  uint64_t* y_full = p_full + 2;            // [2] commit
   uint64_t* y_empty = y_full + 2;           // [2] 128 arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_TMEM);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sm.tmem);
+  float* consts = reinterpret_cast<float*>(smem + sm.consts);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int XC = (DP / 2 + 15) / 16 * 16;       // TMEM columns of the packed bf16 X operand
+  constexpr uint32_t COL_H = 0, COL_Y = 256, COL_X = 256 + DP;  // + 128 * s
+  static_assert(256 + DP + XC <= 384, "TMEM plan");
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -176,45 +91,61 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
       mbar_init(&w2_empty[i], 1);
     }
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&t_full[s], 1);
+      mbar_init(&t_empty[s], 1);
       mbar_init(&x_full[s], 128);
       mbar_init(&h_full[s], 1);
       mbar_init(&p_full[s], 128);
-      mbar_init(&p_empty[s], 1);
       mbar_init(&y_full[s], 1);
       mbar_init(&y_empty[s], 128);
     }
     fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 3 * DP; i += NUM_THREADS) {
+    const int w = i / DP, c = i % DP;
+    consts[i] = c < d ? (w == 0 ? b2[c] : w == 1 ? lnw[c] : lnb[c]) : 0.f;
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: H_A [0,128) H_B [128,256) Y_A [256,256+DP) Y_B [384,384+DP)
 
   if (warp == 0) {
     // ================= bulk-copy producer =================
     if (lane == 0) {
-      uint32_t k1 = 0, k2 = 0;  // loads issued into each ring
+      uint32_t k1 = 0, k2 = 0, npair = 0;
       auto load_w1 = [&](int j) {
         const uint32_t st = k1 % STAGES, u = k1 / STAGES;
         mbar_wait(&w1_empty[st], (u & 1) ^ 1);
-        mbar_expect_tx(&w1_full[st], S::W1_BYTES);
-        bulk_load(smem + S::OFF_W1 + st * S::W1_BYTES, w1img + (size_t)j * S::W1_BYTES, S::W1_BYTES, &w1_full[st]);
+        mbar_expect_tx(&w1_full[st], sm.w1_bytes);
+        bulk_load(smem + sm.w1 + st * sm.w1_bytes, w1img + (size_t)j * sm.w1_bytes, sm.w1_bytes, &w1_full[st]);
         ++k1;
       };
       auto load_w2 = [&](int j) {
         const uint32_t st = k2 % STAGES, u = k2 / STAGES;
         mbar_wait(&w2_empty[st], (u & 1) ^ 1);
-        mbar_expect_tx(&w2_full[st], S::W2_BYTES);
-        bulk_load(smem + S::OFF_W2 + st * S::W2_BYTES, w2img + (size_t)j * S::W2_BYTES, S::W2_BYTES, &w2_full[st]);
+        mbar_expect_tx(&w2_full[st], sm.w2_bytes);
+        bulk_load(smem + sm.w2 + st * sm.w2_bytes, w2img + (size_t)j * sm.w2_bytes, sm.w2_bytes, &w2_full[st]);
         ++k2;
       };
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        load_w1(0);  // same order as the MMA warp consumes: W1_0, then W1_{j+1}, W2_j
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++npair) {
+        for (int s = 0; s < 2; ++s) {
+          const int64_t row0 = (pair * 2 + s) * TILE_M;
+          const int64_t rows = M - row0 < TILE_M ? (M - row0 > 0 ? M - row0 : 0) : TILE_M;
+          mbar_wait(&t_empty[s], (npair & 1) ^ 1);
+          if (rows > 0) {
+            const uint32_t bytes = (uint32_t)(rows * d * 4);
+            mbar_expect_tx(&t_full[s], bytes);
+            bulk_load(smem + sm.x32 + s * tile_stride, x + row0 * d, bytes, &t_full[s]);
+          } else {
+            mbar_arrive(&t_full[s]);
+          }
+        }
+        load_w1(0);  // same order as the MMA warp consumes: W1_0, then W2_j, W1_{j+1}
         for (int j = 0; j < n_chunks; ++j) {
-          if (j + 1 < n_chunks) load_w1(j + 1);
           load_w2(j);
+          if (j + 1 < n_chunks) load_w1(j + 1);
         }
       }
     }
@@ -223,32 +154,27 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
     if (lane == 0) {
       constexpr uint32_t IDESC1 = make_idesc(TILE_M, CHUNK);
       constexpr uint32_t IDESC2 = make_idesc(TILE_M, DP);
-      constexpr uint32_t LBO_ROWS128 = 128 * 16;  // k-group stride of a 128-row operand
-      constexpr uint32_t LBO_ROWSDP = DP * 16;    // k-group stride of a DP-row operand
       uint32_t c1 = 0, c2 = 0;  // ring consumption counters
-      uint32_t nchunk = 0;      // chunks processed so far by this CTA (both tiles advance together)
+      uint32_t nchunk = 0;      // slices processed so far by this CTA (both tiles advance together)
       uint32_t npair = 0;
-      const uint32_t xa = smem_u32(smem + S::OFF_X), pa = smem_u32(smem + S::OFF_P);
       auto gemm1 = [&](int s, uint32_t w1addr) {
-        const uint32_t xs = xa + s * S::X_BYTES;
 #pragma unroll
         for (int k = 0; k < DP / 16; ++k)
-          umma(tmem_base + s * 128, make_desc(xs + k * 2 * LBO_ROWS128, LBO_ROWS128, 128),
-               make_desc(w1addr + k * 2 * LBO_ROWS128, LBO_ROWS128, 128), IDESC1, k > 0);
+          umma_ts(tmem_base + COL_H + s * 128, tmem_base + COL_X + s * 128 + k * 8,
+                  make_desc(w1addr + k * 2 * (CHUNK * 16), CHUNK * 16, 128), IDESC1, k > 0);
       };
       auto gemm2 = [&](int s, uint32_t w2addr, bool first) {
-        const uint32_t ps = pa + s * S::P_BYTES;
 #pragma unroll
         for (int k = 0; k < CHUNK / 16; ++k)
-          umma(tmem_base + 256 + s * 128, make_desc(ps + k * 2 * LBO_ROWS128, LBO_ROWS128, 128),
-               make_desc(w2addr + k * 2 * LBO_ROWSDP, LBO_ROWSDP, 128), IDESC2, (!first || k > 0) ? 1u : 0u);
+          umma_ts(tmem_base + COL_Y + s * 128, tmem_base + COL_H + s * 128 + k * 8,
+                  make_desc(w2addr + k * 2 * (DP * 16), DP * 16, 128), IDESC2, (!first || k > 0) ? 1u : 0u);
       };
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++npair) {
         // prologue: GEMM1 of slice 0 for both tiles
         {
           const uint32_t st = c1 % STAGES, u = c1 / STAGES;
           mbar_wait(&w1_full[st], u & 1);
-          const uint32_t w1addr = smem_u32(smem + S::OFF_W1 + st * S::W1_BYTES);
+          const uint32_t w1addr = smem_u32(smem + sm.w1 + st * sm.w1_bytes);
           for (int s = 0; s < 2; ++s) {
             mbar_wait(&x_full[s], npair & 1);
             tc_fence_after();
@@ -260,36 +186,32 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
         }
         for (int j = 0; j < n_chunks; ++j, ++nchunk) {
           const bool more = j + 1 < n_chunks;
+          const uint32_t st2 = c2 % STAGES;
+          mbar_wait(&w2_full[st2], (c2 / STAGES) & 1);
+          const uint32_t w2addr = smem_u32(smem + sm.w2 + st2 * sm.w2_bytes);
           uint32_t w1addr = 0, st1 = 0;
           if (more) {
             st1 = c1 % STAGES;
             mbar_wait(&w1_full[st1], (c1 / STAGES) & 1);
-            w1addr = smem_u32(smem + S::OFF_W1 + st1 * S::W1_BYTES);
+            w1addr = smem_u32(smem + sm.w1 + st1 * sm.w1_bytes);
           }
-          const uint32_t st2 = c2 % STAGES;
-          mbar_wait(&w2_full[st2], (c2 / STAGES) & 1);
-          const uint32_t w2addr = smem_u32(smem + S::OFF_W2 + st2 * S::W2_BYTES);
           for (int s = 0; s < 2; ++s) {
-            mbar_wait(&p_full[s], nchunk & 1);  // relu(H_s) of slice j is in P_s; H_s is free again
+            mbar_wait(&p_full[s], nchunk & 1);  // relu(H_s) of slice j sits (bf16) in the H_s columns
+            if (j == 0) mbar_wait(&y_empty[s], (npair & 1) ^ 1);  // previous pair's Y_s has been read out
             tc_fence_after();
+            gemm2(s, w2addr, j == 0);
+            if (!more) umma_commit(&y_full[s]);
             if (more) {
-              gemm1(s, w1addr);
+              gemm1(s, w1addr);  // issued after GEMM2: it overwrites the columns GEMM2 reads
               umma_commit(&h_full[s]);
             }
-            if (j == 0) {
-              mbar_wait(&y_empty[s], (npair & 1) ^ 1);  // previous pair's Y_s has been read out
-              tc_fence_after();
-            }
-            gemm2(s, w2addr, j == 0);
-            umma_commit(&p_empty[s]);
-            if (!more) umma_commit(&y_full[s]);
           }
+          umma_commit(&w2_empty[st2]);
+          ++c2;
           if (more) {
             umma_commit(&w1_empty[st1]);
             ++c1;
           }
-          umma_commit(&w2_empty[st2]);
-          ++c2;
         }
       }
     }
@@ -299,76 +221,66 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;      // row inside the 128-token tile
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    uint8_t* xs = smem + S::OFF_X + s * S::X_BYTES;
-    uint8_t* ps = smem + S::OFF_P + s * S::P_BYTES;
-    const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
+    float* tile = reinterpret_cast<float*>(smem + sm.x32 + s * tile_stride);
+    float4* myrow = reinterpret_cast<float4*>(tile + row * d);
+    const uint32_t hcol = tmem_base + lane_base + COL_H + s * 128;
     uint32_t nchunk = 0, npair = 0;
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++npair) {
-      const int64_t grow = (pair * 2 + s) * TILE_M + row;
-      const bool valid = grow < M;
-      // ---- stage X_s as bf16 K-major core matrices; columns d, d+1 are the constant-1 bias columns ----
+      const int64_t row0 = (pair * 2 + s) * TILE_M;
+      const bool valid = row0 + row < M;
+      // ---- X_s: fp32 row from the tile buffer -> bf16 pairs -> TMEM (A operand of GEMM1);
+      //      columns d, d+1 are the constant-1 bias columns ----
+      mbar_wait(&t_full[s], npair & 1);
       {
-        const float* xr = x + grow * d;
+        uint32_t xp[XC];
 #pragma unroll
-        for (int g = 0; g < DP / 8; ++g) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = g * 8 + e;
-            v[e] = (c < d) ? (valid ? __ldg(xr + c) : 0.f) : ((c == d || c == d + 1) ? 1.f : 0.f);
+        for (int i = 0; i < XC / 2; ++i) {  // 4 columns -> 2 packed words
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int c = i * 4;
+          if (c < d) {
+            if (valid) v = myrow[i];
+          } else {
+            if (c == d) v.x = 1.f, v.y = 1.f;
           }
-          uint4 q;
-          q.x = pack_bf16(v[0], v[1]);
-          q.y = pack_bf16(v[2], v[3]);
-          q.z = pack_bf16(v[4], v[5]);
-          q.w = pack_bf16(v[6], v[7]);
-          *reinterpret_cast<uint4*>(xs + row_off + g * (TILE_M * 16)) = q;
+          xp[2 * i] = pack_bf16(v.x, v.y);
+          xp[2 * i + 1] = pack_bf16(v.z, v.w);
         }
-        fence_proxy_async();
+#pragma unroll
+        for (int c0 = 0; c0 < XC; c0 += 16) FFD_TMEM_ST16(tmem_base + lane_base + COL_X + s * 128 + c0, (xp + c0));
+        tmem_st_wait();
+        tc_fence_before();
         mbar_arrive(&x_full[s]);
       }
-      // ---- per slice: H_s (TMEM fp32) -> relu -> bf16 -> P_s (shared) ----
+      // ---- per slice: H_s (TMEM fp32) -> relu -> bf16, written back in place ----
       for (int j = 0; j < n_chunks; ++j, ++nchunk) {
         mbar_wait(&h_full[s], nchunk & 1);
         tc_fence_after();
-        mbar_wait(&p_empty[s], (nchunk & 1) ^ 1);  // GEMM2 of the previous slice has finished reading P_s
 #pragma unroll
-        for (int c0 = 0; c0 < CHUNK; c0 += 32) {
-          uint32_t r0[16], r1[16];
-          FFD_TMEM_LD16(tmem_base + lane_base + s * 128 + c0, r0);
-          FFD_TMEM_LD16(tmem_base + lane_base + s * 128 + c0 + 16, r1);
+        for (int c0 = 0; c0 < CHUNK; c0 += 64) {
+          uint32_t r[64], pk[32];
+          FFD_TMEM_LD16(hcol + c0, r);
+          FFD_TMEM_LD16(hcol + c0 + 16, (r + 16));
+          FFD_TMEM_LD16(hcol + c0 + 32, (r + 32));
+          FFD_TMEM_LD16(hcol + c0 + 48, (r + 48));
           tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint4 q;
-            q.x = relu_pack_bf16(r0[g * 8 + 0], r0[g * 8 + 1]);
-            q.y = relu_pack_bf16(r0[g * 8 + 2], r0[g * 8 + 3]);
-            q.z = relu_pack_bf16(r0[g * 8 + 4], r0[g * 8 + 5]);
-            q.w = relu_pack_bf16(r0[g * 8 + 6], r0[g * 8 + 7]);
-            *reinterpret_cast<uint4*>(ps + row_off + (c0 / 8 + g) * (TILE_M * 16)) = q;
-          }
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint4 q;
-            q.x = relu_pack_bf16(r1[g * 8 + 0], r1[g * 8 + 1]);
-            q.y = relu_pack_bf16(r1[g * 8 + 2], r1[g * 8 + 3]);
-            q.z = relu_pack_bf16(r1[g * 8 + 4], r1[g * 8 + 5]);
-            q.w = relu_pack_bf16(r1[g * 8 + 6], r1[g * 8 + 7]);
-            *reinterpret_cast<uint4*>(ps + row_off + (c0 / 8 + 2 + g) * (TILE_M * 16)) = q;
-          }
+          for (int e = 0; e < 32; ++e) pk[e] = relu_pack_bf16(r[2 * e], r[2 * e + 1]);
+          // 64 fp32 columns [c0, c0+64) -> 32 packed columns [c0/2, c0/2+32): all already consumed
+          FFD_TMEM_ST16(hcol + (c0 >> 1), pk);
+          FFD_TMEM_ST16(hcol + (c0 >> 1) + 16, (pk + 16));
         }
+        tmem_st_wait();
         tc_fence_before();
-        fence_proxy_async();
         mbar_arrive(&p_full[s]);
       }
-      // ---- final: Y_s + b2 + residual -> LayerNorm -> global ----
+      // ---- final: Y_s + b2 + residual -> LayerNorm -> tile buffer -> one bulk store ----
       mbar_wait(&y_full[s], npair & 1);
       tc_fence_after();
       float v[DP];
 #pragma unroll
       for (int c0 = 0; c0 < DP; c0 += 16) {
         uint32_t r[16];
-        FFD_TMEM_LD16(tmem_base + lane_base + 256 + s * 128 + c0, r);
+        FFD_TMEM_LD16(tmem_base + lane_base + COL_Y + s * 128 + c0, r);
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[c0 + e] = __uint_as_float(r[e]);
@@ -376,13 +288,16 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
       tc_fence_before();
       mbar_arrive(&y_empty[s]);
       if (valid) {
-        const float* xr = x + grow * d;
         float sum = 0.f;
 #pragma unroll
-        for (int c = 0; c < DP; ++c) {
-          if (c < d) {
-            v[c] = v[c] + __ldg(b2 + c) + __ldg(xr + c);
-            sum += v[c];
+        for (int i = 0; i < DP / 4; ++i) {
+          if (i * 4 < d) {
+            const float4 xr = myrow[i];
+            v[4 * i + 0] += consts[4 * i + 0] + xr.x;
+            v[4 * i + 1] += consts[4 * i + 1] + xr.y;
+            v[4 * i + 2] += consts[4 * i + 2] + xr.z;
+            v[4 * i + 3] += consts[4 * i + 3] + xr.w;
+            sum += (v[4 * i] + v[4 * i + 1]) + (v[4 * i + 2] + v[4 * i + 3]);
           }
         }
         const float mean = sum / (float)d;
@@ -395,13 +310,31 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
           }
         }
         const float rstd = rsqrtf(var / (float)d + eps);
-        float* yr = y + grow * d;
 #pragma unroll
-        for (int c = 0; c < DP; ++c) {
-          if (c < d) yr[c] = (v[c] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
+        for (int i = 0; i < DP / 4; ++i) {
+          if (i * 4 < d) {
+            float4 o;
+            o.x = (v[4 * i + 0] - mean) * rstd * consts[DP + 4 * i + 0] + consts[2 * DP + 4 * i + 0];
+            o.y = (v[4 * i + 1] - mean) * rstd * consts[DP + 4 * i + 1] + consts[2 * DP + 4 * i + 1];
+            o.z = (v[4 * i + 2] - mean) * rstd * consts[DP + 4 * i + 2] + consts[2 * DP + 4 * i + 2];
+            o.w = (v[4 * i + 3] - mean) * rstd * consts[DP + 4 * i + 3] + consts[2 * DP + 4 * i + 3];
+            myrow[i] = o;
+          }
         }
       }
+      fence_proxy_async();
+      named_bar_sync(1 + s, 128);
+      if (quad == 0 && lane == 0) {
+        const int64_t rows = M - row0 < TILE_M ? (M - row0 > 0 ? M - row0 : 0) : TILE_M;
+        if (rows > 0) {
+          bulk_store(y + row0 * d, tile, (uint32_t)(rows * d * 4));
+          bulk_commit();
+          bulk_wait_read();
+        }
+        mbar_arrive(&t_empty[s]);
+      }
     }
+    if (quad == 0 && lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -448,16 +381,27 @@ __global__ void pack_ffn_kernel(const float* __restrict__ W1, const float* __res
 
 }  // namespace tc
 
-bool tc_supported(const ffd_dims& m) { return m.d_model + 2 <= 80 && m.d_ff % tc::CHUNK == 0 && m.d_ff >= tc::CHUNK; }
+bool tc_supported(const ffd_dims& m) {
+  return m.d_model + 2 <= 80 && m.d_model % 4 == 0 && m.d_ff % tc::CHUNK == 0 && m.d_ff >= tc::CHUNK;
+}
 
-static int64_t layer_image_bytes(const ffd_dims& m) {
+int64_t tc_ffn_image_bytes(const ffd_dims& m) {
   const int DP = tc::dp_of(m.d_model);
   return (int64_t)2 * (m.d_ff / tc::CHUNK) * tc::CHUNK * DP * 2;
+}
+
+// per layer: [FFN W1 images][FFN W2 images][WqP image][WoP image]
+static int64_t layer_image_bytes(const ffd_dims& m) {
+  return tc_ffn_image_bytes(m) + (tc_attn_supported(m) ? tc_attn_image_bytes(m) : 0);
 }
 
 int64_t tc_packed_bytes(const ffd_dims& m) {
   if (!tc_supported(m)) return 0;
   return layer_image_bytes(m) * m.n_layers;
+}
+
+const void* tc_attn_image(const ffd_dims& m, const void* packed, int layer) {
+  return (const uint8_t*)packed + (size_t)layer * layer_image_bytes(m) + tc_ffn_image_bytes(m);
 }
 
 int tc_pack_weights(const ffd_dims& m, const float* weights, void* packed, cudaStream_t s) {
@@ -470,27 +414,28 @@ int tc_pack_weights(const ffd_dims& m, const float* weights, void* packed, cudaS
                                             m.d_model, m.d_ff, DP);
     FFD_CHECK_LAUNCH("pack_ffn_kernel");
   }
+  if (tc_attn_supported(m)) return tc_pack_attn(m, weights, packed, layer_image_bytes(m), tc_ffn_image_bytes(m), s);
   return FFD_OK;
 }
 
 template <int DP>
 static int launch_ffn_tc(const ffd_dims& m, const uint8_t* img, const float* w, const Arena& ar, const float* x,
                          float* y, int64_t M, cudaStream_t s) {
-  using S = tc::Smem<DP>;
+  const tc::FfnSmem sm = tc::ffn_smem(DP, m.d_model);
   static int n_sm = 0;
   if (n_sm == 0) {
     int dev = 0;
     FFD_CHECK_CUDA(cudaGetDevice(&dev));
     FFD_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    FFD_CHECK_CUDA(cudaFuncSetAttribute(tc::ffn_ln_tc_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        S::TOTAL));
   }
+  FFD_CHECK_CUDA(cudaFuncSetAttribute(tc::ffn_ln_tc_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      sm.total));
   const int n_chunks = m.d_ff / tc::CHUNK;
   const int64_t n_pairs = (M + 2 * tc::TILE_M - 1) / (2 * tc::TILE_M);
   const unsigned grid = (unsigned)(n_pairs < n_sm ? n_pairs : n_sm);
   const uint8_t* w1img = img;
-  const uint8_t* w2img = img + (size_t)n_chunks * S::W1_BYTES;
-  tc::ffn_ln_tc_kernel<DP><<<grid, tc::NUM_THREADS, S::TOTAL, s>>>(x, y, w1img, w2img, w + ar.b2, w + ar.n2w,
+  const uint8_t* w2img = img + (size_t)n_chunks * sm.w1_bytes;
+  tc::ffn_ln_tc_kernel<DP><<<grid, tc::NUM_THREADS, sm.total, s>>>(x, y, w1img, w2img, w + ar.b2, w + ar.n2w,
                                                                     w + ar.n2b, M, m.d_model, n_chunks, n_pairs,
                                                                     1e-5f);
   FFD_CHECK_LAUNCH("ffn_ln_tc_kernel");

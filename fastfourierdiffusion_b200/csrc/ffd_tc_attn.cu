@@ -1,0 +1,543 @@
+// tcgen05 / TMEM kernel for the attention half of a PURE-CACHE encoder layer (998 of 1000 default steps):
+//   y = LN1(x + out_proj(softmax(q K_c^T / sqrt(hd)) V_c)),  q = x Wq^T + bq
+//   cached_transformer.py:228-258 (pure-cache K/V), :309-321 (attention, out-proj, residual, norm1)
+// K_c / V_c are the sample-0 cache rows shared by the whole batch (caching.py:326-328), so every token
+// row is independent and the work is a chain of GEMMs over 128-token tiles:
+//   Q[128 x 16H]   = X[128 x DP] . WqP^T          (heads padded to 16 columns; log2(e)/sqrt(hd) and bq folded in)
+//   S_h[128 x NKV] = Q_h[128 x 16] . K_h^T        one MMA per head, fp32 scores in TMEM
+//   P_h            = exp2(S_h - rowmax)           softmax warps: TMEM -> registers -> TMEM (bf16, in place over S_h)
+//   O_h[128 x 16]  = P_h . V_h                    A operand read from TMEM (tcgen05.mma with A in TMEM)
+//   OUT[128 x DP]  = concat_h(O_h / rowsum_h) . WoP^T   (bo folded in) -> + residual -> LayerNorm -> fp32 store
+// Nothing but x and y touches HBM; the [tokens x heads x L] score tensor the reference materialises twice
+// per layer (27.5 GB each at B=16384) lives in TMEM.
+//
+// Warp roles (10 warps): 0 = bulk-copy producer (Wq/Wo once, K/V head images through rings),
+// 1 = TMEM allocator + MMA issuer, 2..5 = softmax group 0 (even heads), 6..9 = softmax group 1 (odd heads).
+#include "ffd_tc_ptx.cuh"
+
+namespace ffd {
+namespace tc {
+
+constexpr int ATT_THREADS = 320;
+constexpr int KV_STAGES = 3;
+constexpr int HP = 16;  // padded head dim (UMMA K of the score MMA, N of the PV MMA)
+
+// TMEM columns
+constexpr uint32_t COL_S1 = 0;     // Q accumulators, then score buffer of group 1
+constexpr uint32_t COL_S0 = 192;   // score buffer of group 0
+constexpr uint32_t COL_O = 384;    // O accumulators: group g at COL_O + 16 g
+constexpr uint32_t COL_OUT = 416;  // out-proj accumulators [416, 416 + DP)
+
+struct AttnSmem {
+  int x, obf, qbf, wq, wo, kring, vring, bars, tmem, total;
+  int k_bytes, v_bytes, wq_bytes, wo_bytes;
+};
+
+__host__ __device__ inline AttnSmem attn_smem(int DP, int QN, int NKV) {
+  AttnSmem s;
+  int o = 0;
+  auto take = [&](int bytes) {
+    int r = o;
+    o += (bytes + 127) / 128 * 128;
+    return r;
+  };
+  s.k_bytes = NKV * HP * 2;
+  s.v_bytes = HP * NKV * 2;
+  s.wq_bytes = QN * DP * 2;
+  s.wo_bytes = DP * DP * 2;
+  s.x = take(TILE_M * DP * 2);
+  s.obf = take(TILE_M * DP * 2);
+  s.qbf = take(TILE_M * QN * 2);
+  s.wq = take(s.wq_bytes);
+  s.wo = take(s.wo_bytes);
+  s.kring = take(KV_STAGES * s.k_bytes);
+  s.vring = take(KV_STAGES * s.v_bytes);
+  s.bars = take(64 * 8);
+  s.tmem = take(16);
+  s.total = o;
+  return s;
+}
+
+#define FFD_TMEM_LD32(taddr, r)        \
+  do {                                 \
+    FFD_TMEM_LD16((taddr), (r));       \
+    FFD_TMEM_LD16((taddr) + 16, ((r) + 16)); \
+  } while (0)
+
+template <int DP>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t* __restrict__ wqimg,
+                      const uint8_t* __restrict__ woimg, const uint8_t* __restrict__ kvimg,
+                      const float* __restrict__ lnw, const float* __restrict__ lnb, int64_t M, int d, int H, int hd,
+                      int L, int NKV, int64_t n_tiles, float eps) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int QN = H * HP;
+  const AttnSmem sm = attn_smem(DP, QN, NKV);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);
+  uint64_t* k_full = bars;                       // [KV_STAGES] tx
+  uint64_t* k_empty = k_full + KV_STAGES;        // [KV_STAGES] commit
+  uint64_t* v_full = k_empty + KV_STAGES;        // [KV_STAGES] tx
+  uint64_t* v_empty = v_full + KV_STAGES;        // [KV_STAGES] commit
+  uint64_t* w_full = v_empty + KV_STAGES;        // [1] tx (Wq + Wo, once)
+  uint64_t* x_full = w_full + 1;                 // [1] 256 arrivals
+  uint64_t* q_full = x_full + 1;                 // [1] commit
+  uint64_t* qbf_full = q_full + 1;               // [1] 256 arrivals
+  uint64_t* s_full = qbf_full + 1;               // [2] commit
+  uint64_t* p_full = s_full + 2;                 // [2] 128 arrivals
+  uint64_t* o_full = p_full + 2;                 // [2] commit
+  uint64_t* o_empty = o_full + 2;                // [2] 128 arrivals
+  uint64_t* obf_full = o_empty + 2;              // [1] 256 arrivals
+  uint64_t* out_full = obf_full + 1;             // [1] commit
+  uint64_t* out_empty = out_full + 1;            // [1] 128 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sm.tmem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < KV_STAGES; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(w_full, 1);
+    mbar_init(x_full, 256);
+    mbar_init(q_full, 1);
+    mbar_init(qbf_full, 256);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 128);
+      mbar_init(&o_full[g], 1);
+      mbar_init(&o_empty[g], 128);
+    }
+    mbar_init(obf_full, 256);
+    mbar_init(out_full, 1);
+    mbar_init(out_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= producer =================
+    if (lane == 0) {
+      mbar_expect_tx(w_full, sm.wq_bytes + sm.wo_bytes);
+      bulk_load(smem + sm.wq, wqimg, sm.wq_bytes, w_full);
+      bulk_load(smem + sm.wo, woimg, sm.wo_bytes, w_full);
+      uint32_t nk = 0, nv = 0;
+      const size_t head_stride = (size_t)sm.k_bytes + sm.v_bytes;
+      auto load_k = [&](int h) {
+        const uint32_t st = nk % KV_STAGES, u = nk / KV_STAGES;
+        mbar_wait(&k_empty[st], (u & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], sm.k_bytes);
+        bulk_load(smem + sm.kring + st * sm.k_bytes, kvimg + h * head_stride, sm.k_bytes, &k_full[st]);
+        ++nk;
+      };
+      auto load_v = [&](int h) {
+        const uint32_t st = nv % KV_STAGES, u = nv / KV_STAGES;
+        mbar_wait(&v_empty[st], (u & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], sm.v_bytes);
+        bulk_load(smem + sm.vring + st * sm.v_bytes, kvimg + h * head_stride + sm.k_bytes, sm.v_bytes, &v_full[st]);
+        ++nv;
+      };
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // consumption order of the MMA warp: K0, K1, then per head h: V_h, K_{h+2}
+        load_k(0);
+        if (H > 1) load_k(1);
+        for (int h = 0; h < H; ++h) {
+          load_v(h);
+          if (h + 2 < H) load_k(h + 2);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc_q = make_idesc(TILE_M, QN);
+      const uint32_t idesc_s = make_idesc(TILE_M, NKV);
+      constexpr uint32_t IDESC_PV = make_idesc(TILE_M, HP);
+      constexpr uint32_t IDESC_OUT = make_idesc(TILE_M, DP);
+      constexpr uint32_t LBO128 = 128 * 16;
+      const uint32_t xs = smem_u32(smem + sm.x), obf = smem_u32(smem + sm.obf), qbf = smem_u32(smem + sm.qbf);
+      const uint32_t wq = smem_u32(smem + sm.wq), wo = smem_u32(smem + sm.wo);
+      uint32_t nk = 0, nv = 0, ntile = 0;
+      uint32_t nhead[2] = {0, 0};  // heads processed so far per softmax group
+      auto issue_s = [&](int h) {
+        const int g = h & 1;
+        const uint32_t st = nk % KV_STAGES;
+        mbar_wait(&k_full[st], (nk / KV_STAGES) & 1);
+        tc_fence_after();
+        umma(tmem_base + (g ? COL_S1 : COL_S0), make_desc(qbf + h * 2 * LBO128, LBO128, 128),
+             make_desc(smem_u32(smem + sm.kring + st * sm.k_bytes), NKV * 16, 128), idesc_s, 0);
+        umma_commit(&s_full[g]);
+        umma_commit(&k_empty[st]);
+        ++nk;
+      };
+      mbar_wait(w_full, 0);
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
+        // ---- Q projection ----
+        mbar_wait(x_full, ntile & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DP / 16; ++k)
+          umma(tmem_base + COL_S1, make_desc(xs + k * 2 * LBO128, LBO128, 128),
+               make_desc(wq + k * 2 * (QN * 16), QN * 16, 128), idesc_q, k > 0);
+        umma_commit(q_full);
+        mbar_wait(qbf_full, ntile & 1);  // Q is in shared memory as bf16; its TMEM columns are free
+        tc_fence_after();
+        issue_s(0);
+        if (H > 1) issue_s(1);
+        for (int h = 0; h < H; ++h) {
+          const int g = h & 1;
+          const uint32_t n = nhead[g]++;
+          mbar_wait(&p_full[g], n & 1);          // P_h (bf16) sits in the score buffer
+          mbar_wait(&o_empty[g], (n & 1) ^ 1);   // O of this group's previous head has been read out
+          const uint32_t st = nv % KV_STAGES;
+          mbar_wait(&v_full[st], (nv / KV_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t vaddr = smem_u32(smem + sm.vring + st * sm.v_bytes);
+          const uint32_t pcol = tmem_base + (g ? COL_S1 : COL_S0);
+          for (int k = 0; k < NKV / 16; ++k)
+            umma_ts(tmem_base + COL_O + 16 * g, pcol + k * 8, make_desc(vaddr + k * 2 * (HP * 16), HP * 16, 128),
+                    IDESC_PV, k > 0);
+          umma_commit(&o_full[g]);
+          umma_commit(&v_empty[st]);
+          ++nv;
+          if (h + 2 < H) issue_s(h + 2);  // after PV_h in issue order: it overwrites P_h's columns
+        }
+        // ---- output projection ----
+        mbar_wait(obf_full, ntile & 1);
+        mbar_wait(out_empty, (ntile & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DP / 16; ++k)
+          umma(tmem_base + COL_OUT, make_desc(obf + k * 2 * LBO128, LBO128, 128),
+               make_desc(wo + k * 2 * (DP * 16), DP * 16, 128), IDESC_OUT, k > 0);
+        umma_commit(out_full);
+      }
+    }
+  } else {
+    // ================= softmax / epilogue groups =================
+    const int g = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
+    uint8_t* xs = smem + sm.x;
+    uint8_t* obf = smem + sm.obf;
+    uint8_t* qbf = smem + sm.qbf;
+    const uint32_t scol = tmem_base + lane_base + (g ? COL_S1 : COL_S0);
+    const uint32_t ocol = tmem_base + lane_base + COL_O + 16 * g;
+    uint32_t ntile = 0, nhead = 0;
+    // constant columns of the out-proj A operand: d, d+1 = 1 (bias hi/lo), the rest of the padding = 0
+    if (g == 0) {
+      for (int c = d; c < DP; ++c)
+        *reinterpret_cast<__nv_bfloat16*>(obf + row_off + (c >> 3) * (TILE_M * 16) + (c & 7) * 2) =
+            __float2bfloat16_rn((c == d || c == d + 1) ? 1.f : 0.f);
+    }
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
+      const int64_t grow = tile * TILE_M + row;
+      const bool valid = grow < M;
+      // ---- stage this group's half of X (k-groups) as bf16 ----
+      {
+        const float* xr = x + grow * d;
+        constexpr int NG = DP / 8;
+        for (int kg = g * (NG / 2); kg < (g + 1) * (NG / 2); ++kg) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = kg * 8 + e;
+            v[e] = (c < d) ? (valid ? __ldg(xr + c) : 0.f) : ((c == d || c == d + 1) ? 1.f : 0.f);
+          }
+          uint4 q;
+          q.x = pack_bf16(v[0], v[1]);
+          q.y = pack_bf16(v[2], v[3]);
+          q.z = pack_bf16(v[4], v[5]);
+          q.w = pack_bf16(v[6], v[7]);
+          *reinterpret_cast<uint4*>(xs + row_off + kg * (TILE_M * 16)) = q;
+        }
+        fence_proxy_async();
+        mbar_arrive(x_full);
+      }
+      // ---- Q: TMEM fp32 -> bf16 A-operand tiles, heads of this group ----
+      mbar_wait(q_full, ntile & 1);
+      tc_fence_after();
+      for (int h = g; h < H; h += 2) {
+        uint32_t r[16];
+        FFD_TMEM_LD16(tmem_base + lane_base + COL_S1 + h * HP, r);
+        tmem_ld_wait();
+        uint4 q0, q1;
+        q0.x = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));
+        q0.y = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
+        q0.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));
+        q0.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
+        q1.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));
+        q1.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
+        q1.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13]));
+        q1.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
+        *reinterpret_cast<uint4*>(qbf + row_off + (2 * h) * (TILE_M * 16)) = q0;
+        *reinterpret_cast<uint4*>(qbf + row_off + (2 * h + 1) * (TILE_M * 16)) = q1;
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(qbf_full);
+      // ---- heads of this group ----
+      float inv_prev = 0.f;
+      int h_prev = -1;
+      auto collect_o = [&](int h, float inv, uint32_t n) {
+        mbar_wait(&o_full[g], n & 1);
+        tc_fence_after();
+        uint32_t r[16];
+        FFD_TMEM_LD16(ocol, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&o_empty[g]);
+#pragma unroll
+        for (int c = 0; c < HP; ++c) {
+          if (c < hd) {
+            const int col = h * hd + c;
+            *reinterpret_cast<__nv_bfloat16*>(obf + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                __float2bfloat16_rn(__uint_as_float(r[c]) * inv);
+          }
+        }
+      };
+      for (int h = g; h < H; h += 2, ++nhead) {
+        mbar_wait(&s_full[g], nhead & 1);
+        tc_fence_after();
+        // pass 1: row max over the L valid key columns
+        float mx = -INFINITY;
+        for (int c0 = 0; c0 < NKV; c0 += 16) {
+          uint32_t r[16];
+          FFD_TMEM_LD16(scol + c0, r);
+          tmem_ld_wait();
+          if (c0 + 16 > L) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (c0 + e >= L) r[e] = 0xff800000u;  // -inf
+          }
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) mx = max3(mx, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+        }
+        // pass 2: p = exp2(s - max) (scores are pre-scaled by log2(e)/sqrt(hd)); bf16 P written over S
+        float sum = 0.f;
+        for (int c0 = 0; c0 < NKV; c0 += 32) {
+          uint32_t r[32];
+          uint32_t pk[16];
+          const bool two = c0 + 16 < NKV;
+          FFD_TMEM_LD16(scol + c0, r);
+          if (two) FFD_TMEM_LD16(scol + c0 + 16, (r + 16));
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = (c0 + e < L) ? ex2_approx(__uint_as_float(r[e]) - mx) : 0.f;
+            float p1 = (c0 + e + 1 < L) ? ex2_approx(__uint_as_float(r[e + 1]) - mx) : 0.f;
+            if (!two && e >= 16) { p0 = 0.f; p1 = 0.f; }
+            sum += p0 + p1;
+            pk[e >> 1] = pack_bf16(p0, p1);
+          }
+          // 32 score columns -> 16 packed columns; a 16-column tail writes 8 (the upper 8 hold zeros
+          // and land on already-consumed score columns)
+          if (two) {
+            FFD_TMEM_ST16(scol + (c0 >> 1), pk);
+          } else {
+            uint32_t a[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) a[e] = e < 8 ? pk[e] : 0u;
+            FFD_TMEM_ST16(scol + (c0 >> 1), a);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[g]);
+        if (h_prev >= 0) collect_o(h_prev, inv_prev, nhead - 1);
+        h_prev = h;
+        inv_prev = 1.f / sum;
+      }
+      if (h_prev >= 0) collect_o(h_prev, inv_prev, nhead - 1);
+      fence_proxy_async();
+      mbar_arrive(obf_full);
+      // ---- out-proj result + residual -> LayerNorm -> global (groups alternate tiles) ----
+      if ((int)(ntile & 1) == g) {
+        mbar_wait(out_full, ntile & 1);
+        tc_fence_after();
+        float v[DP];
+#pragma unroll
+        for (int c0 = 0; c0 < DP; c0 += 16) {
+          uint32_t r[16];
+          FFD_TMEM_LD16(tmem_base + lane_base + COL_OUT + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[c0 + e] = __uint_as_float(r[e]);
+        }
+        tc_fence_before();
+        mbar_arrive(out_empty);
+        if (valid) {
+          const float* xr = x + grow * d;
+          float s1 = 0.f;
+#pragma unroll
+          for (int c = 0; c < DP; ++c)
+            if (c < d) {
+              v[c] += __ldg(xr + c);
+              s1 += v[c];
+            }
+          const float mean = s1 / (float)d;
+          float var = 0.f;
+#pragma unroll
+          for (int c = 0; c < DP; ++c)
+            if (c < d) {
+              const float t = v[c] - mean;
+              var = fmaf(t, t, var);
+            }
+          const float rstd = rsqrtf(var / (float)d + eps);
+          float* yr = y + grow * d;
+#pragma unroll
+          for (int c = 0; c < DP; ++c)
+            if (c < d) yr[c] = (v[c] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- packing ---------------------------------------------------------------------------------------
+// WqP [QN n x DP k]: row h*16+c = Wq[h*hd+c, :] * log2(e)/sqrt(hd), bias hi/lo in columns d, d+1.
+// WoP [DP n x DP k]: row n = Wo[n, :], bias hi/lo in columns d, d+1.   bf16 core-matrix order.
+__global__ void pack_attn_kernel(const float* __restrict__ in_w, const float* __restrict__ in_b,
+                                 const float* __restrict__ out_w, const float* __restrict__ out_b,
+                                 __nv_bfloat16* __restrict__ wq, __nv_bfloat16* __restrict__ wo, int d, int H, int DP) {
+  const int hd = d / H, QN = H * HP;
+  const float scale = 1.4426950408889634f / sqrtf((float)hd);
+  const int total = QN * DP + DP * DP;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const bool is_o = i >= QN * DP;
+    const int e = is_o ? i - QN * DP : i;
+    const int rows = is_o ? DP : QN;
+    const int kg = e / (rows * 8), rem = e % (rows * 8);
+    const int n = (rem / 64) * 8 + (rem % 64) / 8, k = kg * 8 + rem % 8;
+    float v = 0.f;
+    if (!is_o) {
+      const int h = n / HP, c = n % HP;
+      if (c < hd) {
+        const int r = h * hd + c;
+        const float b = in_b[r] * scale;
+        if (k < d) v = in_w[r * d + k] * scale;
+        else if (k == d) v = __bfloat162float(__float2bfloat16_rn(b));
+        else if (k == d + 1) v = b - __bfloat162float(__float2bfloat16_rn(b));
+      }
+    } else if (n < d) {
+      const float b = out_b[n];
+      if (k < d) v = out_w[n * d + k];
+      else if (k == d) v = __bfloat162float(__float2bfloat16_rn(b));
+      else if (k == d + 1) v = b - __bfloat162float(__float2bfloat16_rn(b));
+    }
+    (is_o ? wo : wq)[e] = __float2bfloat16_rn(v);
+  }
+}
+
+// K image per (layer, head): B operand [NKV n(key) x 16 k(dim)]; V image: B operand [16 n(dim) x NKV k(key)].
+__global__ void pack_kv_kernel(const float* __restrict__ kc, const float* __restrict__ vc,
+                               __nv_bfloat16* __restrict__ img, int n_lh, int L, int hd, int NKV) {
+  const int per = NKV * HP;  // elements per image
+  const int total = n_lh * 2 * per;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int lh = i / (2 * per);
+    const int r = i % (2 * per);
+    const bool is_v = r >= per;
+    const int e = is_v ? r - per : r;
+    const int rows = is_v ? HP : NKV;
+    const int kg = e / (rows * 8), rem = e % (rows * 8);
+    const int n = (rem / 64) * 8 + (rem % 64) / 8, k = kg * 8 + rem % 8;
+    const int key = is_v ? k : n, dim = is_v ? n : k;
+    float v = 0.f;
+    if (key < L && dim < hd) v = (is_v ? vc : kc)[((int64_t)lh * L + key) * hd + dim];
+    img[i] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace tc
+
+bool tc_attn_supported(const ffd_dims& m) {
+  const int hd = m.d_model / m.n_head;
+  return tc_supported(m) && hd <= tc::HP && m.n_head * tc::HP <= 192 && m.max_len <= 192;
+}
+
+static int nkv_of(const ffd_dims& m) { return (m.max_len + 15) / 16 * 16; }
+
+int64_t tc_attn_image_bytes(const ffd_dims& m) {
+  const int DP = tc::dp_of(m.d_model), QN = m.n_head * tc::HP;
+  return (int64_t)(QN * DP + DP * DP) * 2;
+}
+
+int64_t tc_kv_image_bytes(const ffd_dims& m) {
+  return (int64_t)m.n_layers * m.n_head * 2 * nkv_of(m) * tc::HP * 2;
+}
+
+int tc_pack_attn(const ffd_dims& m, const float* weights, void* img_base, int64_t layer_stride_bytes,
+                 int64_t attn_off_bytes, cudaStream_t s) {
+  const Arena ar = arena_of(m);
+  const int DP = tc::dp_of(m.d_model), QN = m.n_head * tc::HP;
+  for (int l = 0; l < m.n_layers; ++l) {
+    const float* w = weights + ar.layer0 + (int64_t)l * ar.layer_stride;
+    __nv_bfloat16* wq = (__nv_bfloat16*)((uint8_t*)img_base + l * layer_stride_bytes + attn_off_bytes);
+    tc::pack_attn_kernel<<<32, 256, 0, s>>>(w + ar.in_w, w + ar.in_b, w + ar.out_w, w + ar.out_b, wq,
+                                            wq + (size_t)QN * DP, m.d_model, m.n_head, DP);
+    FFD_CHECK_LAUNCH("pack_attn_kernel");
+  }
+  return FFD_OK;
+}
+
+int tc_pack_kv(const ffd_dims& m, const float* kc, const float* vc, void* kvimg, cudaStream_t s) {
+  const int n_lh = m.n_layers * m.n_head;
+  tc::pack_kv_kernel<<<148, 256, 0, s>>>(kc, vc, (__nv_bfloat16*)kvimg, n_lh, m.max_len, m.d_model / m.n_head,
+                                         nkv_of(m));
+  FFD_CHECK_LAUNCH("pack_kv_kernel");
+  return FFD_OK;
+}
+
+template <int DP>
+static int launch_attn(const ffd_dims& m, const uint8_t* wqimg, const uint8_t* kvimg_layer, const float* lnw,
+                       const float* lnb, const float* x, float* y, int64_t M, cudaStream_t s) {
+  static int n_sm = 0;
+  const int QN = m.n_head * tc::HP, NKV = nkv_of(m);
+  const tc::AttnSmem sm = tc::attn_smem(DP, QN, NKV);
+  if (n_sm == 0) {
+    int dev = 0;
+    FFD_CHECK_CUDA(cudaGetDevice(&dev));
+    FFD_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  FFD_CHECK_CUDA(cudaFuncSetAttribute(tc::attn_cached_tc_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      sm.total));
+  const int64_t n_tiles = (M + tc::TILE_M - 1) / tc::TILE_M;
+  const unsigned grid = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);
+  tc::attn_cached_tc_kernel<DP><<<grid, tc::ATT_THREADS, sm.total, s>>>(
+      x, y, wqimg, wqimg + (size_t)QN * DP * 2, kvimg_layer, lnw, lnb, M, m.d_model, m.n_head,
+      m.d_model / m.n_head, m.max_len, NKV, n_tiles, 1e-5f);
+  FFD_CHECK_LAUNCH("attn_cached_tc_kernel");
+  return FFD_OK;
+}
+
+int tc_attn_cached(const ffd_dims& m, const void* attn_img, const void* kvimg, const float* weights, int layer,
+                   const float* x, float* y, int64_t M, cudaStream_t s) {
+  const Arena ar = arena_of(m);
+  const float* w = weights + ar.layer0 + (int64_t)layer * ar.layer_stride;
+  const uint8_t* kvl = (const uint8_t*)kvimg + (size_t)layer * m.n_head * 2 * nkv_of(m) * tc::HP * 2;
+  const uint8_t* wq = (const uint8_t*)attn_img;
+  switch (tc::dp_of(m.d_model)) {
+    case 16: return launch_attn<16>(m, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
+    case 32: return launch_attn<32>(m, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
+    case 48: return launch_attn<48>(m, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
+    case 64: return launch_attn<64>(m, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
+    case 80: return launch_attn<80>(m, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
+  }
+  set_error("tensor-core attention: unsupported d_model %d", m.d_model);
+  return FFD_ERR_UNSUPPORTED;
+}
+
+}  // namespace ffd
