@@ -5,14 +5,18 @@
 // row is independent and the work is a chain of GEMMs over 128-token tiles:
 //   Q[128 x 16H]   = X[128 x DP] . WqP^T          (heads padded to 16 columns; log2(e)/sqrt(hd) and bq folded in)
 //   S_h[128 x NKV] = Q_h[128 x 16] . K_h^T        one MMA per head, fp32 scores in TMEM
-//   P_h            = exp2(S_h - rowmax)           softmax warps: TMEM -> registers -> TMEM (bf16, in place over S_h)
-//   O_h[128 x 16]  = P_h . V_h                    A operand read from TMEM (tcgen05.mma with A in TMEM)
-//   OUT[128 x DP]  = concat_h(O_h / rowsum_h) . WoP^T   (bo folded in) -> + residual -> LayerNorm -> fp32 store
-// Nothing but x and y touches HBM; the [tokens x heads x L] score tensor the reference materialises twice
-// per layer (27.5 GB each at B=16384) lives in TMEM.
+//   P_h            = exp2(S_h - rowmax)           softmax warps: TMEM -> registers -> TMEM (fp16 pairs, in place
+//                                                 over S_h; two exponentials per MUFU op via ex2.f16x2)
+//   O_h[128 x 16]  = P_h . [V_h | 1]              A operand read from TMEM; the extra ones column of the V image
+//                                                 makes the tensor core return the softmax row sum as well
+//   OUT[128 x DP]  = concat_h(O_h / rowsum_h) . WoP^T   (bo folded in) -> + residual -> LayerNorm
+// The fp32 token tile enters and leaves shared memory as one bulk async copy each way; the [tokens x heads x L]
+// score tensor the reference materialises twice per layer (27.5 GB each at B=16384) lives in TMEM.
 //
-// Warp roles (10 warps): 0 = bulk-copy producer (Wq/Wo once, K/V head images through rings),
+// Warp roles (10 warps): 0 = bulk-copy producer (Wq/Wo once, token tiles, K/V head images through rings),
 // 1 = TMEM allocator + MMA issuer, 2..5 = softmax group 0 (even heads), 6..9 = softmax group 1 (odd heads).
+#include <cuda_fp16.h>
+
 #include "ffd_tc_ptx.cuh"
 
 namespace ffd {
@@ -29,11 +33,11 @@ constexpr uint32_t COL_O = 384;    // O accumulators: group g at COL_O + 16 g
 constexpr uint32_t COL_OUT = 416;  // out-proj accumulators [416, 416 + DP)
 
 struct AttnSmem {
-  int x, obf, qbf, wq, wo, kring, vring, bars, tmem, total;
-  int k_bytes, v_bytes, wq_bytes, wo_bytes;
+  int x32, xo, qbf, wq, wo, kring, vring, consts, bars, tmem, total;
+  int tile_bytes, tile_stride, k_bytes, v_bytes, wq_bytes, wo_bytes;
 };
 
-__host__ __device__ inline AttnSmem attn_smem(int DP, int QN, int NKV) {
+__host__ __device__ inline AttnSmem attn_smem(int DP, int QN, int NKV, int d) {
   AttnSmem s;
   int o = 0;
   auto take = [&](int bytes) {
@@ -41,28 +45,25 @@ __host__ __device__ inline AttnSmem attn_smem(int DP, int QN, int NKV) {
     o += (bytes + 127) / 128 * 128;
     return r;
   };
+  s.tile_bytes = TILE_M * d * 4;
+  s.tile_stride = (s.tile_bytes + 127) / 128 * 128;
   s.k_bytes = NKV * HP * 2;
   s.v_bytes = HP * NKV * 2;
   s.wq_bytes = QN * DP * 2;
   s.wo_bytes = DP * DP * 2;
-  s.x = take(TILE_M * DP * 2);
-  s.obf = take(TILE_M * DP * 2);
+  s.x32 = take(2 * s.tile_stride);      // fp32 token tiles (ping-pong): input, residual, output staging
+  s.xo = take(TILE_M * DP * 2);         // bf16 A operand: X for the Q projection, later O for the out-proj
   s.qbf = take(TILE_M * QN * 2);
   s.wq = take(s.wq_bytes);
   s.wo = take(s.wo_bytes);
   s.kring = take(KV_STAGES * s.k_bytes);
   s.vring = take(KV_STAGES * s.v_bytes);
+  s.consts = take(2 * DP * 4);
   s.bars = take(64 * 8);
   s.tmem = take(16);
   s.total = o;
   return s;
 }
-
-#define FFD_TMEM_LD32(taddr, r)        \
-  do {                                 \
-    FFD_TMEM_LD16((taddr), (r));       \
-    FFD_TMEM_LD16((taddr) + 16, ((r) + 16)); \
-  } while (0)
 
 template <int DP>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -72,14 +73,16 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
                       int L, int NKV, int64_t n_tiles, float eps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int QN = H * HP;
-  const AttnSmem sm = attn_smem(DP, QN, NKV);
+  const AttnSmem sm = attn_smem(DP, QN, NKV, d);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);
   uint64_t* k_full = bars;                       // [KV_STAGES] tx
   uint64_t* k_empty = k_full + KV_STAGES;        // [KV_STAGES] commit
   uint64_t* v_full = k_empty + KV_STAGES;        // [KV_STAGES] tx
   uint64_t* v_empty = v_full + KV_STAGES;        // [KV_STAGES] commit
   uint64_t* w_full = v_empty + KV_STAGES;        // [1] tx (Wq + Wo, once)
-  uint64_t* x_full = w_full + 1;                 // [1] 256 arrivals
+  uint64_t* t_full = w_full + 1;                 // [2] tx: fp32 tile landed
+  uint64_t* t_empty = t_full + 2;                // [2] 1 arrival: tile buffer stored back
+  uint64_t* x_full = t_empty + 2;                // [1] 256 arrivals
   uint64_t* q_full = x_full + 1;                 // [1] commit
   uint64_t* qbf_full = q_full + 1;               // [1] 256 arrivals
   uint64_t* s_full = qbf_full + 1;               // [2] commit
@@ -90,6 +93,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
   uint64_t* out_full = obf_full + 1;             // [1] commit
   uint64_t* out_empty = out_full + 1;            // [1] 128 arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sm.tmem);
+  float* consts = reinterpret_cast<float*>(smem + sm.consts);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -101,6 +105,10 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(w_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&t_full[b], 1);
+      mbar_init(&t_empty[b], 1);
+    }
     mbar_init(x_full, 256);
     mbar_init(q_full, 1);
     mbar_init(qbf_full, 256);
@@ -115,6 +123,10 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     mbar_init(out_empty, 128);
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < 2 * DP; i += ATT_THREADS) {
+    const int w = i / DP, c = i % DP;
+    consts[i] = c < d ? (w == 0 ? lnw[c] : lnb[c]) : 0.f;
+  }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -127,7 +139,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       mbar_expect_tx(w_full, sm.wq_bytes + sm.wo_bytes);
       bulk_load(smem + sm.wq, wqimg, sm.wq_bytes, w_full);
       bulk_load(smem + sm.wo, woimg, sm.wo_bytes, w_full);
-      uint32_t nk = 0, nv = 0;
+      uint32_t nk = 0, nv = 0, ntile = 0;
       const size_t head_stride = (size_t)sm.k_bytes + sm.v_bytes;
       auto load_k = [&](int h) {
         const uint32_t st = nk % KV_STAGES, u = nk / KV_STAGES;
@@ -143,7 +155,13 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         bulk_load(smem + sm.vring + st * sm.v_bytes, kvimg + h * head_stride + sm.k_bytes, sm.v_bytes, &v_full[st]);
         ++nv;
       };
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
+        const uint32_t b = ntile & 1, u = ntile >> 1;
+        const int64_t row0 = tile * TILE_M;
+        const int64_t rows = M - row0 < TILE_M ? M - row0 : TILE_M;
+        mbar_wait(&t_empty[b], (u & 1) ^ 1);
+        mbar_expect_tx(&t_full[b], (uint32_t)(rows * d * 4));
+        bulk_load(smem + sm.x32 + b * sm.tile_stride, x + row0 * d, (uint32_t)(rows * d * 4), &t_full[b]);
         // consumption order of the MMA warp: K0, K1, then per head h: V_h, K_{h+2}
         load_k(0);
         if (H > 1) load_k(1);
@@ -158,10 +176,10 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     if (lane == 0) {
       const uint32_t idesc_q = make_idesc(TILE_M, QN);
       const uint32_t idesc_s = make_idesc(TILE_M, NKV);
-      constexpr uint32_t IDESC_PV = make_idesc(TILE_M, HP);
+      constexpr uint32_t IDESC_PV = make_idesc_f16(TILE_M, HP);
       constexpr uint32_t IDESC_OUT = make_idesc(TILE_M, DP);
       constexpr uint32_t LBO128 = 128 * 16;
-      const uint32_t xs = smem_u32(smem + sm.x), obf = smem_u32(smem + sm.obf), qbf = smem_u32(smem + sm.qbf);
+      const uint32_t xo = smem_u32(smem + sm.xo), qbf = smem_u32(smem + sm.qbf);
       const uint32_t wq = smem_u32(smem + sm.wq), wo = smem_u32(smem + sm.wo);
       uint32_t nk = 0, nv = 0, ntile = 0;
       uint32_t nhead[2] = {0, 0};  // heads processed so far per softmax group
@@ -183,7 +201,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < DP / 16; ++k)
-          umma(tmem_base + COL_S1, make_desc(xs + k * 2 * LBO128, LBO128, 128),
+          umma(tmem_base + COL_S1, make_desc(xo + k * 2 * LBO128, LBO128, 128),
                make_desc(wq + k * 2 * (QN * 16), QN * 16, 128), idesc_q, k > 0);
         umma_commit(q_full);
         mbar_wait(qbf_full, ntile & 1);  // Q is in shared memory as bf16; its TMEM columns are free
@@ -193,7 +211,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         for (int h = 0; h < H; ++h) {
           const int g = h & 1;
           const uint32_t n = nhead[g]++;
-          mbar_wait(&p_full[g], n & 1);          // P_h (bf16) sits in the score buffer
+          mbar_wait(&p_full[g], n & 1);          // P_h (fp16 pairs) sits in the score buffer
           mbar_wait(&o_empty[g], (n & 1) ^ 1);   // O of this group's previous head has been read out
           const uint32_t st = nv % KV_STAGES;
           mbar_wait(&v_full[st], (nv / KV_STAGES) & 1);
@@ -214,7 +232,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < DP / 16; ++k)
-          umma(tmem_base + COL_OUT, make_desc(obf + k * 2 * LBO128, LBO128, 128),
+          umma(tmem_base + COL_OUT, make_desc(xo + k * 2 * LBO128, LBO128, 128),
                make_desc(wo + k * 2 * (DP * 16), DP * 16, 128), IDESC_OUT, k > 0);
         umma_commit(out_full);
       }
@@ -226,38 +244,44 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
-    uint8_t* xs = smem + sm.x;
-    uint8_t* obf = smem + sm.obf;
+    uint8_t* xo = smem + sm.xo;
     uint8_t* qbf = smem + sm.qbf;
     const uint32_t scol = tmem_base + lane_base + (g ? COL_S1 : COL_S0);
     const uint32_t ocol = tmem_base + lane_base + COL_O + 16 * g;
     uint32_t ntile = 0, nhead = 0;
-    // constant columns of the out-proj A operand: d, d+1 = 1 (bias hi/lo), the rest of the padding = 0
-    if (g == 0) {
-      for (int c = d; c < DP; ++c)
-        *reinterpret_cast<__nv_bfloat16*>(obf + row_off + (c >> 3) * (TILE_M * 16) + (c & 7) * 2) =
-            __float2bfloat16_rn((c == d || c == d + 1) ? 1.f : 0.f);
-    }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
-      const int64_t grow = tile * TILE_M + row;
-      const bool valid = grow < M;
-      // ---- stage this group's half of X (k-groups) as bf16 ----
+      const int64_t row0 = tile * TILE_M;
+      const bool valid = row0 + row < M;
+      const uint32_t tb = ntile & 1;
+      float* tile32 = reinterpret_cast<float*>(smem + sm.x32 + tb * sm.tile_stride);
+      float4* myrow = reinterpret_cast<float4*>(tile32 + row * d);
+      // ---- stage this group's half of X (k-groups of 8 columns) as bf16; the buffer doubles as the
+      //      out-proj A operand, so the previous tile's out-proj must have finished reading it ----
+      mbar_wait(&t_full[tb], (ntile >> 1) & 1);
+      if (ntile > 0) mbar_wait(out_full, (ntile - 1) & 1);
       {
-        const float* xr = x + grow * d;
         constexpr int NG = DP / 8;
-        for (int kg = g * (NG / 2); kg < (g + 1) * (NG / 2); ++kg) {
-          float v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = kg * 8 + e;
-            v[e] = (c < d) ? (valid ? __ldg(xr + c) : 0.f) : ((c == d || c == d + 1) ? 1.f : 0.f);
+        for (int i = 0; i < NG / 2; ++i) {
+          const int kg = g * (NG / 2) + i;
+          const int c = kg * 8;
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
+          if (c < d) {
+            if (valid) a = myrow[2 * kg];
+          } else if (c == d) {
+            a.x = 1.f, a.y = 1.f;
+          }
+          if (c + 4 < d) {
+            if (valid) b4 = myrow[2 * kg + 1];
+          } else if (c + 4 == d) {
+            b4.x = 1.f, b4.y = 1.f;
           }
           uint4 q;
-          q.x = pack_bf16(v[0], v[1]);
-          q.y = pack_bf16(v[2], v[3]);
-          q.z = pack_bf16(v[4], v[5]);
-          q.w = pack_bf16(v[6], v[7]);
-          *reinterpret_cast<uint4*>(xs + row_off + kg * (TILE_M * 16)) = q;
+          q.x = pack_bf16(a.x, a.y);
+          q.y = pack_bf16(a.z, a.w);
+          q.z = pack_bf16(b4.x, b4.y);
+          q.w = pack_bf16(b4.z, b4.w);
+          *reinterpret_cast<uint4*>(xo + row_off + kg * (TILE_M * 16)) = q;
         }
         fence_proxy_async();
         mbar_arrive(x_full);
@@ -285,9 +309,8 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       fence_proxy_async();
       mbar_arrive(qbf_full);
       // ---- heads of this group ----
-      float inv_prev = 0.f;
       int h_prev = -1;
-      auto collect_o = [&](int h, float inv, uint32_t n) {
+      auto collect_o = [&](int h, uint32_t n) {
         mbar_wait(&o_full[g], n & 1);
         tc_fence_after();
         uint32_t r[16];
@@ -295,11 +318,16 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&o_empty[g]);
+        float rs = 1.f;
+#pragma unroll
+        for (int c = 0; c < HP; ++c)
+          if (c == hd) rs = __uint_as_float(r[c]);  // row sum from the ones column of the V image
+        const float inv = 1.f / rs;
 #pragma unroll
         for (int c = 0; c < HP; ++c) {
           if (c < hd) {
             const int col = h * hd + c;
-            *reinterpret_cast<__nv_bfloat16*>(obf + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+            *reinterpret_cast<__nv_bfloat16*>(xo + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
                 __float2bfloat16_rn(__uint_as_float(r[c]) * inv);
           }
         }
@@ -309,57 +337,45 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         tc_fence_after();
         // pass 1: row max over the L valid key columns
         float mx = -INFINITY;
-        for (int c0 = 0; c0 < NKV; c0 += 16) {
-          uint32_t r[16];
+        for (int c0 = 0; c0 < NKV; c0 += 32) {
+          uint32_t r[32];
           FFD_TMEM_LD16(scol + c0, r);
+          FFD_TMEM_LD16(scol + c0 + 16, (r + 16));
           tmem_ld_wait();
-          if (c0 + 16 > L) {
+          if (c0 + 32 > L) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
+            for (int e = 0; e < 32; ++e)
               if (c0 + e >= L) r[e] = 0xff800000u;  // -inf
           }
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) mx = max3(mx, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+          for (int e = 0; e < 32; e += 2) mx = max3(mx, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
         }
-        // pass 2: p = exp2(s - max) (scores are pre-scaled by log2(e)/sqrt(hd)); bf16 P written over S
-        float sum = 0.f;
+        // pass 2: p = exp2(s - max) as fp16 pairs (scores are pre-scaled by log2(e)/sqrt(hd)), written over S
         for (int c0 = 0; c0 < NKV; c0 += 32) {
-          uint32_t r[32];
-          uint32_t pk[16];
-          const bool two = c0 + 16 < NKV;
+          uint32_t r[32], pk[16];
           FFD_TMEM_LD16(scol + c0, r);
-          if (two) FFD_TMEM_LD16(scol + c0 + 16, (r + 16));
+          FFD_TMEM_LD16(scol + c0 + 16, (r + 16));
           tmem_ld_wait();
+          if (c0 + 32 > L) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float p0 = (c0 + e < L) ? ex2_approx(__uint_as_float(r[e]) - mx) : 0.f;
-            float p1 = (c0 + e + 1 < L) ? ex2_approx(__uint_as_float(r[e + 1]) - mx) : 0.f;
-            if (!two && e >= 16) { p0 = 0.f; p1 = 0.f; }
-            sum += p0 + p1;
-            pk[e >> 1] = pack_bf16(p0, p1);
+            for (int e = 0; e < 32; ++e)
+              if (c0 + e >= L) r[e] = 0xff800000u;  // exp2(-inf) = 0: padded keys carry no weight
           }
-          // 32 score columns -> 16 packed columns; a 16-column tail writes 8 (the upper 8 hold zeros
-          // and land on already-consumed score columns)
-          if (two) {
-            FFD_TMEM_ST16(scol + (c0 >> 1), pk);
-          } else {
-            uint32_t a[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) a[e] = e < 8 ? pk[e] : 0u;
-            FFD_TMEM_ST16(scol + (c0 >> 1), a);
-          }
+          for (int e = 0; e < 32; e += 2)
+            pk[e >> 1] = ex2_f16x2(__uint_as_float(r[e]) - mx, __uint_as_float(r[e + 1]) - mx);
+          FFD_TMEM_ST16(scol + (c0 >> 1), pk);  // packed columns [c0/2, c0/2+16) were all consumed already
         }
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[g]);
-        if (h_prev >= 0) collect_o(h_prev, inv_prev, nhead - 1);
+        if (h_prev >= 0) collect_o(h_prev, nhead - 1);
         h_prev = h;
-        inv_prev = 1.f / sum;
       }
-      if (h_prev >= 0) collect_o(h_prev, inv_prev, nhead - 1);
+      if (h_prev >= 0) collect_o(h_prev, nhead - 1);
       fence_proxy_async();
       mbar_arrive(obf_full);
-      // ---- out-proj result + residual -> LayerNorm -> global (groups alternate tiles) ----
+      // ---- out-proj result + residual -> LayerNorm -> tile buffer -> bulk store (groups alternate tiles) ----
       if ((int)(ntile & 1) == g) {
         mbar_wait(out_full, ntile & 1);
         tc_fence_after();
@@ -375,13 +391,16 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         tc_fence_before();
         mbar_arrive(out_empty);
         if (valid) {
-          const float* xr = x + grow * d;
           float s1 = 0.f;
 #pragma unroll
-          for (int c = 0; c < DP; ++c)
-            if (c < d) {
-              v[c] += __ldg(xr + c);
-              s1 += v[c];
+          for (int i = 0; i < DP / 4; ++i)
+            if (i * 4 < d) {
+              const float4 xr = myrow[i];
+              v[4 * i + 0] += xr.x;
+              v[4 * i + 1] += xr.y;
+              v[4 * i + 2] += xr.z;
+              v[4 * i + 3] += xr.w;
+              s1 += (v[4 * i] + v[4 * i + 1]) + (v[4 * i + 2] + v[4 * i + 3]);
             }
           const float mean = s1 / (float)d;
           float var = 0.f;
@@ -392,13 +411,29 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
               var = fmaf(t, t, var);
             }
           const float rstd = rsqrtf(var / (float)d + eps);
-          float* yr = y + grow * d;
 #pragma unroll
-          for (int c = 0; c < DP; ++c)
-            if (c < d) yr[c] = (v[c] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
+          for (int i = 0; i < DP / 4; ++i)
+            if (i * 4 < d) {
+              float4 o;
+              o.x = (v[4 * i + 0] - mean) * rstd * consts[4 * i + 0] + consts[DP + 4 * i + 0];
+              o.y = (v[4 * i + 1] - mean) * rstd * consts[4 * i + 1] + consts[DP + 4 * i + 1];
+              o.z = (v[4 * i + 2] - mean) * rstd * consts[4 * i + 2] + consts[DP + 4 * i + 2];
+              o.w = (v[4 * i + 3] - mean) * rstd * consts[4 * i + 3] + consts[DP + 4 * i + 3];
+              myrow[i] = o;
+            }
+        }
+        fence_proxy_async();
+        named_bar_sync(1 + g, 128);
+        if (quad == 0 && lane == 0) {
+          const int64_t rows = M - row0 < TILE_M ? M - row0 : TILE_M;
+          bulk_store(y + row0 * d, tile32, (uint32_t)(rows * d * 4));
+          bulk_commit();
+          bulk_wait_read();
+          mbar_arrive(&t_empty[tb]);
         }
       }
     }
+    if (quad == 0 && lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -441,9 +476,11 @@ __global__ void pack_attn_kernel(const float* __restrict__ in_w, const float* __
   }
 }
 
-// K image per (layer, head): B operand [NKV n(key) x 16 k(dim)]; V image: B operand [16 n(dim) x NKV k(key)].
+// K image per (layer, head): B operand [NKV n(key) x 16 k(dim)], bf16.  V image: B operand
+// [16 n(dim) x NKV k(key)], fp16 (P is fp16), with row n = hd set to 1 for the valid keys so that
+// column hd of O = P . V^T is the softmax row sum.
 __global__ void pack_kv_kernel(const float* __restrict__ kc, const float* __restrict__ vc,
-                               __nv_bfloat16* __restrict__ img, int n_lh, int L, int hd, int NKV) {
+                               uint16_t* __restrict__ img, int n_lh, int L, int hd, int NKV) {
   const int per = NKV * HP;  // elements per image
   const int total = n_lh * 2 * per;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -457,7 +494,8 @@ __global__ void pack_kv_kernel(const float* __restrict__ kc, const float* __rest
     const int key = is_v ? k : n, dim = is_v ? n : k;
     float v = 0.f;
     if (key < L && dim < hd) v = (is_v ? vc : kc)[((int64_t)lh * L + key) * hd + dim];
-    img[i] = __float2bfloat16_rn(v);
+    if (is_v && key < L && dim == hd) v = 1.f;
+    img[i] = is_v ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
   }
 }
 
@@ -465,10 +503,10 @@ __global__ void pack_kv_kernel(const float* __restrict__ kc, const float* __rest
 
 bool tc_attn_supported(const ffd_dims& m) {
   const int hd = m.d_model / m.n_head;
-  return tc_supported(m) && hd <= tc::HP && m.n_head * tc::HP <= 192 && m.max_len <= 192;
+  return tc_supported(m) && hd < tc::HP && m.n_head * tc::HP <= 192 && m.max_len <= 192;
 }
 
-static int nkv_of(const ffd_dims& m) { return (m.max_len + 15) / 16 * 16; }
+static int nkv_of(const ffd_dims& m) { return (m.max_len + 31) / 32 * 32; }
 
 int64_t tc_attn_image_bytes(const ffd_dims& m) {
   const int DP = tc::dp_of(m.d_model), QN = m.n_head * tc::HP;
@@ -495,7 +533,7 @@ int tc_pack_attn(const ffd_dims& m, const float* weights, void* img_base, int64_
 
 int tc_pack_kv(const ffd_dims& m, const float* kc, const float* vc, void* kvimg, cudaStream_t s) {
   const int n_lh = m.n_layers * m.n_head;
-  tc::pack_kv_kernel<<<148, 256, 0, s>>>(kc, vc, (__nv_bfloat16*)kvimg, n_lh, m.max_len, m.d_model / m.n_head,
+  tc::pack_kv_kernel<<<148, 256, 0, s>>>(kc, vc, (uint16_t*)kvimg, n_lh, m.max_len, m.d_model / m.n_head,
                                          nkv_of(m));
   FFD_CHECK_LAUNCH("pack_kv_kernel");
   return FFD_OK;
@@ -506,7 +544,7 @@ static int launch_attn(const ffd_dims& m, const uint8_t* wqimg, const uint8_t* k
                        const float* lnb, const float* x, float* y, int64_t M, cudaStream_t s) {
   static int n_sm = 0;
   const int QN = m.n_head * tc::HP, NKV = nkv_of(m);
-  const tc::AttnSmem sm = tc::attn_smem(DP, QN, NKV);
+  const tc::AttnSmem sm = tc::attn_smem(DP, QN, NKV, m.d_model);
   if (n_sm == 0) {
     int dev = 0;
     FFD_CHECK_CUDA(cudaGetDevice(&dev));

@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Launch one of the dominant kernels a few times on ECG-sized inputs (for ncu captures).
+
+    python tools/prof_kernels.py --kernel ffn|layer [--batch 16384] [--reps 3]
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch
+
+import bench
+from fastfourierdiffusion_b200 import _lib
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--kernel", default="ffn")
+ap.add_argument("--batch", type=int, default=16384)
+ap.add_argument("--reps", type=int, default=3)
+a = ap.parse_args()
+
+import __graft_entry__ as e
+
+e.build()
+lib = _lib.load()
+model = bench.build_model("bf16").cuda().eval()
+M = a.batch * 187
+st = _lib.stream_handle()
+if a.kernel == "ffn":
+    arena, packed = model.device_weights()
+    x = torch.randn(M, 72, device="cuda")
+    y = torch.empty_like(x)
+    for _ in range(a.reps):
+        _lib.check(lib.ffd_ffn_ln(model.dims, 1, _lib.ptr(arena), _lib.ptr(packed), 3, _lib.ptr(x), _lib.ptr(y), None, M, st))
+else:
+    import fastfourierdiffusion_b200 as F
+
+    s = F.DiffusionSampler(model, a.batch, use_cache=True, noise="philox")
+    model.noise_scheduler.set_timesteps(1000)
+    X = s.sample_prior(a.batch)
+    model.cache.reset()
+    s.run_steps(X, 0, step_begin=0, step_end=1 + a.reps)
+torch.cuda.synchronize()
+print("ok")
