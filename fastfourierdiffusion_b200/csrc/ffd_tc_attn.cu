@@ -318,11 +318,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&o_empty[g]);
-        float rs = 1.f;
-#pragma unroll
-        for (int c = 0; c < HP; ++c)
-          if (c == hd) rs = __uint_as_float(r[c]);  // row sum from the ones column of the V image
-        const float inv = 1.f / rs;
+        const float inv = 1.f / __uint_as_float(r[HP - 1]);  // row sum: ones row (slot 15) of the V image
 #pragma unroll
         for (int c = 0; c < HP; ++c) {
           if (c < hd) {
@@ -335,36 +331,67 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       for (int h = g; h < H; h += 2, ++nhead) {
         mbar_wait(&s_full[g], nhead & 1);
         tc_fence_after();
-        // pass 1: row max over the L valid key columns
-        float mx = -INFINITY;
-        for (int c0 = 0; c0 < NKV; c0 += 32) {
-          uint32_t r[32];
-          FFD_TMEM_LD16(scol + c0, r);
-          FFD_TMEM_LD16(scol + c0 + 16, (r + 16));
-          tmem_ld_wait();
-          if (c0 + 32 > L) {
+        // pass 1: row max.  Padded key columns need no mask: slot 15 of every Q head is the constant 1 and
+        // slot 15 of a padded K row is -29952, so their scores are hugely negative.  TMEM loads are
+        // software-pipelined: the next 32 columns are in flight while the current 32 are consumed.
+        uint32_t ra[32], rb[32];
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        auto max32 = [&](const uint32_t* r) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (c0 + e >= L) r[e] = 0xff800000u;  // -inf
+          for (int e = 0; e < 32; e += 8) {
+            m0 = max3(m0, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+            m1 = max3(m1, __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+            m2 = max3(m2, __uint_as_float(r[e + 4]), __uint_as_float(r[e + 5]));
+            m3 = max3(m3, __uint_as_float(r[e + 6]), __uint_as_float(r[e + 7]));
           }
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) mx = max3(mx, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+        };
+        FFD_TMEM_LD16(scol, ra);
+        FFD_TMEM_LD16(scol + 16, (ra + 16));
+        for (int c0 = 0; c0 < NKV; c0 += 64) {
+          tmem_ld_wait();
+          const bool has_b = c0 + 32 < NKV;
+          if (has_b) {
+            FFD_TMEM_LD16(scol + c0 + 32, rb);
+            FFD_TMEM_LD16(scol + c0 + 48, (rb + 16));
+          }
+          max32(ra);
+          if (has_b) {
+            tmem_ld_wait();
+            if (c0 + 64 < NKV) {
+              FFD_TMEM_LD16(scol + c0 + 64, ra);
+              FFD_TMEM_LD16(scol + c0 + 80, (ra + 16));
+            }
+            max32(rb);
+          }
         }
-        // pass 2: p = exp2(s - max) as fp16 pairs (scores are pre-scaled by log2(e)/sqrt(hd)), written over S
-        for (int c0 = 0; c0 < NKV; c0 += 32) {
-          uint32_t r[32], pk[16];
-          FFD_TMEM_LD16(scol + c0, r);
-          FFD_TMEM_LD16(scol + c0 + 16, (r + 16));
-          tmem_ld_wait();
-          if (c0 + 32 > L) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (c0 + e >= L) r[e] = 0xff800000u;  // exp2(-inf) = 0: padded keys carry no weight
-          }
+        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        // pass 2: p = exp2(s - max) as fp16 pairs (scores are pre-scaled by log2(e)/sqrt(hd)), written over S:
+        // 32 score columns [c, c+32) -> 16 packed columns [c/2, c/2+16), all consumed before they are written
+        auto exp32 = [&](const uint32_t* r, int c0) {
+          uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 32; e += 2)
-            pk[e >> 1] = ex2_f16x2(__uint_as_float(r[e]) - mx, __uint_as_float(r[e + 1]) - mx);
-          FFD_TMEM_ST16(scol + (c0 >> 1), pk);  // packed columns [c0/2, c0/2+16) were all consumed already
+            pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[e]) - mx, __uint_as_float(r[e + 1]) - mx);
+          FFD_TMEM_ST16(scol + (c0 >> 1), pk);
+        };
+        FFD_TMEM_LD16(scol, ra);
+        FFD_TMEM_LD16(scol + 16, (ra + 16));
+        for (int c0 = 0; c0 < NKV; c0 += 64) {
+          tmem_ld_wait();
+          const bool has_b = c0 + 32 < NKV;
+          if (has_b) {
+            FFD_TMEM_LD16(scol + c0 + 32, rb);
+            FFD_TMEM_LD16(scol + c0 + 48, (rb + 16));
+          }
+          exp32(ra, c0);
+          if (has_b) {
+            tmem_ld_wait();
+            if (c0 + 64 < NKV) {
+              FFD_TMEM_LD16(scol + c0 + 64, ra);
+              FFD_TMEM_LD16(scol + c0 + 80, (ra + 16));
+            }
+            exp32(rb, c0 + 32);
+          }
         }
         tmem_st_wait();
         tc_fence_before();
@@ -459,7 +486,9 @@ __global__ void pack_attn_kernel(const float* __restrict__ in_w, const float* __
     float v = 0.f;
     if (!is_o) {
       const int h = n / HP, c = n % HP;
-      if (c < hd) {
+      if (c == HP - 1) {
+        v = (k == d) ? 1.f : 0.f;  // constant-1 slot of every Q head (pairs with the key-padding slot of K)
+      } else if (c < hd) {
         const int r = h * hd + c;
         const float b = in_b[r] * scale;
         if (k < d) v = in_w[r * d + k] * scale;
@@ -476,9 +505,9 @@ __global__ void pack_attn_kernel(const float* __restrict__ in_w, const float* __
   }
 }
 
-// K image per (layer, head): B operand [NKV n(key) x 16 k(dim)], bf16.  V image: B operand
-// [16 n(dim) x NKV k(key)], fp16 (P is fp16), with row n = hd set to 1 for the valid keys so that
-// column hd of O = P . V^T is the softmax row sum.
+// K image per (layer, head): B operand [NKV n(key) x 16 k(dim)], bf16; slot 15 of a padded key row is
+// -29952 (slot 15 of Q is the constant 1).  V image: B operand [16 n(dim) x NKV k(key)], fp16 (P is fp16),
+// with row 15 set to 1 for the valid keys so that column 15 of O = P . V^T is the softmax row sum.
 __global__ void pack_kv_kernel(const float* __restrict__ kc, const float* __restrict__ vc,
                                uint16_t* __restrict__ img, int n_lh, int L, int hd, int NKV) {
   const int per = NKV * HP;  // elements per image
@@ -494,7 +523,8 @@ __global__ void pack_kv_kernel(const float* __restrict__ kc, const float* __rest
     const int key = is_v ? k : n, dim = is_v ? n : k;
     float v = 0.f;
     if (key < L && dim < hd) v = (is_v ? vc : kc)[((int64_t)lh * L + key) * hd + dim];
-    if (is_v && key < L && dim == hd) v = 1.f;
+    if (is_v && key < L && dim == HP - 1) v = 1.f;        // O[:, 15] = softmax row sum
+    if (!is_v && key >= L && dim == HP - 1) v = -29952.f;  // padded keys: score = -29952 -> weight 0
     img[i] = is_v ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
   }
 }
