@@ -145,10 +145,14 @@ static int check_forward(const ffd_forward_args& a) {
 
 }  // namespace ffd
 
+namespace ffd {
+extern long long* g_attn_dbg;
+}
 using namespace ffd;
 
 extern "C" {
 
+void ffd_debug_set_attn_stamps(long long* dev_buf) { ffd::g_attn_dbg = dev_buf; }
 int ffd_version(void) { return 1; }
 uint64_t ffd_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 const char* ffd_last_error(void) { return g_err; }

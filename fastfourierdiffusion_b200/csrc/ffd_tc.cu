@@ -109,7 +109,7 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // provably warp-uniform
 
   if (warp == 0) {
     // ================= bulk-copy producer =================
@@ -150,24 +150,20 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp converged, one elected lane issues) =================
+    {
       constexpr uint32_t IDESC1 = make_idesc(TILE_M, CHUNK);
       constexpr uint32_t IDESC2 = make_idesc(TILE_M, DP);
       uint32_t c1 = 0, c2 = 0;  // ring consumption counters
       uint32_t nchunk = 0;      // slices processed so far by this CTA (both tiles advance together)
       uint32_t npair = 0;
       auto gemm1 = [&](int s, uint32_t w1addr) {
-#pragma unroll
-        for (int k = 0; k < DP / 16; ++k)
-          umma_ts(tmem_base + COL_H + s * 128, tmem_base + COL_X + s * 128 + k * 8,
-                  make_desc(w1addr + k * 2 * (CHUNK * 16), CHUNK * 16, 128), IDESC1, k > 0);
+        umma_ts_chain<DP / 16>(tmem_base + COL_H + s * 128, tmem_base + COL_X + s * 128, 8,
+                               make_desc(w1addr, CHUNK * 16, 128), (2 * CHUNK * 16) >> 4, IDESC1, 0);
       };
       auto gemm2 = [&](int s, uint32_t w2addr, bool first) {
-#pragma unroll
-        for (int k = 0; k < CHUNK / 16; ++k)
-          umma_ts(tmem_base + COL_Y + s * 128, tmem_base + COL_H + s * 128 + k * 8,
-                  make_desc(w2addr + k * 2 * (DP * 16), DP * 16, 128), IDESC2, (!first || k > 0) ? 1u : 0u);
+        umma_ts_chain<CHUNK / 16>(tmem_base + COL_Y + s * 128, tmem_base + COL_H + s * 128, 8,
+                                  make_desc(w2addr, DP * 16, 128), (2 * DP * 16) >> 4, IDESC2, first ? 0u : 1u);
       };
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++npair) {
         // prologue: GEMM1 of slice 0 for both tiles

@@ -13,8 +13,11 @@
 // The fp32 token tile enters and leaves shared memory as one bulk async copy each way; the [tokens x heads x L]
 // score tensor the reference materialises twice per layer (27.5 GB each at B=16384) lives in TMEM.
 //
-// Warp roles (10 warps): 0 = bulk-copy producer (Wq/Wo once, token tiles, K/V head images through rings),
-// 1 = TMEM allocator + MMA issuer, 2..5 = softmax group 0 (even heads), 6..9 = softmax group 1 (odd heads).
+// Warp roles (18 warps): 0 = bulk-copy producer (Wq/Wo once, token tiles, K/V head images through rings),
+// 1 = TMEM allocator + MMA issuer, 2..17 = four softmax groups of four warps.  All four groups work on the same
+// head, each on one quarter of the key columns (partial row maxima are exchanged through shared memory); the
+// score buffers alternate between consecutive heads, so the tensor core computes S_{h+1} and P_{h-1} V_{h-1}
+// while the softmax warps are busy with head h.  The softmax is bound by MUFU.EX2 (16 lanes/clk/SM).
 #include <cuda_fp16.h>
 
 #include "ffd_tc_ptx.cuh"
@@ -22,18 +25,18 @@
 namespace ffd {
 namespace tc {
 
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 576;
 constexpr int KV_STAGES = 3;
 constexpr int HP = 16;  // padded head dim (UMMA K of the score MMA, N of the PV MMA)
 
 // TMEM columns
-constexpr uint32_t COL_S1 = 0;     // Q accumulators, then score buffer of group 1
-constexpr uint32_t COL_S0 = 192;   // score buffer of group 0
-constexpr uint32_t COL_O = 384;    // O accumulators: group g at COL_O + 16 g
+constexpr uint32_t COL_S1 = 0;     // Q accumulators, then score buffer of the odd heads
+constexpr uint32_t COL_S0 = 192;   // score buffer of the even heads
+constexpr uint32_t COL_O = 384;    // O accumulators: pair p at COL_O + 16 p
 constexpr uint32_t COL_OUT = 416;  // out-proj accumulators [416, 416 + DP)
 
 struct AttnSmem {
-  int x32, xo, qbf, wq, wo, kring, vring, consts, bars, tmem, total;
+  int x32, xo, qbf, wq, wo, kring, vring, consts, pmax, bars, tmem, total;
   int tile_bytes, tile_stride, k_bytes, v_bytes, wq_bytes, wo_bytes;
 };
 
@@ -59,6 +62,7 @@ __host__ __device__ inline AttnSmem attn_smem(int DP, int QN, int NKV, int d) {
   s.kring = take(KV_STAGES * s.k_bytes);
   s.vring = take(KV_STAGES * s.v_bytes);
   s.consts = take(2 * DP * 4);
+  s.pmax = take(2 * 4 * TILE_M * 4);    // partial row maxima [head parity][quarter][row]
   s.bars = take(64 * 8);
   s.tmem = take(16);
   s.total = o;
@@ -70,9 +74,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t* __restrict__ wqimg,
                       const uint8_t* __restrict__ woimg, const uint8_t* __restrict__ kvimg,
                       const float* __restrict__ lnw, const float* __restrict__ lnb, int64_t M, int d, int H, int hd,
-                      int L, int NKV, int64_t n_tiles, float eps) {
+                      int L, int NKV, int64_t n_tiles, float eps, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int QN = H * HP;
+#define FFD_STAMP(slot) do { if (dbg && blockIdx.x == 0 && ntile == 2 && lane == 0) dbg[slot] = clock64(); } while (0)
+  const int NQ = NKV >> 2;  // key columns per softmax group (multiple of 16)
   const AttnSmem sm = attn_smem(DP, QN, NKV, d);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);
   uint64_t* k_full = bars;                       // [KV_STAGES] tx
@@ -82,18 +88,19 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
   uint64_t* w_full = v_empty + KV_STAGES;        // [1] tx (Wq + Wo, once)
   uint64_t* t_full = w_full + 1;                 // [2] tx: fp32 tile landed
   uint64_t* t_empty = t_full + 2;                // [2] 1 arrival: tile buffer stored back
-  uint64_t* x_full = t_empty + 2;                // [1] 256 arrivals
+  uint64_t* x_full = t_empty + 2;                // [1] 512 arrivals
   uint64_t* q_full = x_full + 1;                 // [1] commit
-  uint64_t* qbf_full = q_full + 1;               // [1] 256 arrivals
+  uint64_t* qbf_full = q_full + 1;               // [1] 512 arrivals
   uint64_t* s_full = qbf_full + 1;               // [2] commit
-  uint64_t* p_full = s_full + 2;                 // [2] 128 arrivals
+  uint64_t* p_full = s_full + 2;                 // [2] 512 arrivals (all four groups)
   uint64_t* o_full = p_full + 2;                 // [2] commit
-  uint64_t* o_empty = o_full + 2;                // [2] 128 arrivals
-  uint64_t* obf_full = o_empty + 2;              // [1] 256 arrivals
+  uint64_t* o_empty = o_full + 2;                // [2] 128 arrivals (the collecting group)
+  uint64_t* obf_full = o_empty + 2;              // [1] 512 arrivals
   uint64_t* out_full = obf_full + 1;             // [1] commit
   uint64_t* out_empty = out_full + 1;            // [1] 128 arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sm.tmem);
   float* consts = reinterpret_cast<float*>(smem + sm.consts);
+  float* pmax = reinterpret_cast<float*>(smem + sm.pmax);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -109,16 +116,16 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       mbar_init(&t_full[b], 1);
       mbar_init(&t_empty[b], 1);
     }
-    mbar_init(x_full, 256);
+    mbar_init(x_full, 512);
     mbar_init(q_full, 1);
-    mbar_init(qbf_full, 256);
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(&s_full[g], 1);
-      mbar_init(&p_full[g], 128);
-      mbar_init(&o_full[g], 1);
-      mbar_init(&o_empty[g], 128);
+    mbar_init(qbf_full, 512);
+    for (int p = 0; p < 2; ++p) {
+      mbar_init(&s_full[p], 1);
+      mbar_init(&p_full[p], 512);
+      mbar_init(&o_full[p], 1);
+      mbar_init(&o_empty[p], 128);
     }
-    mbar_init(obf_full, 256);
+    mbar_init(obf_full, 512);
     mbar_init(out_full, 1);
     mbar_init(out_empty, 128);
     fence_barrier_init();
@@ -131,7 +138,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // provably warp-uniform
 
   if (warp == 0) {
     // ================= producer =================
@@ -172,8 +179,8 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp converged, one elected lane issues) =================
+    {
       const uint32_t idesc_q = make_idesc(TILE_M, QN);
       const uint32_t idesc_s = make_idesc(TILE_M, NKV);
       constexpr uint32_t IDESC_PV = make_idesc_f16(TILE_M, HP);
@@ -182,15 +189,15 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       const uint32_t xo = smem_u32(smem + sm.xo), qbf = smem_u32(smem + sm.qbf);
       const uint32_t wq = smem_u32(smem + sm.wq), wo = smem_u32(smem + sm.wo);
       uint32_t nk = 0, nv = 0, ntile = 0;
-      uint32_t nhead[2] = {0, 0};  // heads processed so far per softmax group
+      uint32_t nhead0 = 0, nhead1 = 0;  // heads processed so far per score buffer
       auto issue_s = [&](int h) {
-        const int g = h & 1;
+        const int p = h & 1;
         const uint32_t st = nk % KV_STAGES;
         mbar_wait(&k_full[st], (nk / KV_STAGES) & 1);
         tc_fence_after();
-        umma(tmem_base + (g ? COL_S1 : COL_S0), make_desc(qbf + h * 2 * LBO128, LBO128, 128),
+        umma(tmem_base + (p ? COL_S1 : COL_S0), make_desc(qbf + h * 2 * LBO128, LBO128, 128),
              make_desc(smem_u32(smem + sm.kring + st * sm.k_bytes), NKV * 16, 128), idesc_s, 0);
-        umma_commit(&s_full[g]);
+        umma_commit(&s_full[p]);
         umma_commit(&k_empty[st]);
         ++nk;
       };
@@ -199,71 +206,79 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         // ---- Q projection ----
         mbar_wait(x_full, ntile & 1);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < DP / 16; ++k)
-          umma(tmem_base + COL_S1, make_desc(xo + k * 2 * LBO128, LBO128, 128),
-               make_desc(wq + k * 2 * (QN * 16), QN * 16, 128), idesc_q, k > 0);
+        umma_ss_chain<DP / 16>(tmem_base + COL_S1, make_desc(xo, LBO128, 128), (2 * LBO128) >> 4,
+                               make_desc(wq, QN * 16, 128), (2 * QN * 16) >> 4, idesc_q, 0);
         umma_commit(q_full);
         mbar_wait(qbf_full, ntile & 1);  // Q is in shared memory as bf16; its TMEM columns are free
         tc_fence_after();
         issue_s(0);
         if (H > 1) issue_s(1);
         for (int h = 0; h < H; ++h) {
-          const int g = h & 1;
-          const uint32_t n = nhead[g]++;
-          mbar_wait(&p_full[g], n & 1);          // P_h (fp16 pairs) sits in the score buffer
-          mbar_wait(&o_empty[g], (n & 1) ^ 1);   // O of this group's previous head has been read out
+          const int p = h & 1;
+          const uint32_t n = p ? nhead1++ : nhead0++;
+          mbar_wait(&p_full[p], n & 1);          // P_h (fp16 pairs) sits in the score buffer
+          FFD_STAMP(h * 8 + 0);
+          mbar_wait(&o_empty[p], (n & 1) ^ 1);   // O of this pair's previous head has been read out
+          FFD_STAMP(h * 8 + 1);
           const uint32_t st = nv % KV_STAGES;
           mbar_wait(&v_full[st], (nv / KV_STAGES) & 1);
           tc_fence_after();
+          FFD_STAMP(h * 8 + 2);
           const uint32_t vaddr = smem_u32(smem + sm.vring + st * sm.v_bytes);
-          const uint32_t pcol = tmem_base + (g ? COL_S1 : COL_S0);
-          for (int k = 0; k < NKV / 16; ++k)
-            umma_ts(tmem_base + COL_O + 16 * g, pcol + k * 8, make_desc(vaddr + k * 2 * (HP * 16), HP * 16, 128),
-                    IDESC_PV, k > 0);
-          umma_commit(&o_full[g]);
+          const uint32_t pcol = tmem_base + (p ? COL_S1 : COL_S0);
+          // every softmax group keeps its packed P at the start of its own quarter of the buffer:
+          // one chain of kq (1..3) K-steps per quarter
+          const int kq = NQ >> 4;  // k-steps (16 keys) per quarter
+          const uint64_t vdesc = make_desc(vaddr, HP * 16, 128);
+          const uint32_t ocol = tmem_base + COL_O + 16 * p;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t a0 = pcol + q * NQ;
+            const uint64_t b0 = vdesc + (uint64_t)(q * kq) * ((2 * HP * 16) >> 4);
+            if (kq == 3) umma_ts_chain<3>(ocol, a0, 8, b0, (2 * HP * 16) >> 4, IDESC_PV, q != 0);
+            else if (kq == 2) umma_ts_chain<2>(ocol, a0, 8, b0, (2 * HP * 16) >> 4, IDESC_PV, q != 0);
+            else umma_ts_chain<1>(ocol, a0, 8, b0, (2 * HP * 16) >> 4, IDESC_PV, q != 0);
+          }
+          umma_commit(&o_full[p]);
           umma_commit(&v_empty[st]);
           ++nv;
+          FFD_STAMP(h * 8 + 3);
           if (h + 2 < H) issue_s(h + 2);  // after PV_h in issue order: it overwrites P_h's columns
+          FFD_STAMP(h * 8 + 4);
         }
         // ---- output projection ----
         mbar_wait(obf_full, ntile & 1);
         mbar_wait(out_empty, (ntile & 1) ^ 1);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < DP / 16; ++k)
-          umma(tmem_base + COL_OUT, make_desc(xo + k * 2 * LBO128, LBO128, 128),
-               make_desc(wo + k * 2 * (DP * 16), DP * 16, 128), IDESC_OUT, k > 0);
+        umma_ss_chain<DP / 16>(tmem_base + COL_OUT, make_desc(xo, LBO128, 128), (2 * LBO128) >> 4,
+                               make_desc(wo, DP * 16, 128), (2 * DP * 16) >> 4, IDESC_OUT, 0);
         umma_commit(out_full);
       }
     }
   } else {
     // ================= softmax / epilogue groups =================
-    const int g = (warp - 2) >> 2;
+    const int wg = (warp - 2) >> 2;        // 0..3: quarter of the key columns
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
     uint8_t* xo = smem + sm.xo;
     uint8_t* qbf = smem + sm.qbf;
-    const uint32_t scol = tmem_base + lane_base + (g ? COL_S1 : COL_S0);
-    const uint32_t ocol = tmem_base + lane_base + COL_O + 16 * g;
-    uint32_t ntile = 0, nhead = 0;
+    uint32_t ntile = 0;
+    uint32_t cnt0 = 0, cnt1 = 0;  // uses so far of score buffer / O buffer 0 and 1
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
       const int64_t row0 = tile * TILE_M;
       const bool valid = row0 + row < M;
       const uint32_t tb = ntile & 1;
       float* tile32 = reinterpret_cast<float*>(smem + sm.x32 + tb * sm.tile_stride);
       float4* myrow = reinterpret_cast<float4*>(tile32 + row * d);
-      // ---- stage this group's half of X (k-groups of 8 columns) as bf16; the buffer doubles as the
+      // ---- stage this group's share of X (k-groups of 8 columns) as bf16; the buffer doubles as the
       //      out-proj A operand, so the previous tile's out-proj must have finished reading it ----
       mbar_wait(&t_full[tb], (ntile >> 1) & 1);
       if (ntile > 0) mbar_wait(out_full, (ntile - 1) & 1);
       {
         constexpr int NG = DP / 8;
-#pragma unroll
-        for (int i = 0; i < NG / 2; ++i) {
-          const int kg = g * (NG / 2) + i;
+        for (int kg = wg; kg < NG; kg += 4) {
           const int c = kg * 8;
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
           if (c < d) {
@@ -286,10 +301,10 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         fence_proxy_async();
         mbar_arrive(x_full);
       }
-      // ---- Q: TMEM fp32 -> bf16 A-operand tiles, heads of this group ----
+      // ---- Q: TMEM fp32 -> bf16 A-operand tiles, heads split over the four groups ----
       mbar_wait(q_full, ntile & 1);
       tc_fence_after();
-      for (int h = g; h < H; h += 2) {
+      for (int h = wg; h < H; h += 4) {
         uint32_t r[16];
         FFD_TMEM_LD16(tmem_base + lane_base + COL_S1 + h * HP, r);
         tmem_ld_wait();
@@ -308,16 +323,19 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(qbf_full);
-      // ---- heads of this group ----
-      int h_prev = -1;
+      // ---- heads ----
+      // O_h (accumulator buffer h & 1) is read out by group (h >> 1) & 3, two heads later: by then
+      // S_{h+2} has completed, and it was issued after P_h V_h.
       auto collect_o = [&](int h, uint32_t n) {
-        mbar_wait(&o_full[g], n & 1);
+        const int b = h & 1;
+        if (((h >> 1) & 3) != wg) return;
+        mbar_wait(&o_full[b], n & 1);
         tc_fence_after();
         uint32_t r[16];
-        FFD_TMEM_LD16(ocol, r);
+        FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 16 * b, r);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&o_empty[g]);
+        mbar_arrive(&o_empty[b]);
         const float inv = 1.f / __uint_as_float(r[HP - 1]);  // row sum: ones row (slot 15) of the V image
 #pragma unroll
         for (int c = 0; c < HP; ++c) {
@@ -328,129 +346,118 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
           }
         }
       };
-      for (int h = g; h < H; h += 2, ++nhead) {
-        mbar_wait(&s_full[g], nhead & 1);
+      for (int h = 0; h < H; ++h) {
+        const int b = h & 1;
+        const uint32_t n = b ? cnt1++ : cnt0++;
+        const uint32_t scol = tmem_base + lane_base + (b ? COL_S1 : COL_S0) + wg * NQ;  // this group's columns
+        float* pm = pmax + (b * 4) * TILE_M + row;
+        mbar_wait(&s_full[b], n & 1);
         tc_fence_after();
-        // pass 1: row max.  Padded key columns need no mask: slot 15 of every Q head is the constant 1 and
-        // slot 15 of a padded K row is -29952, so their scores are hugely negative.  TMEM loads are
-        // software-pipelined: the next 32 columns are in flight while the current 32 are consumed.
-        uint32_t ra[32], rb[32];
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-        auto max32 = [&](const uint32_t* r) {
+        if (warp == 2) FFD_STAMP(128 + h * 8 + 0);
+        if (h >= 2) collect_o(h - 2, n - 1);
+        if (warp == 2) FFD_STAMP(128 + h * 8 + 1);
+        // pass 1: maximum over this group's quarter of the key columns.  Padded keys need no mask: slot 15 of
+        // every Q head is the constant 1 and slot 15 of a padded K row is -29952 (hugely negative score).
+        uint32_t r[48];
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY;
+        FFD_TMEM_LD16(scol, r);
+        if (NQ > 16) FFD_TMEM_LD16(scol + 16, (r + 16));
+        if (NQ > 32) FFD_TMEM_LD16(scol + 32, (r + 32));
+        tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; e += 8) {
-            m0 = max3(m0, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
-            m1 = max3(m1, __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
-            m2 = max3(m2, __uint_as_float(r[e + 4]), __uint_as_float(r[e + 5]));
-            m3 = max3(m3, __uint_as_float(r[e + 6]), __uint_as_float(r[e + 7]));
-          }
-        };
-        FFD_TMEM_LD16(scol, ra);
-        FFD_TMEM_LD16(scol + 16, (ra + 16));
-        for (int c0 = 0; c0 < NKV; c0 += 64) {
-          tmem_ld_wait();
-          const bool has_b = c0 + 32 < NKV;
-          if (has_b) {
-            FFD_TMEM_LD16(scol + c0 + 32, rb);
-            FFD_TMEM_LD16(scol + c0 + 48, (rb + 16));
-          }
-          max32(ra);
-          if (has_b) {
-            tmem_ld_wait();
-            if (c0 + 64 < NKV) {
-              FFD_TMEM_LD16(scol + c0 + 64, ra);
-              FFD_TMEM_LD16(scol + c0 + 80, (ra + 16));
-            }
-            max32(rb);
-          }
+        for (int e = 0; e < 16; e += 2) m0 = max3(m0, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+        if (NQ > 16) {
+#pragma unroll
+          for (int e = 16; e < 32; e += 2) m1 = max3(m1, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
         }
-        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        // pass 2: p = exp2(s - max) as fp16 pairs (scores are pre-scaled by log2(e)/sqrt(hd)), written over S:
-        // 32 score columns [c, c+32) -> 16 packed columns [c/2, c/2+16), all consumed before they are written
-        auto exp32 = [&](const uint32_t* r, int c0) {
-          uint32_t pk[16];
+        if (NQ > 32) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 2)
+          for (int e = 32; e < 48; e += 2) m2 = max3(m2, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+        }
+        pm[wg * TILE_M] = max3(m0, m1, m2);
+        if (warp == 2) FFD_STAMP(128 + h * 8 + 2);
+        named_bar_sync(5, 512);  // all four groups
+        if (warp == 2) FFD_STAMP(128 + h * 8 + 3);
+        const float mx = fmaxf(fmaxf(pm[0], pm[TILE_M]), fmaxf(pm[2 * TILE_M], pm[3 * TILE_M]));
+        // pass 2: p = exp2(s - max) as fp16 pairs (scores are pre-scaled by log2(e)/sqrt(hd)), written in place:
+        // 16 score columns [c, c+16) -> 8 packed columns [c/2, c/2+8) of this group's own quarter.
+        // The scores are still in registers from pass 1.
+        {
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 16; e += 2)
             pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[e]) - mx, __uint_as_float(r[e + 1]) - mx);
-          FFD_TMEM_ST16(scol + (c0 >> 1), pk);
-        };
-        FFD_TMEM_LD16(scol, ra);
-        FFD_TMEM_LD16(scol + 16, (ra + 16));
-        for (int c0 = 0; c0 < NKV; c0 += 64) {
-          tmem_ld_wait();
-          const bool has_b = c0 + 32 < NKV;
-          if (has_b) {
-            FFD_TMEM_LD16(scol + c0 + 32, rb);
-            FFD_TMEM_LD16(scol + c0 + 48, (rb + 16));
+          FFD_TMEM_ST8(scol, pk);
+          if (NQ > 16) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2)
+              pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[16 + e]) - mx, __uint_as_float(r[17 + e]) - mx);
+            FFD_TMEM_ST8(scol + 8, pk);
           }
-          exp32(ra, c0);
-          if (has_b) {
-            tmem_ld_wait();
-            if (c0 + 64 < NKV) {
-              FFD_TMEM_LD16(scol + c0 + 64, ra);
-              FFD_TMEM_LD16(scol + c0 + 80, (ra + 16));
-            }
-            exp32(rb, c0 + 32);
+          if (NQ > 32) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2)
+              pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[32 + e]) - mx, __uint_as_float(r[33 + e]) - mx);
+            FFD_TMEM_ST8(scol + 16, pk);
           }
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_full[g]);
-        if (h_prev >= 0) collect_o(h_prev, nhead - 1);
-        h_prev = h;
+        mbar_arrive(&p_full[b]);
+        if (warp == 2) FFD_STAMP(128 + h * 8 + 4);
       }
-      if (h_prev >= 0) collect_o(h_prev, nhead - 1);
+      // the last two heads' O
+      if (H >= 2) collect_o(H - 2, (((H - 2) & 1) ? cnt1 : cnt0) - 1);
+      collect_o(H - 1, (((H - 1) & 1) ? cnt1 : cnt0) - 1);
       fence_proxy_async();
       mbar_arrive(obf_full);
-      // ---- out-proj result + residual -> LayerNorm -> tile buffer -> bulk store (groups alternate tiles) ----
-      if ((int)(ntile & 1) == g) {
+      // ---- out-proj result + residual -> LayerNorm -> tile buffer -> bulk store (groups take turns) ----
+      if ((int)(ntile & 3) == wg) {
         mbar_wait(out_full, ntile & 1);
         tc_fence_after();
-        float v[DP];
+        // two sweeps over the accumulator columns keep the register footprint small
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int c0 = 0; c0 < DP; c0 += 16) {
           uint32_t r[16];
           FFD_TMEM_LD16(tmem_base + lane_base + COL_OUT + c0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[c0 + e] = __uint_as_float(r[e]);
+          for (int i = 0; i < 4; ++i) {
+            if (c0 + 4 * i < d) {
+              const float4 xr = valid ? myrow[c0 / 4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float a0 = __uint_as_float(r[4 * i]) + xr.x, a1 = __uint_as_float(r[4 * i + 1]) + xr.y;
+              const float a2 = __uint_as_float(r[4 * i + 2]) + xr.z, a3 = __uint_as_float(r[4 * i + 3]) + xr.w;
+              s1 += (a0 + a1) + (a2 + a3);
+              s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, s2))));
+            }
+          }
+        }
+        const float mean = s1 / (float)d;
+        const float rstd = rsqrtf(fmaxf(s2 / (float)d - mean * mean, 0.f) + eps);
+#pragma unroll
+        for (int c0 = 0; c0 < DP; c0 += 16) {
+          uint32_t r[16];
+          FFD_TMEM_LD16(tmem_base + lane_base + COL_OUT + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (c0 + 4 * i < d && valid) {
+              const float4 xr = myrow[c0 / 4 + i];
+              const int c = c0 + 4 * i;
+              float4 o;
+              o.x = (__uint_as_float(r[4 * i]) + xr.x - mean) * rstd * consts[c] + consts[DP + c];
+              o.y = (__uint_as_float(r[4 * i + 1]) + xr.y - mean) * rstd * consts[c + 1] + consts[DP + c + 1];
+              o.z = (__uint_as_float(r[4 * i + 2]) + xr.z - mean) * rstd * consts[c + 2] + consts[DP + c + 2];
+              o.w = (__uint_as_float(r[4 * i + 3]) + xr.w - mean) * rstd * consts[c + 3] + consts[DP + c + 3];
+              myrow[c0 / 4 + i] = o;
+            }
+          }
         }
         tc_fence_before();
         mbar_arrive(out_empty);
-        if (valid) {
-          float s1 = 0.f;
-#pragma unroll
-          for (int i = 0; i < DP / 4; ++i)
-            if (i * 4 < d) {
-              const float4 xr = myrow[i];
-              v[4 * i + 0] += xr.x;
-              v[4 * i + 1] += xr.y;
-              v[4 * i + 2] += xr.z;
-              v[4 * i + 3] += xr.w;
-              s1 += (v[4 * i] + v[4 * i + 1]) + (v[4 * i + 2] + v[4 * i + 3]);
-            }
-          const float mean = s1 / (float)d;
-          float var = 0.f;
-#pragma unroll
-          for (int c = 0; c < DP; ++c)
-            if (c < d) {
-              const float t = v[c] - mean;
-              var = fmaf(t, t, var);
-            }
-          const float rstd = rsqrtf(var / (float)d + eps);
-#pragma unroll
-          for (int i = 0; i < DP / 4; ++i)
-            if (i * 4 < d) {
-              float4 o;
-              o.x = (v[4 * i + 0] - mean) * rstd * consts[4 * i + 0] + consts[DP + 4 * i + 0];
-              o.y = (v[4 * i + 1] - mean) * rstd * consts[4 * i + 1] + consts[DP + 4 * i + 1];
-              o.z = (v[4 * i + 2] - mean) * rstd * consts[4 * i + 2] + consts[DP + 4 * i + 2];
-              o.w = (v[4 * i + 3] - mean) * rstd * consts[4 * i + 3] + consts[DP + 4 * i + 3];
-              myrow[i] = o;
-            }
-        }
         fence_proxy_async();
-        named_bar_sync(1 + g, 128);
+        named_bar_sync(1 + wg, 128);
         if (quad == 0 && lane == 0) {
           const int64_t rows = M - row0 < TILE_M ? M - row0 : TILE_M;
           bulk_store(y + row0 * d, tile32, (uint32_t)(rows * d * 4));
@@ -536,7 +543,7 @@ bool tc_attn_supported(const ffd_dims& m) {
   return tc_supported(m) && hd < tc::HP && m.n_head * tc::HP <= 192 && m.max_len <= 192;
 }
 
-static int nkv_of(const ffd_dims& m) { return (m.max_len + 31) / 32 * 32; }
+static int nkv_of(const ffd_dims& m) { return (m.max_len + 63) / 64 * 64; }
 
 int64_t tc_attn_image_bytes(const ffd_dims& m) {
   const int DP = tc::dp_of(m.d_model), QN = m.n_head * tc::HP;
@@ -569,6 +576,8 @@ int tc_pack_kv(const ffd_dims& m, const float* kc, const float* vc, void* kvimg,
   return FFD_OK;
 }
 
+long long* g_attn_dbg = nullptr;  // optional device buffer of clock64 stamps (profiling aid)
+
 template <int DP>
 static int launch_attn(const ffd_dims& m, const uint8_t* wqimg, const uint8_t* kvimg_layer, const float* lnw,
                        const float* lnb, const float* x, float* y, int64_t M, cudaStream_t s) {
@@ -586,7 +595,7 @@ static int launch_attn(const ffd_dims& m, const uint8_t* wqimg, const uint8_t* k
   const unsigned grid = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);
   tc::attn_cached_tc_kernel<DP><<<grid, tc::ATT_THREADS, sm.total, s>>>(
       x, y, wqimg, wqimg + (size_t)QN * DP * 2, kvimg_layer, lnw, lnb, M, m.d_model, m.n_head,
-      m.d_model / m.n_head, m.max_len, NKV, n_tiles, 1e-5f);
+      m.d_model / m.n_head, m.max_len, NKV, n_tiles, 1e-5f, g_attn_dbg);
   FFD_CHECK_LAUNCH("attn_cached_tc_kernel");
   return FFD_OK;
 }

@@ -93,18 +93,26 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// The MMA-issuing warp runs CONVERGED: every lane executes the issue loop with warp-uniform operands and
+// the single issuing lane is elected inside the asm statement.  (Issuing from inside an `if (lane == 0)`
+// branch makes ptxas wrap every UTCHMMA in a per-thread "waterfall" loop with R2UR moves -- measured ~240
+// cycles per MMA instead of ~20.)
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
-// arrive on an mbarrier once every MMA issued so far by this thread has completed
+// arrive on an mbarrier once every MMA issued so far by the elected lane has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
 }
 
 #define FFD_TMEM_LD16(taddr, r)                                                                                     \
@@ -127,20 +135,81 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 
-// A operand read from TMEM (bf16 pairs packed per 32-bit column), B from shared memory
+// A operand read from TMEM (16-bit pairs packed per 32-bit column), B from shared memory
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
+}
+
+// ---- chained issue: several K-steps of one GEMM under a single election ------------------------------
+// Measured on B200 (tools/mma_bench.cu): one tcgen05.mma per asm statement costs ~92 (A in smem) / ~110 (A in
+// TMEM) cycles whatever N is; eight per statement cost max(N/2, ~25) cycles each with A in TMEM and
+// max(N/2, ~42) with A in shared memory -- so K-loops are issued as chains.
+#define FFD_TS_HEAD                                                                   \
+  "{\n\t.reg .pred q, p;\n\t.reg .b32 ra;\n\t.reg .b64 bd, bs;\n\t"                     \
+  "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"                          \
+  "mov.b32 ra, %1;\n\tmov.b64 bd, %2;\n\tcvt.u64.u32 bs, %6;\n\t"                      \
+  "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ra], bd, %3, p;\n\t"
+#define FFD_TS_NEXT \
+  "add.u32 ra, ra, %5;\n\tadd.u64 bd, bd, bs;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ra], bd, %3, 1;\n\t"
+#define FFD_TS_ARGS ::"r"(d), "r"(a), "l"(bd), "r"(idesc), "r"(acc), "r"(a_step), "r"(b_step) : "memory"
+
+// D[tmem d] (+)= A[tmem a + i*a_step columns] . B[desc bd + i*b_step (16-byte units)], i < NK
+template <int NK>
+__device__ __forceinline__ void umma_ts_chain(uint32_t d, uint32_t a, uint32_t a_step, uint64_t bd, uint32_t b_step,
+                                              uint32_t idesc, uint32_t acc) {
+  if constexpr (NK >= 8) {
+    asm volatile(FFD_TS_HEAD FFD_TS_NEXT FFD_TS_NEXT FFD_TS_NEXT FFD_TS_NEXT FFD_TS_NEXT FFD_TS_NEXT FFD_TS_NEXT
+                 "}" FFD_TS_ARGS);
+    umma_ts_chain<NK - 8>(d, a + 8 * a_step, a_step, bd + 8 * (uint64_t)b_step, b_step, idesc, 1);
+  } else if constexpr (NK >= 4) {
+    asm volatile(FFD_TS_HEAD FFD_TS_NEXT FFD_TS_NEXT FFD_TS_NEXT "}" FFD_TS_ARGS);
+    umma_ts_chain<NK - 4>(d, a + 4 * a_step, a_step, bd + 4 * (uint64_t)b_step, b_step, idesc, 1);
+  } else if constexpr (NK >= 2) {
+    asm volatile(FFD_TS_HEAD FFD_TS_NEXT "}" FFD_TS_ARGS);
+    umma_ts_chain<NK - 2>(d, a + 2 * a_step, a_step, bd + 2 * (uint64_t)b_step, b_step, idesc, 1);
+  } else if constexpr (NK == 1) {
+    asm volatile(FFD_TS_HEAD "}" FFD_TS_ARGS);
+  }
+}
+
+#define FFD_SS_HEAD                                                                   \
+  "{\n\t.reg .pred q, p;\n\t.reg .b64 ad, bd, as, bs;\n\t"                             \
+  "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"                          \
+  "mov.b64 ad, %1;\n\tmov.b64 bd, %2;\n\tcvt.u64.u32 as, %5;\n\tcvt.u64.u32 bs, %6;\n\t" \
+  "@q tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %3, p;\n\t"
+#define FFD_SS_NEXT \
+  "add.u64 ad, ad, as;\n\tadd.u64 bd, bd, bs;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %3, 1;\n\t"
+#define FFD_SS_ARGS ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc), "r"(a_step), "r"(b_step) : "memory"
+
+// same with both operands in shared memory; steps in 16-byte descriptor units
+template <int NK>
+__device__ __forceinline__ void umma_ss_chain(uint32_t d, uint64_t ad, uint32_t a_step, uint64_t bd, uint32_t b_step,
+                                              uint32_t idesc, uint32_t acc) {
+  if constexpr (NK >= 4) {
+    asm volatile(FFD_SS_HEAD FFD_SS_NEXT FFD_SS_NEXT FFD_SS_NEXT "}" FFD_SS_ARGS);
+    umma_ss_chain<NK - 4>(d, ad + 4 * (uint64_t)a_step, a_step, bd + 4 * (uint64_t)b_step, b_step, idesc, 1);
+  } else if constexpr (NK >= 2) {
+    asm volatile(FFD_SS_HEAD FFD_SS_NEXT "}" FFD_SS_ARGS);
+    umma_ss_chain<NK - 2>(d, ad + 2 * (uint64_t)a_step, a_step, bd + 2 * (uint64_t)b_step, b_step, idesc, 1);
+  } else if constexpr (NK == 1) {
+    asm volatile(FFD_SS_HEAD "}" FFD_SS_ARGS);
+  }
 }
 
 #define FFD_TMEM_ST16(taddr, r)                                                                                     \
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),  \
                  "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])         \
+               : "memory")
+#define FFD_TMEM_ST8(taddr, r)                                                                        \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),  \
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])   \
                : "memory")
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
