@@ -103,7 +103,7 @@ static inline Workspace carve(const ffd_dims& m, int64_t B, void* base) {
   w.qkv = take(M * 3 * d);
   w.kvtmp = take((int64_t)m.max_len * 2 * d);
   // [NL, H] x (K image [NKV x 16] + V image [16 x NKV]) bf16, NKV = ceil64(L)
-  w.kvimg = take((int64_t)m.n_layers * m.n_head * ((m.max_len + 63) / 64 * 64) * 16);
+  w.kvimg = take((int64_t)m.n_layers * m.n_head * (((m.max_len + 63) / 64 * 64) * 16 + 1));
   w.bytes = o;
   return w;
 }

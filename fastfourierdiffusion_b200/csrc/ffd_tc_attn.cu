@@ -5,8 +5,11 @@
 // row is independent and the work is a chain of GEMMs over 128-token tiles:
 //   Q[128 x 16H]   = X[128 x DP] . WqP^T          (heads padded to 16 columns; log2(e)/sqrt(hd) and bq folded in)
 //   S_h[128 x NKV] = Q_h[128 x 16] . K_h^T        one MMA per head, fp32 scores in TMEM
-//   P_h            = exp2(S_h - rowmax)           softmax warps: TMEM -> registers -> TMEM (fp16 pairs, in place
-//                                                 over S_h; two exponentials per MUFU op via ex2.f16x2)
+//   P_h            = exp2(S_h - m)                softmax warps: TMEM -> registers -> TMEM (fp16 pairs, in place over
+//                                                 S_h).  The key columns are split in four quarters, one per softmax
+//                                                 group; each quarter uses ITS OWN row maximum m_q as the shift and
+//                                                 gets its own O accumulator, and the quarters are combined when O is
+//                                                 read out (flash-attention style split-K: exact, no exchange needed)
 //   O_h[128 x 16]  = P_h . [V_h | 1]              A operand read from TMEM; the extra ones column of the V image
 //                                                 makes the tensor core return the softmax row sum as well
 //   OUT[128 x DP]  = concat_h(O_h / rowsum_h) . WoP^T   (bo folded in) -> + residual -> LayerNorm
@@ -15,7 +18,7 @@
 //
 // Warp roles (18 warps): 0 = bulk-copy producer (Wq/Wo once, token tiles, K/V head images through rings),
 // 1 = TMEM allocator + MMA issuer, 2..17 = four softmax groups of four warps.  All four groups work on the same
-// head, each on one quarter of the key columns (partial row maxima are exchanged through shared memory); the
+// head, each on one quarter of the key columns, with no synchronisation among them inside a head; the
 // score buffers alternate between consecutive heads, so the tensor core computes S_{h+1} and P_{h-1} V_{h-1}
 // while the softmax warps are busy with head h.  The softmax is bound by MUFU.EX2 (16 lanes/clk/SM).
 #include <cuda_fp16.h>
@@ -26,14 +29,15 @@ namespace ffd {
 namespace tc {
 
 constexpr int ATT_THREADS = 576;
-constexpr int KV_STAGES = 3;
+constexpr int KV_STAGES = 3;   // K image ring
+constexpr int V_STAGES = 2;    // V image ring (shared memory is full)
 constexpr int HP = 16;  // padded head dim (UMMA K of the score MMA, N of the PV MMA)
 
 // TMEM columns
 constexpr uint32_t COL_S1 = 0;     // Q accumulators, then score buffer of the odd heads
 constexpr uint32_t COL_S0 = 192;   // score buffer of the even heads
-constexpr uint32_t COL_O = 384;    // O accumulators: pair p at COL_O + 16 p
-constexpr uint32_t COL_OUT = 416;  // out-proj accumulators [416, 416 + DP)
+constexpr uint32_t COL_O = 384;    // O accumulators: buffer b, quarter q at COL_O + 64 b + 16 q
+constexpr uint32_t COL_OUT = 192;  // out-proj accumulators [192, 192 + DP): aliases S0, free at that point
 
 struct AttnSmem {
   int x32, xo, qbf, wq, wo, kring, vring, consts, pmax, bars, tmem, total;
@@ -60,9 +64,9 @@ __host__ __device__ inline AttnSmem attn_smem(int DP, int QN, int NKV, int d) {
   s.wq = take(s.wq_bytes);
   s.wo = take(s.wo_bytes);
   s.kring = take(KV_STAGES * s.k_bytes);
-  s.vring = take(KV_STAGES * s.v_bytes);
+  s.vring = take(V_STAGES * s.v_bytes);
   s.consts = take(2 * DP * 4);
-  s.pmax = take(2 * 4 * TILE_M * 4);    // partial row maxima [head parity][quarter][row]
+  s.pmax = take(4 * 4 * TILE_M * 4);    // quarter row maxima [head & 3][quarter][row]
   s.bars = take(64 * 8);
   s.tmem = take(16);
   s.total = o;
@@ -74,7 +78,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t* __restrict__ wqimg,
                       const uint8_t* __restrict__ woimg, const uint8_t* __restrict__ kvimg,
                       const float* __restrict__ lnw, const float* __restrict__ lnb, int64_t M, int d, int H, int hd,
-                      int L, int NKV, int64_t n_tiles, float eps, long long* __restrict__ dbg) {
+                      int L, int NKV, int64_t n_tiles, float eps, const float* __restrict__ kmax,
+                      long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int QN = H * HP;
 #define FFD_STAMP(slot) do { if (dbg && blockIdx.x == 0 && ntile == 2 && lane == 0) dbg[slot] = clock64(); } while (0)
@@ -100,7 +105,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
   uint64_t* out_empty = out_full + 1;            // [1] 128 arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sm.tmem);
   float* consts = reinterpret_cast<float*>(smem + sm.consts);
-  float* pmax = reinterpret_cast<float*>(smem + sm.pmax);
+  float* mq = reinterpret_cast<float*>(smem + sm.pmax);   // [4][4][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -156,7 +161,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         ++nk;
       };
       auto load_v = [&](int h) {
-        const uint32_t st = nv % KV_STAGES, u = nv / KV_STAGES;
+        const uint32_t st = nv % V_STAGES, u = nv / V_STAGES;
         mbar_wait(&v_empty[st], (u & 1) ^ 1);
         mbar_expect_tx(&v_full[st], sm.v_bytes);
         bulk_load(smem + sm.vring + st * sm.v_bytes, kvimg + h * head_stride + sm.k_bytes, sm.v_bytes, &v_full[st]);
@@ -210,6 +215,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
                                make_desc(wq, QN * 16, 128), (2 * QN * 16) >> 4, idesc_q, 0);
         umma_commit(q_full);
         mbar_wait(qbf_full, ntile & 1);  // Q is in shared memory as bf16; its TMEM columns are free
+        mbar_wait(out_empty, (ntile & 1) ^ 1);  // S0 doubles as the previous tile's out-proj accumulator
         tc_fence_after();
         issue_s(0);
         if (H > 1) issue_s(1);
@@ -220,8 +226,8 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
           FFD_STAMP(h * 8 + 0);
           mbar_wait(&o_empty[p], (n & 1) ^ 1);   // O of this pair's previous head has been read out
           FFD_STAMP(h * 8 + 1);
-          const uint32_t st = nv % KV_STAGES;
-          mbar_wait(&v_full[st], (nv / KV_STAGES) & 1);
+          const uint32_t st = nv % V_STAGES;
+          mbar_wait(&v_full[st], (nv / V_STAGES) & 1);
           tc_fence_after();
           FFD_STAMP(h * 8 + 2);
           const uint32_t vaddr = smem_u32(smem + sm.vring + st * sm.v_bytes);
@@ -230,14 +236,14 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
           // one chain of kq (1..3) K-steps per quarter
           const int kq = NQ >> 4;  // k-steps (16 keys) per quarter
           const uint64_t vdesc = make_desc(vaddr, HP * 16, 128);
-          const uint32_t ocol = tmem_base + COL_O + 16 * p;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
+            const uint32_t ocol = tmem_base + COL_O + 64 * p + 16 * q;  // quarter q has its own accumulator
             const uint32_t a0 = pcol + q * NQ;
             const uint64_t b0 = vdesc + (uint64_t)(q * kq) * ((2 * HP * 16) >> 4);
-            if (kq == 3) umma_ts_chain<3>(ocol, a0, 8, b0, (2 * HP * 16) >> 4, IDESC_PV, q != 0);
-            else if (kq == 2) umma_ts_chain<2>(ocol, a0, 8, b0, (2 * HP * 16) >> 4, IDESC_PV, q != 0);
-            else umma_ts_chain<1>(ocol, a0, 8, b0, (2 * HP * 16) >> 4, IDESC_PV, q != 0);
+            if (kq == 3) umma_ts_chain<3>(ocol, a0, 8, b0, (2 * HP * 16) >> 4, IDESC_PV, 0);
+            else if (kq == 2) umma_ts_chain<2>(ocol, a0, 8, b0, (2 * HP * 16) >> 4, IDESC_PV, 0);
+            else umma_ts_chain<1>(ocol, a0, 8, b0, (2 * HP * 16) >> 4, IDESC_PV, 0);
           }
           umma_commit(&o_full[p]);
           umma_commit(&v_empty[st]);
@@ -248,7 +254,6 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         }
         // ---- output projection ----
         mbar_wait(obf_full, ntile & 1);
-        mbar_wait(out_empty, (ntile & 1) ^ 1);
         tc_fence_after();
         umma_ss_chain<DP / 16>(tmem_base + COL_OUT, make_desc(xo, LBO128, 128), (2 * LBO128) >> 4,
                                make_desc(wo, DP * 16, 128), (2 * DP * 16) >> 4, IDESC_OUT, 0);
@@ -331,39 +336,60 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         if (((h >> 1) & 3) != wg) return;
         mbar_wait(&o_full[b], n & 1);
         tc_fence_after();
-        uint32_t r[16];
-        FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 16 * b, r);
-        tmem_ld_wait();
+        // combine the four quarters: weights exp2(m_q - max m_q); slot 15 of each O_q is that quarter's row sum
+        const float* mh = mq + ((h & 3) * 4) * TILE_M + row;
+        const float q0 = mh[0], q1 = mh[TILE_M], q2 = mh[2 * TILE_M], q3 = mh[3 * TILE_M];
+        const float mm = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
+        const float w0 = ex2_approx(q0 - mm), w1 = ex2_approx(q1 - mm), w2 = ex2_approx(q2 - mm),
+                    w3 = ex2_approx(q3 - mm);
+        float acc[HP];
+        {
+          uint32_t r[32];
+          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 64 * b, r);
+          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 64 * b + 16, (r + 16));
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < HP; ++c) acc[c] = w0 * __uint_as_float(r[c]) + w1 * __uint_as_float(r[16 + c]);
+          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 64 * b + 32, r);
+          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 64 * b + 48, (r + 16));
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < HP; ++c)
+            acc[c] = fmaf(w2, __uint_as_float(r[c]), fmaf(w3, __uint_as_float(r[16 + c]), acc[c]));
+        }
         tc_fence_before();
         mbar_arrive(&o_empty[b]);
-        const float inv = 1.f / __uint_as_float(r[HP - 1]);  // row sum: ones row (slot 15) of the V image
+        if (warp == 2) FFD_STAMP(256 + h * 4 + 1);
+        const float inv = 1.f / acc[HP - 1];
 #pragma unroll
-        for (int c = 0; c < HP; ++c) {
+        for (int c = 0; c < HP - 1; ++c) {
           if (c < hd) {
             const int col = h * hd + c;
             *reinterpret_cast<__nv_bfloat16*>(xo + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
-                __float2bfloat16_rn(__uint_as_float(r[c]) * inv);
+                __float2bfloat16_rn(acc[c] * inv);
           }
         }
+        if (warp == 2) FFD_STAMP(256 + h * 4 + 2);
       };
       for (int h = 0; h < H; ++h) {
         const int b = h & 1;
         const uint32_t n = b ? cnt1++ : cnt0++;
         const uint32_t scol = tmem_base + lane_base + (b ? COL_S1 : COL_S0) + wg * NQ;  // this group's columns
-        float* pm = pmax + (b * 4) * TILE_M + row;
         mbar_wait(&s_full[b], n & 1);
         tc_fence_after();
         if (warp == 2) FFD_STAMP(128 + h * 8 + 0);
         if (h >= 2) collect_o(h - 2, n - 1);
         if (warp == 2) FFD_STAMP(128 + h * 8 + 1);
-        // pass 1: maximum over this group's quarter of the key columns.  Padded keys need no mask: slot 15 of
-        // every Q head is the constant 1 and slot 15 of a padded K row is -29952 (hugely negative score).
+        // p = exp2(s - m_q) as fp16 pairs with m_q the row maximum over THIS group's quarter of the keys, written
+        // in place: 16 score columns [c, c+16) -> 8 packed columns [c/2, c/2+8) of the quarter.  Padded keys need no
+        // mask: slot 15 of every Q head is the constant 1 and slot 15 of a padded K row is -29952 (a quarter made
+        // only of padding gets m_q = -29952 and weight exp2(m_q - max) = 0 in the combine).
         uint32_t r[48];
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY;
         FFD_TMEM_LD16(scol, r);
         if (NQ > 16) FFD_TMEM_LD16(scol + 16, (r + 16));
         if (NQ > 32) FFD_TMEM_LD16(scol + 32, (r + 32));
         tmem_ld_wait();
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY;
 #pragma unroll
         for (int e = 0; e < 16; e += 2) m0 = max3(m0, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
         if (NQ > 16) {
@@ -374,33 +400,29 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
 #pragma unroll
           for (int e = 32; e < 48; e += 2) m2 = max3(m2, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
         }
-        pm[wg * TILE_M] = max3(m0, m1, m2);
+        const float mb = max3(m0, m1, m2);
+        mq[((h & 3) * 4 + wg) * TILE_M + row] = mb;
         if (warp == 2) FFD_STAMP(128 + h * 8 + 2);
-        named_bar_sync(5, 512);  // all four groups
-        if (warp == 2) FFD_STAMP(128 + h * 8 + 3);
-        const float mx = fmaxf(fmaxf(pm[0], pm[TILE_M]), fmaxf(pm[2 * TILE_M], pm[3 * TILE_M]));
-        // pass 2: p = exp2(s - max) as fp16 pairs (scores are pre-scaled by log2(e)/sqrt(hd)), written in place:
-        // 16 score columns [c, c+16) -> 8 packed columns [c/2, c/2+8) of this group's own quarter.
-        // The scores are still in registers from pass 1.
         {
           uint32_t pk[8];
 #pragma unroll
           for (int e = 0; e < 16; e += 2)
-            pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[e]) - mx, __uint_as_float(r[e + 1]) - mx);
+            pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[e]) - mb, __uint_as_float(r[e + 1]) - mb);
           FFD_TMEM_ST8(scol, pk);
           if (NQ > 16) {
 #pragma unroll
             for (int e = 0; e < 16; e += 2)
-              pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[16 + e]) - mx, __uint_as_float(r[17 + e]) - mx);
+              pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[16 + e]) - mb, __uint_as_float(r[17 + e]) - mb);
             FFD_TMEM_ST8(scol + 8, pk);
           }
           if (NQ > 32) {
 #pragma unroll
             for (int e = 0; e < 16; e += 2)
-              pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[32 + e]) - mx, __uint_as_float(r[33 + e]) - mx);
+              pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[32 + e]) - mb, __uint_as_float(r[33 + e]) - mb);
             FFD_TMEM_ST8(scol + 16, pk);
           }
         }
+        if (warp == 2) FFD_STAMP(128 + h * 8 + 3);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[b]);
@@ -536,6 +558,23 @@ __global__ void pack_kv_kernel(const float* __restrict__ kc, const float* __rest
   }
 }
 
+// Kmax[l, h] = max_j |bf16(k_j)|_2 over the valid keys: the softmax shift bound is |q| Kmax (one warp per head)
+__global__ void kmax_kernel(const float* __restrict__ kc, float* __restrict__ out, int L, int hd) {
+  const int lh = blockIdx.x, lane = threadIdx.x;
+  float mx = 0.f;
+  for (int j = lane; j < L; j += 32) {
+    float n2 = 0.f;
+    for (int c = 0; c < hd; ++c) {
+      const float v = __bfloat162float(__float2bfloat16_rn(kc[((int64_t)lh * L + j) * hd + c]));
+      n2 = fmaf(v, v, n2);
+    }
+    mx = fmaxf(mx, n2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) out[lh] = sqrtf(mx);
+}
+
 }  // namespace tc
 
 bool tc_attn_supported(const ffd_dims& m) {
@@ -550,9 +589,12 @@ int64_t tc_attn_image_bytes(const ffd_dims& m) {
   return (int64_t)(QN * DP + DP * DP) * 2;
 }
 
-int64_t tc_kv_image_bytes(const ffd_dims& m) {
+static int64_t kv_images_only_bytes(const ffd_dims& m) {
   return (int64_t)m.n_layers * m.n_head * 2 * nkv_of(m) * tc::HP * 2;
 }
+
+// K/V operand images of all layers and heads, then Kmax[NL, H] (fp32)
+int64_t tc_kv_image_bytes(const ffd_dims& m) { return kv_images_only_bytes(m) + (int64_t)m.n_layers * m.n_head * 4; }
 
 int tc_pack_attn(const ffd_dims& m, const float* weights, void* img_base, int64_t layer_stride_bytes,
                  int64_t attn_off_bytes, cudaStream_t s) {
@@ -573,14 +615,17 @@ int tc_pack_kv(const ffd_dims& m, const float* kc, const float* vc, void* kvimg,
   tc::pack_kv_kernel<<<148, 256, 0, s>>>(kc, vc, (uint16_t*)kvimg, n_lh, m.max_len, m.d_model / m.n_head,
                                          nkv_of(m));
   FFD_CHECK_LAUNCH("pack_kv_kernel");
+  tc::kmax_kernel<<<n_lh, 32, 0, s>>>(kc, (float*)((uint8_t*)kvimg + kv_images_only_bytes(m)), m.max_len,
+                                      m.d_model / m.n_head);
+  FFD_CHECK_LAUNCH("kmax_kernel");
   return FFD_OK;
 }
 
 long long* g_attn_dbg = nullptr;  // optional device buffer of clock64 stamps (profiling aid)
 
 template <int DP>
-static int launch_attn(const ffd_dims& m, const uint8_t* wqimg, const uint8_t* kvimg_layer, const float* lnw,
-                       const float* lnb, const float* x, float* y, int64_t M, cudaStream_t s) {
+static int launch_attn(const ffd_dims& m, const uint8_t* wqimg, const uint8_t* kvimg_layer, const float* kmax,
+                       const float* lnw, const float* lnb, const float* x, float* y, int64_t M, cudaStream_t s) {
   static int n_sm = 0;
   const int QN = m.n_head * tc::HP, NKV = nkv_of(m);
   const tc::AttnSmem sm = tc::attn_smem(DP, QN, NKV, m.d_model);
@@ -595,7 +640,7 @@ static int launch_attn(const ffd_dims& m, const uint8_t* wqimg, const uint8_t* k
   const unsigned grid = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);
   tc::attn_cached_tc_kernel<DP><<<grid, tc::ATT_THREADS, sm.total, s>>>(
       x, y, wqimg, wqimg + (size_t)QN * DP * 2, kvimg_layer, lnw, lnb, M, m.d_model, m.n_head,
-      m.d_model / m.n_head, m.max_len, NKV, n_tiles, 1e-5f, g_attn_dbg);
+      m.d_model / m.n_head, m.max_len, NKV, n_tiles, 1e-5f, kmax, g_attn_dbg);
   FFD_CHECK_LAUNCH("attn_cached_tc_kernel");
   return FFD_OK;
 }
@@ -606,12 +651,13 @@ int tc_attn_cached(const ffd_dims& m, const void* attn_img, const void* kvimg, c
   const float* w = weights + ar.layer0 + (int64_t)layer * ar.layer_stride;
   const uint8_t* kvl = (const uint8_t*)kvimg + (size_t)layer * m.n_head * 2 * nkv_of(m) * tc::HP * 2;
   const uint8_t* wq = (const uint8_t*)attn_img;
+  const float* km = (const float*)((const uint8_t*)kvimg + kv_images_only_bytes(m)) + (size_t)layer * m.n_head;
   switch (tc::dp_of(m.d_model)) {
-    case 16: return launch_attn<16>(m, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
-    case 32: return launch_attn<32>(m, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
-    case 48: return launch_attn<48>(m, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
-    case 64: return launch_attn<64>(m, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
-    case 80: return launch_attn<80>(m, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
+    case 16: return launch_attn<16>(m, wq, kvl, km, w + ar.n1w, w + ar.n1b, x, y, M, s);
+    case 32: return launch_attn<32>(m, wq, kvl, km, w + ar.n1w, w + ar.n1b, x, y, M, s);
+    case 48: return launch_attn<48>(m, wq, kvl, km, w + ar.n1w, w + ar.n1b, x, y, M, s);
+    case 64: return launch_attn<64>(m, wq, kvl, km, w + ar.n1w, w + ar.n1b, x, y, M, s);
+    case 80: return launch_attn<80>(m, wq, kvl, km, w + ar.n1w, w + ar.n1b, x, y, M, s);
   }
   set_error("tensor-core attention: unsupported d_model %d", m.d_model);
   return FFD_ERR_UNSUPPORTED;

@@ -23,3 +23,5 @@ print("MMA thread per head: p_full, o_empty, v_full, PV issued, S issued (cycles
 for h in range(12): print(h, [int(v - t0) if v else None for v in t[h*8:h*8+5]])
 print("softmax warp 2 per head: s_full, collected, pass1 done, barrier passed, p_full arrive")
 for h in range(12): print(h, [int(v - t0) if v else None for v in t[128+h*8:128+h*8+5]])
+print("collect_o (warp 2): after o_full wait, after ld")
+for h in range(12): print(h, [int(v - t0) if v else None for v in t[256+h*4:256+h*4+3]])
