@@ -102,7 +102,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
   uint64_t* o_empty = o_full + 2;                // [2] 128 arrivals (the collecting group)
   uint64_t* obf_full = o_empty + 2;              // [1] 512 arrivals
   uint64_t* out_full = obf_full + 1;             // [1] commit
-  uint64_t* out_empty = out_full + 1;            // [1] 128 arrivals
+  uint64_t* out_empty = out_full + 1;            // [1] 512 arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sm.tmem);
   float* consts = reinterpret_cast<float*>(smem + sm.consts);
   float* mq = reinterpret_cast<float*>(smem + sm.pmax);   // [4][4][128]
@@ -132,7 +132,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     }
     mbar_init(obf_full, 512);
     mbar_init(out_full, 1);
-    mbar_init(out_empty, 128);
+    mbar_init(out_empty, 512);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 2 * DP; i += ATT_THREADS) {
@@ -236,14 +236,17 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
           // one chain of kq (1..3) K-steps per quarter
           const int kq = NQ >> 4;  // k-steps (16 keys) per quarter
           const uint64_t vdesc = make_desc(vaddr, HP * 16, 128);
+          if (kq == 3) {
+            umma_ts_4x3(tmem_base + COL_O + 64 * p, pcol, NQ, vdesc, (2 * HP * 16) >> 4, IDESC_PV);
+          } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t ocol = tmem_base + COL_O + 64 * p + 16 * q;  // quarter q has its own accumulator
-            const uint32_t a0 = pcol + q * NQ;
-            const uint64_t b0 = vdesc + (uint64_t)(q * kq) * ((2 * HP * 16) >> 4);
-            if (kq == 3) umma_ts_chain<3>(ocol, a0, 8, b0, (2 * HP * 16) >> 4, IDESC_PV, 0);
-            else if (kq == 2) umma_ts_chain<2>(ocol, a0, 8, b0, (2 * HP * 16) >> 4, IDESC_PV, 0);
-            else umma_ts_chain<1>(ocol, a0, 8, b0, (2 * HP * 16) >> 4, IDESC_PV, 0);
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t ocol = tmem_base + COL_O + 64 * p + 16 * q;  // quarter q has its own accumulator
+              const uint32_t a0 = pcol + q * NQ;
+              const uint64_t b0 = vdesc + (uint64_t)(q * kq) * ((2 * HP * 16) >> 4);
+              if (kq == 2) umma_ts_chain<2>(ocol, a0, 8, b0, (2 * HP * 16) >> 4, IDESC_PV, 0);
+              else umma_ts_chain<1>(ocol, a0, 8, b0, (2 * HP * 16) >> 4, IDESC_PV, 0);
+            }
           }
           umma_commit(&o_full[p]);
           umma_commit(&v_empty[st]);
@@ -277,10 +280,13 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       const uint32_t tb = ntile & 1;
       float* tile32 = reinterpret_cast<float*>(smem + sm.x32 + tb * sm.tile_stride);
       float4* myrow = reinterpret_cast<float4*>(tile32 + row * d);
+      if (warp == 2) FFD_STAMP(300);
       // ---- stage this group's share of X (k-groups of 8 columns) as bf16; the buffer doubles as the
       //      out-proj A operand, so the previous tile's out-proj must have finished reading it ----
       mbar_wait(&t_full[tb], (ntile >> 1) & 1);
+      if (warp == 2) FFD_STAMP(301);
       if (ntile > 0) mbar_wait(out_full, (ntile - 1) & 1);
+      if (warp == 2) FFD_STAMP(302);
       {
         constexpr int NG = DP / 8;
         for (int kg = wg; kg < NG; kg += 4) {
@@ -307,8 +313,10 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         mbar_arrive(x_full);
       }
       // ---- Q: TMEM fp32 -> bf16 A-operand tiles, heads split over the four groups ----
+      if (warp == 2) FFD_STAMP(303);
       mbar_wait(q_full, ntile & 1);
       tc_fence_after();
+      if (warp == 2) FFD_STAMP(304);
       for (int h = wg; h < H; h += 4) {
         uint32_t r[16];
         FFD_TMEM_LD16(tmem_base + lane_base + COL_S1 + h * HP, r);
@@ -328,6 +336,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(qbf_full);
+      if (warp == 2) FFD_STAMP(305);
       // ---- heads ----
       // O_h (accumulator buffer h & 1) is read out by group (h >> 1) & 3, two heads later: by then
       // S_{h+2} has completed, and it was issued after P_h V_h.
@@ -340,8 +349,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         const float* mh = mq + ((h & 3) * 4) * TILE_M + row;
         const float q0 = mh[0], q1 = mh[TILE_M], q2 = mh[2 * TILE_M], q3 = mh[3 * TILE_M];
         const float mm = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
-        const float w0 = ex2_approx(q0 - mm), w1 = ex2_approx(q1 - mm), w2 = ex2_approx(q2 - mm),
-                    w3 = ex2_approx(q3 - mm);
+        const float w0 = exp2_fma(q0 - mm), w1 = exp2_fma(q1 - mm), w2 = exp2_fma(q2 - mm), w3 = exp2_fma(q3 - mm);
         float acc[HP];
         {
           uint32_t r[32];
@@ -360,7 +368,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         tc_fence_before();
         mbar_arrive(&o_empty[b]);
         if (warp == 2) FFD_STAMP(256 + h * 4 + 1);
-        const float inv = 1.f / acc[HP - 1];
+        const float inv = rcp_fma(acc[HP - 1]);
 #pragma unroll
         for (int c = 0; c < HP - 1; ++c) {
           if (c < hd) {
@@ -433,63 +441,84 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       collect_o(H - 1, (((H - 1) & 1) ? cnt1 : cnt0) - 1);
       fence_proxy_async();
       mbar_arrive(obf_full);
-      // ---- out-proj result + residual -> LayerNorm -> tile buffer -> bulk store (groups take turns) ----
-      if ((int)(ntile & 3) == wg) {
+      if (warp == 2) FFD_STAMP(306);
+      // ---- out-proj result + residual -> LayerNorm -> tile buffer -> bulk store.  All four groups share the
+      //      work: 16-column unit u of the accumulator belongs to group u & 3; the row sums are exchanged
+      //      through shared memory. ----
+      {
         mbar_wait(out_full, ntile & 1);
         tc_fence_after();
-        // two sweeps over the accumulator columns keep the register footprint small
+        if (warp == 10) FFD_STAMP(307);
+        constexpr int NU = DP / 16;            // 16-column units
+        constexpr int MAXU = (NU + 3) / 4;     // units per group
+        float vals[MAXU][16];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int c0 = 0; c0 < DP; c0 += 16) {
-          uint32_t r[16];
-          FFD_TMEM_LD16(tmem_base + lane_base + COL_OUT + c0, r);
-          tmem_ld_wait();
+        for (int i = 0; i < MAXU; ++i) {
+          const int u = wg + 4 * i;
+          if (u < NU) {
+            uint32_t r[16];
+            FFD_TMEM_LD16(tmem_base + lane_base + COL_OUT + 16 * u, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (c0 + 4 * i < d) {
-              const float4 xr = valid ? myrow[c0 / 4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-              const float a0 = __uint_as_float(r[4 * i]) + xr.x, a1 = __uint_as_float(r[4 * i + 1]) + xr.y;
-              const float a2 = __uint_as_float(r[4 * i + 2]) + xr.z, a3 = __uint_as_float(r[4 * i + 3]) + xr.w;
+            for (int j = 0; j < 4; ++j) {
+              const int c = 16 * u + 4 * j;
+              float4 xr = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (c < d && valid) xr = myrow[c >> 2];
+              const float a0 = (c < d) ? __uint_as_float(r[4 * j]) + xr.x : 0.f;
+              const float a1 = (c < d) ? __uint_as_float(r[4 * j + 1]) + xr.y : 0.f;
+              const float a2 = (c < d) ? __uint_as_float(r[4 * j + 2]) + xr.z : 0.f;
+              const float a3 = (c < d) ? __uint_as_float(r[4 * j + 3]) + xr.w : 0.f;
+              vals[i][4 * j] = a0, vals[i][4 * j + 1] = a1, vals[i][4 * j + 2] = a2, vals[i][4 * j + 3] = a3;
               s1 += (a0 + a1) + (a2 + a3);
               s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, s2))));
             }
           }
         }
-        const float mean = s1 / (float)d;
-        const float rstd = rsqrtf(fmaxf(s2 / (float)d - mean * mean, 0.f) + eps);
+        tc_fence_before();
+        mbar_arrive(out_empty);
+        float2* ps = reinterpret_cast<float2*>(mq);  // the quarter-maxima buffer is idle between tiles
+        ps[wg * TILE_M + row] = make_float2(s1, s2);
+        named_bar_sync(5, 512);
+        const float2 p0 = ps[row], p1 = ps[TILE_M + row], p2 = ps[2 * TILE_M + row], p3 = ps[3 * TILE_M + row];
+        const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) / (float)d;
+        const float ex2v = ((p0.y + p1.y) + (p2.y + p3.y)) / (float)d;
+        const float rstd = rsqrtf(fmaxf(ex2v - mean * mean, 0.f) + eps);
+        if (valid) {
 #pragma unroll
-        for (int c0 = 0; c0 < DP; c0 += 16) {
-          uint32_t r[16];
-          FFD_TMEM_LD16(tmem_base + lane_base + COL_OUT + c0, r);
-          tmem_ld_wait();
+          for (int i = 0; i < MAXU; ++i) {
+            const int u = wg + 4 * i;
+            if (u < NU) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (c0 + 4 * i < d && valid) {
-              const float4 xr = myrow[c0 / 4 + i];
-              const int c = c0 + 4 * i;
-              float4 o;
-              o.x = (__uint_as_float(r[4 * i]) + xr.x - mean) * rstd * consts[c] + consts[DP + c];
-              o.y = (__uint_as_float(r[4 * i + 1]) + xr.y - mean) * rstd * consts[c + 1] + consts[DP + c + 1];
-              o.z = (__uint_as_float(r[4 * i + 2]) + xr.z - mean) * rstd * consts[c + 2] + consts[DP + c + 2];
-              o.w = (__uint_as_float(r[4 * i + 3]) + xr.w - mean) * rstd * consts[c + 3] + consts[DP + c + 3];
-              myrow[c0 / 4 + i] = o;
+              for (int j = 0; j < 4; ++j) {
+                const int c = 16 * u + 4 * j;
+                if (c < d) {
+                  float4 o;
+                  o.x = (vals[i][4 * j] - mean) * rstd * consts[c] + consts[DP + c];
+                  o.y = (vals[i][4 * j + 1] - mean) * rstd * consts[c + 1] + consts[DP + c + 1];
+                  o.z = (vals[i][4 * j + 2] - mean) * rstd * consts[c + 2] + consts[DP + c + 2];
+                  o.w = (vals[i][4 * j + 3] - mean) * rstd * consts[c + 3] + consts[DP + c + 3];
+                  myrow[c >> 2] = o;
+                }
+              }
             }
           }
         }
-        tc_fence_before();
-        mbar_arrive(out_empty);
+        if (warp == 10) FFD_STAMP(308);
         fence_proxy_async();
-        named_bar_sync(1 + wg, 128);
-        if (quad == 0 && lane == 0) {
+        named_bar_sync(5, 512);
+        if (warp == 2 && lane == 0) {
           const int64_t rows = M - row0 < TILE_M ? M - row0 : TILE_M;
           bulk_store(y + row0 * d, tile32, (uint32_t)(rows * d * 4));
           bulk_commit();
           bulk_wait_read();
           mbar_arrive(&t_empty[tb]);
+          if (dbg && blockIdx.x == 0 && ntile == 2) dbg[309] = clock64();
         }
       }
     }
-    if (quad == 0 && lane == 0) bulk_wait_all();
+    if (warp == 2 && lane == 0) bulk_wait_all();
+
   }
 
   tc_fence_before();

@@ -178,6 +178,27 @@ __device__ __forceinline__ void umma_ts_chain(uint32_t d, uint32_t a, uint32_t a
   }
 }
 
+// Four independent 3-step chains under ONE election (the split-K P.V of the attention kernel):
+//   D_q[tmem d + 16 q] = sum_j A[tmem a + q*a_qstride + 8 j] . B[desc bd + (3 q + j) * b_step],  q < 4, j < 3
+__device__ __forceinline__ void umma_ts_4x3(uint32_t d, uint32_t a, uint32_t a_qstride, uint64_t bd, uint32_t b_step,
+                                            uint32_t idesc) {
+#define FFD_Q3(first)                                                                               \
+  "@q tcgen05.mma.cta_group::1.kind::f16 [rd], [ra], bd, %3, 0;\n\t"                                  \
+  "add.u32 rt, ra, 8;\n\tadd.u64 bd, bd, bs;\n\t"                                                     \
+  "@q tcgen05.mma.cta_group::1.kind::f16 [rd], [rt], bd, %3, 1;\n\t"                                  \
+  "add.u32 rt, ra, 16;\n\tadd.u64 bd, bd, bs;\n\t"                                                    \
+  "@q tcgen05.mma.cta_group::1.kind::f16 [rd], [rt], bd, %3, 1;\n\t"                                  \
+  "add.u32 rd, rd, 16;\n\tadd.u32 ra, ra, %4;\n\tadd.u64 bd, bd, bs;\n\t"
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t.reg .b32 rd, ra, rt;\n\t.reg .b64 bd, bs;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b32 rd, %0;\n\tmov.b32 ra, %1;\n\tmov.b64 bd, %2;\n\tcvt.u64.u32 bs, %5;\n\t" FFD_Q3(1) FFD_Q3(0) FFD_Q3(0)
+          FFD_Q3(0) "}" ::"r"(d),
+      "r"(a), "l"(bd), "r"(idesc), "r"(a_qstride), "r"(b_step)
+      : "memory");
+#undef FFD_Q3
+}
+
 #define FFD_SS_HEAD                                                                   \
   "{\n\t.reg .pred q, p;\n\t.reg .b64 ad, bd, as, bs;\n\t"                             \
   "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"                          \
@@ -218,6 +239,31 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2(x) for x <= 0 and 1/x for x > 0 on the FMA/ALU pipes only.  The softmax warps keep the MUFU queue of
+// their sub-partition full (hundreds of cycles deep), so the few transcendental ops of the O read-out must not
+// queue behind it.  exp2: round-to-nearest split x = n + f, degree-5 polynomial for 2^f on [-0.5, 0.5] (rel.
+// error < 2e-7), exponent added through the integer view.  rcp: bit-trick seed + 3 Newton steps (full fp32).
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;             // 1.5 * 2^23: low mantissa bits now hold round(x)
+  const float f = x - (t - 12582912.f);
+  float p = 1.3333558e-3f;
+  p = fmaf(p, f, 9.6181291e-3f);
+  p = fmaf(p, f, 5.5504109e-2f);
+  p = fmaf(p, f, 2.4022651e-1f);
+  p = fmaf(p, f, 6.9314718e-1f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+__device__ __forceinline__ float rcp_fma(float x) {
+  float r = __int_as_float(0x7EF311C7 - __float_as_int(x));
+  r = r * fmaf(-x, r, 2.f);
+  r = r * fmaf(-x, r, 2.f);
+  r = r * fmaf(-x, r, 2.f);
+  r = r * fmaf(-x, r, 2.f);
+  return r;
+}
+
 // two exponentials packed as an fp16 pair; lo -> low half (lower k index)
 __device__ __forceinline__ uint32_t ex2_pack_f16(float lo, float hi) {
   uint32_t r;

@@ -25,3 +25,5 @@ print("softmax warp 2 per head: s_full, collected, pass1 done, barrier passed, p
 for h in range(12): print(h, [int(v - t0) if v else None for v in t[128+h*8:128+h*8+5]])
 print("collect_o (warp 2): after o_full wait, after ld")
 for h in range(12): print(h, [int(v - t0) if v else None for v in t[256+h*4:256+h*4+3]])
+print("tile phases (warp 2): loop start, t_full, prev out_full, x staged, q_full, qbf arrive | obf arrive, LN start (warp 10 = group 2), LN done, store read")
+print([int(v - t0) if v else None for v in t[300:310]])
