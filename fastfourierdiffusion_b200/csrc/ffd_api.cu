@@ -251,6 +251,44 @@ int ffd_ffn_ln(const ffd_dims* dims, int precision, const float* weights, const 
   return launch_add_ln(x, scratch, w + ar.n2w, w + ar.n2b, y, M, d, s);
 }
 
+int ffd_attn_cached_ln(const ffd_dims* dims, int precision, const float* weights, const void* packed, int layer,
+                       const float* k_cache, const float* v_cache, const float* x, float* y, void* workspace,
+                       int64_t workspace_bytes, int64_t M, ffd_stream_t stream) {
+  FFD_CHECK_ARG(dims && weights && k_cache && v_cache && x && y && workspace && M >= 0, "bad ffd_attn_cached_ln arguments");
+  int rc = check_dims(*dims);
+  if (rc) return rc;
+  const ffd_dims& m = *dims;
+  FFD_CHECK_ARG(layer >= 0 && layer < m.n_layers, "layer %d out of range", layer);
+  const int L = m.max_len, d = m.d_model, H = m.n_head, hd = d / H;
+  FFD_CHECK_ARG(M % L == 0, "M must be a whole number of samples (M %% max_len == 0)");
+  const int64_t B = M / L;
+  if (workspace_bytes < ffd_workspace_bytes(dims, B, precision)) {
+    set_error("workspace too small");
+    return FFD_ERR_WORKSPACE;
+  }
+  if (M == 0) return FFD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const Arena ar = arena_of(m);
+  const Workspace ws = carve(m, B, workspace);
+  const float* w = weights + ar.layer0 + (int64_t)layer * ar.layer_stride;
+  if (precision == FFD_PREC_BF16) {
+    FFD_CHECK_ARG(packed != nullptr, "FFD_PREC_BF16 needs the packed weight image");
+    if (!tc_attn_supported(m)) {
+      set_error("tensor-core attention unsupported for these dims");
+      return FFD_ERR_UNSUPPORTED;
+    }
+    if ((rc = tc_pack_kv(m, k_cache, v_cache, ws.kvimg, s))) return rc;
+    return tc_attn_cached(m, tc_attn_image(m, packed, layer), ws.kvimg, weights, layer, x, y, M, s);
+  }
+  FFD_CHECK_ARG(precision == FFD_PREC_FP32, "unknown precision %d", precision);
+  const float* kc = k_cache + (int64_t)layer * H * L * hd;
+  const float* vc = v_cache + (int64_t)layer * H * L * hd;
+  if ((rc = launch_linear(x, d, w + ar.in_w, d, w + ar.in_b, ws.qkv, 3 * d, M, d, d, 0, s))) return rc;
+  if ((rc = launch_attention(ws.qkv, 3 * d, kc, vc, nullptr, 0, ws.attn, B, L, d, H, s))) return rc;
+  if ((rc = launch_linear(ws.attn, d, w + ar.out_w, d, w + ar.out_b, ws.tmp, d, M, d, d, 0, s))) return rc;
+  return launch_add_ln(x, ws.tmp, w + ar.n1w, w + ar.n1b, y, M, d, s);
+}
+
 int ffd_sde_step(const ffd_step_coef* c, const float* G, const float* x, const float* score, const float* z,
                  uint64_t seed, uint64_t stream_id, float* x_out, int64_t B, int L, int C, ffd_stream_t stream) {
   FFD_CHECK_ARG(c && G && x && score && x_out && B >= 0 && L > 0 && C > 0, "bad ffd_sde_step arguments");

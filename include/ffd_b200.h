@@ -141,6 +141,13 @@ typedef struct ffd_step_coef {
 
 /* x_out = x - drift*dt + sqrt_dt*(coef*G)*z, same rounding order as sde.py:228-244 / :143-163.
  * z == NULL: z is drawn in-kernel, Philox-4x32-10 keyed (seed, stream_id), element index = counter. */
+/* y = LayerNorm1(x + out_proj(softmax(q K_c^T / sqrt(hd)) V_c)) of one PURE-CACHE encoder layer on M token rows
+ * (cached_transformer.py:228-258,309-321): K_c/V_c are the sample-0 cache rows [NL, H, L, hd] shared by the batch.
+ * x, y: [M, d] fp32 (y may alias x for FFD_PREC_BF16); workspace as for ffd_score_forward with B = ceil(M / L). */
+int ffd_attn_cached_ln(const ffd_dims* dims, int precision, const float* weights, const void* packed, int layer,
+                       const float* k_cache, const float* v_cache, const float* x, float* y, void* workspace,
+                       int64_t workspace_bytes, int64_t M, ffd_stream_t stream);
+
 int ffd_sde_step(const ffd_step_coef* c, const float* G, const float* x, const float* score, const float* z,
                  uint64_t seed, uint64_t stream_id, float* x_out, int64_t B, int L, int C, ffd_stream_t stream);
 int ffd_prior(const float* G, const float* z, uint64_t seed, uint64_t stream_id, float scale, float* x_out,

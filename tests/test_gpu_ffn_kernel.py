@@ -61,3 +61,67 @@ def test_ffn_ln_fp32_and_tensor_path(which, M):
     _lib.check(_lib.load().ffd_ffn_ln(model.dims, 1, _lib.ptr(arena), _lib.ptr(packed), layer, _lib.ptr(xin),
                                       _lib.ptr(xin), None, M, _lib.stream_handle()))
     assert torch.equal(xin, got16)
+
+
+@pytest.mark.parametrize("which", ["tiny", "ecg"])
+@pytest.mark.parametrize("B", [1, 3, 70])
+def test_attn_cached_ln_fp32_and_tensor_path(which, B):
+    """The pure-cache attention block on its own (ffd_attn_cached_ln): fp32 path against a float64
+    restatement of cached_transformer.py:228-258,309-321, tcgen05 path against the same."""
+    from fastfourierdiffusion_b200 import _lib
+
+    model = build_tiny_model() if which == "tiny" else build_seeded_model(ECG, 42).to("cuda").eval()
+    d, L, H = model.d_model, model.max_len, model.n_head
+    hd = d // H
+    NL = len(model.backbone.layers)
+    layer = NL - 1
+    torch.manual_seed(B)
+    x = torch.randn(B * L, d, device="cuda") * 1.5
+    kc = torch.randn(NL, H, L, hd, device="cuda")
+    vc = torch.randn(NL, H, L, hd, device="cuda")
+    lyr = model.backbone.layers[layer]
+    with torch.no_grad():
+        xd = x.double().view(B, L, d)
+        q = (xd @ lyr.self_attn.in_proj_weight[:d].double().T + lyr.self_attn.in_proj_bias[:d].double())
+        q = q.view(B, L, H, hd).transpose(1, 2)
+        s = q @ kc[layer].double().transpose(-2, -1) / hd ** 0.5
+        o = (torch.softmax(s, -1) @ vc[layer].double()).transpose(1, 2).reshape(B, L, d)
+        o = o @ lyr.self_attn.out_proj.weight.double().T + lyr.self_attn.out_proj.bias.double()
+        want = torch.nn.functional.layer_norm(xd + o, (d,), lyr.norm1.weight.double(), lyr.norm1.bias.double(),
+                                              1e-5).view(B * L, d)
+
+    def run(prec):
+        model.set_precision(prec)
+        arena, packed = model.device_weights()
+        ws = model.workspace(B)
+        y = torch.empty_like(x)
+        _lib.check(_lib.load().ffd_attn_cached_ln(model.dims, 1 if prec == "bf16" else 0, _lib.ptr(arena),
+                                                  _lib.ptr(packed), layer, _lib.ptr(kc), _lib.ptr(vc), _lib.ptr(x),
+                                                  _lib.ptr(y), _lib.ptr(ws), ws.numel(), B * L, _lib.stream_handle()))
+        torch.cuda.synchronize()
+        return y
+
+    assert rel(run("fp32").cpu().numpy(), want.cpu().numpy()) < 5e-6
+    if not _lib.load().ffd_has_tensor_path() or not model._tc_ok():
+        pytest.skip("tensor path not available")
+    got = run("bf16")
+    assert torch.isfinite(got).all()
+    assert rel(got.cpu().numpy(), want.cpu().numpy()) < 2e-2
+    assert float((got.double() - want).abs().mean() / want.abs().mean()) < 3e-3
+    # large scores (|s| ~ 1e2): the split-K softmax must stay exact where a bounded shift would underflow
+    kc2 = kc * 40
+    model.set_precision("bf16")
+    arena, packed = model.device_weights()
+    ws = model.workspace(B)
+    y2 = torch.empty_like(x)
+    _lib.check(_lib.load().ffd_attn_cached_ln(model.dims, 1, _lib.ptr(arena), _lib.ptr(packed), layer, _lib.ptr(kc2),
+                                              _lib.ptr(vc), _lib.ptr(x), _lib.ptr(y2), _lib.ptr(ws), ws.numel(), B * L,
+                                              _lib.stream_handle()))
+    with torch.no_grad():
+        s2 = q @ kc2[layer].double().transpose(-2, -1) / hd ** 0.5
+        o2 = (torch.softmax(s2, -1) @ vc[layer].double()).transpose(1, 2).reshape(B, L, d)
+        o2 = o2 @ lyr.self_attn.out_proj.weight.double().T + lyr.self_attn.out_proj.bias.double()
+        want2 = torch.nn.functional.layer_norm(xd + o2, (d,), lyr.norm1.weight.double(), lyr.norm1.bias.double(),
+                                               1e-5).view(B * L, d)
+    assert torch.isfinite(y2).all()
+    assert float((y2.double() - want2).abs().mean() / want2.abs().mean()) < 3e-2
