@@ -2,6 +2,8 @@
 golden vectors produced by the unmodified reference.  Tolerances: fp32 arithmetic
 1e-5-class (stated per check), bf16 tensor-core arithmetic 1e-3-class on per-step states."""
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -397,3 +399,25 @@ def test_full_batch_properties(prec):
     Xc = sampler.run_steps(Xc, 0, noise=nz, step_begin=0, step_end=3)
     assert torch.isfinite(Xc).all()
     assert rel(Xc.cpu().numpy(), Xc[:1].expand(B, -1, -1).cpu().numpy()) < (1e-6 if prec == "fp32" else 1e-5)
+
+
+def test_entry_points_run(tmp_path):
+    """cmd/sample.py and cmd/benchmark_cache.py with the reference's key names (tiny settings)."""
+    import subprocess
+    import sys
+
+    from ffd_testutil import ROOT
+
+    out = tmp_path / "o"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "cmd", "sample.py"), "num_samples=8",
+                        "num_diffusion_steps=5", "use_cache=true", "cache_kwargs={'K': 5, 'R': 10}",
+                        "sampler.sample_batch_size=4", "score_model.num_layers=2", f"output_dir={out}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    X = torch.load(out / "samples.pt")
+    assert X.shape == (8, 187, 1) and torch.isfinite(X).all()
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "cmd", "benchmark_cache.py"), "num_samples=2",
+                        "num_diffusion_steps=4", "score_model.num_layers=1", f"output_dir={out}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert (out / "benchmark_results.csv").exists()
