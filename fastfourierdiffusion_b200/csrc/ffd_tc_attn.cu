@@ -16,8 +16,9 @@
 // The fp32 token tile enters and leaves shared memory as one bulk async copy each way; the [tokens x heads x L]
 // score tensor the reference materialises twice per layer (27.5 GB each at B=16384) lives in TMEM.
 //
-// Warp roles (18 warps): 0 = bulk-copy producer (Wq/Wo once, token tiles, K/V head images through rings),
-// 1 = TMEM allocator + MMA issuer, 2..17 = four softmax groups of four warps.  All four groups work on the same
+// Warp roles (22 warps): 0 = bulk-copy producer (Wq/Wo once, token tiles, K/V head images through rings),
+// 1 = TMEM allocator + MMA issuer, 2..17 = four softmax groups of four warps, 18..21 = O read-out warps
+// (combine the quarter accumulators, normalise, write the out-proj operand) so the softmax groups never wait.  All four groups work on the same
 // head, each on one quarter of the key columns, with no synchronisation among them inside a head; the
 // score buffers alternate between consecutive heads, so the tensor core computes S_{h+1} and P_{h-1} V_{h-1}
 // while the softmax warps are busy with head h.  The softmax is bound by MUFU.EX2 (16 lanes/clk/SM).
@@ -28,7 +29,7 @@
 namespace ffd {
 namespace tc {
 
-constexpr int ATT_THREADS = 576;
+constexpr int ATT_THREADS = 704;
 constexpr int KV_STAGES = 3;   // K image ring
 constexpr int V_STAGES = 2;    // V image ring (shared memory is full)
 constexpr int HP = 16;  // padded head dim (UMMA K of the score MMA, N of the PV MMA)
@@ -100,7 +101,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
   uint64_t* p_full = s_full + 2;                 // [2] 512 arrivals (all four groups)
   uint64_t* o_full = p_full + 2;                 // [2] commit
   uint64_t* o_empty = o_full + 2;                // [2] 128 arrivals (the collecting group)
-  uint64_t* obf_full = o_empty + 2;              // [1] 512 arrivals
+  uint64_t* obf_full = o_empty + 2;              // [1] 128 arrivals (the read-out warps)
   uint64_t* out_full = obf_full + 1;             // [1] commit
   uint64_t* out_empty = out_full + 1;            // [1] 512 arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sm.tmem);
@@ -130,7 +131,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       mbar_init(&o_full[p], 1);
       mbar_init(&o_empty[p], 128);
     }
-    mbar_init(obf_full, 512);
+    mbar_init(obf_full, 128);
     mbar_init(out_full, 1);
     mbar_init(out_empty, 512);
     fence_barrier_init();
@@ -263,6 +264,55 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         umma_commit(out_full);
       }
     }
+  } else if (warp >= 18) {
+    // ================= O read-out warps =================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
+    uint8_t* xo = smem + sm.xo;
+    uint32_t ntile = 0, cnt0 = 0, cnt1 = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
+      for (int h = 0; h < H; ++h) {
+        const int b = h & 1;
+        const uint32_t n = b ? cnt1++ : cnt0++;
+        mbar_wait(&o_full[b], n & 1);
+        tc_fence_after();
+        // combine the four quarters: weights exp2(m_q - max m_q); slot 15 of each O_q is that quarter's row sum
+        const float* mh = mq + ((h & 3) * 4) * TILE_M + row;
+        const float q0 = mh[0], q1 = mh[TILE_M], q2 = mh[2 * TILE_M], q3 = mh[3 * TILE_M];
+        const float mm = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
+        const float w0 = exp2_fma(q0 - mm), w1 = exp2_fma(q1 - mm), w2 = exp2_fma(q2 - mm), w3 = exp2_fma(q3 - mm);
+        float acc[HP];
+        {
+          uint32_t r[32];
+          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 64 * b, r);
+          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 64 * b + 16, (r + 16));
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < HP; ++c) acc[c] = w0 * __uint_as_float(r[c]) + w1 * __uint_as_float(r[16 + c]);
+          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 64 * b + 32, r);
+          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 64 * b + 48, (r + 16));
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < HP; ++c)
+            acc[c] = fmaf(w2, __uint_as_float(r[c]), fmaf(w3, __uint_as_float(r[16 + c]), acc[c]));
+        }
+        tc_fence_before();
+        mbar_arrive(&o_empty[b]);
+        const float inv = rcp_fma(acc[HP - 1]);
+#pragma unroll
+        for (int c = 0; c < HP - 1; ++c) {
+          if (c < hd) {
+            const int col = h * hd + c;
+            *reinterpret_cast<__nv_bfloat16*>(xo + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                __float2bfloat16_rn(acc[c] * inv);
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(obf_full);
+    }
   } else {
     // ================= softmax / epilogue groups =================
     const int wg = (warp - 2) >> 2;        // 0..3: quarter of the key columns
@@ -338,47 +388,6 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       mbar_arrive(qbf_full);
       if (warp == 2) FFD_STAMP(305);
       // ---- heads ----
-      // O_h (accumulator buffer h & 1) is read out by group (h >> 1) & 3, two heads later: by then
-      // S_{h+2} has completed, and it was issued after P_h V_h.
-      auto collect_o = [&](int h, uint32_t n) {
-        const int b = h & 1;
-        if (((h >> 1) & 3) != wg) return;
-        mbar_wait(&o_full[b], n & 1);
-        tc_fence_after();
-        // combine the four quarters: weights exp2(m_q - max m_q); slot 15 of each O_q is that quarter's row sum
-        const float* mh = mq + ((h & 3) * 4) * TILE_M + row;
-        const float q0 = mh[0], q1 = mh[TILE_M], q2 = mh[2 * TILE_M], q3 = mh[3 * TILE_M];
-        const float mm = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
-        const float w0 = exp2_fma(q0 - mm), w1 = exp2_fma(q1 - mm), w2 = exp2_fma(q2 - mm), w3 = exp2_fma(q3 - mm);
-        float acc[HP];
-        {
-          uint32_t r[32];
-          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 64 * b, r);
-          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 64 * b + 16, (r + 16));
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < HP; ++c) acc[c] = w0 * __uint_as_float(r[c]) + w1 * __uint_as_float(r[16 + c]);
-          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 64 * b + 32, r);
-          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 64 * b + 48, (r + 16));
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < HP; ++c)
-            acc[c] = fmaf(w2, __uint_as_float(r[c]), fmaf(w3, __uint_as_float(r[16 + c]), acc[c]));
-        }
-        tc_fence_before();
-        mbar_arrive(&o_empty[b]);
-        if (warp == 2) FFD_STAMP(256 + h * 4 + 1);
-        const float inv = rcp_fma(acc[HP - 1]);
-#pragma unroll
-        for (int c = 0; c < HP - 1; ++c) {
-          if (c < hd) {
-            const int col = h * hd + c;
-            *reinterpret_cast<__nv_bfloat16*>(xo + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
-                __float2bfloat16_rn(acc[c] * inv);
-          }
-        }
-        if (warp == 2) FFD_STAMP(256 + h * 4 + 2);
-      };
       for (int h = 0; h < H; ++h) {
         const int b = h & 1;
         const uint32_t n = b ? cnt1++ : cnt0++;
@@ -386,7 +395,6 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         mbar_wait(&s_full[b], n & 1);
         tc_fence_after();
         if (warp == 2) FFD_STAMP(128 + h * 8 + 0);
-        if (h >= 2) collect_o(h - 2, n - 1);
         if (warp == 2) FFD_STAMP(128 + h * 8 + 1);
         // p = exp2(s - m_q) as fp16 pairs with m_q the row maximum over THIS group's quarter of the keys, written
         // in place: 16 score columns [c, c+16) -> 8 packed columns [c/2, c/2+8) of the quarter.  Padded keys need no
@@ -436,11 +444,6 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         mbar_arrive(&p_full[b]);
         if (warp == 2) FFD_STAMP(128 + h * 8 + 4);
       }
-      // the last two heads' O
-      if (H >= 2) collect_o(H - 2, (((H - 2) & 1) ? cnt1 : cnt0) - 1);
-      collect_o(H - 1, (((H - 1) & 1) ? cnt1 : cnt0) - 1);
-      fence_proxy_async();
-      mbar_arrive(obf_full);
       if (warp == 2) FFD_STAMP(306);
       // ---- out-proj result + residual -> LayerNorm -> tile buffer -> bulk store.  All four groups share the
       //      work: 16-column unit u of the accumulator belongs to group u & 3; the row sums are exchanged
