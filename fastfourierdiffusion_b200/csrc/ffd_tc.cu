@@ -15,8 +15,11 @@
 // epilogue is relu + convert only.  The last epilogue adds b2 and the fp32 residual, applies LayerNorm per row
 // (one thread owns a row) into the tile buffer, which one bulk copy stores back.
 //
-// Warp roles (10 warps): 0 = bulk-copy producer, 1 = TMEM allocator + MMA issuer,
-// 2..5 = epilogue of tile A, 6..9 = epilogue of tile B.
+// Warp roles (18 warps): 0 = bulk-copy producer (weight slices, token tiles in, finished tiles out),
+// 1 = TMEM allocator + MMA issuer, 2..17 = four epilogue groups of four warps: group g serves tile g & 1 and the
+// (g >> 1)-th half of every 128-column slice, so a slice is converted by eight warps at once (the kernel is bound
+// by the epilogue's latency, not its instruction count).  At the end of a tile pair the lower-half group does the
+// LayerNorm epilogue while the upper-half group already stages the next pair's activations.
 #include "ffd_tc_ptx.cuh"
 
 namespace ffd {
@@ -24,13 +27,13 @@ namespace ffd {
 namespace tc {
 
 constexpr int CHUNK = 128;    // hidden units per slice (UMMA N of GEMM1, K extent of GEMM2)
-constexpr int STAGES = 3;     // weight ring depth
-constexpr int NUM_THREADS = 320;
+constexpr int STAGES = 2;     // weight ring depth (shared memory holds two tile pairs + the rings)
+constexpr int NUM_THREADS = 576;
 
 // ---- shared-memory plan ------------------------------------------------------------------------
 struct FfnSmem {
   int x32, w1, w2, consts, bars, tmem, total;
-  int tile_bytes, w1_bytes, w2_bytes;
+  int tile_bytes, tile_stride, w1_bytes, w2_bytes;
 };
 
 __host__ __device__ inline FfnSmem ffn_smem(int DP, int d) {
@@ -42,13 +45,14 @@ __host__ __device__ inline FfnSmem ffn_smem(int DP, int d) {
     return r;
   };
   s.tile_bytes = TILE_M * d * 4;  // fp32 [128 x d], row-contiguous exactly as in HBM
+  s.tile_stride = (s.tile_bytes + 127) / 128 * 128;
   s.w1_bytes = CHUNK * DP * 2;    // bf16 [128 n x DP k]
   s.w2_bytes = DP * CHUNK * 2;    // bf16 [DP n x 128 k]
-  s.x32 = take(2 * ((s.tile_bytes + 127) / 128 * 128));
+  s.x32 = take(4 * s.tile_stride);  // two tile pairs: one in flight, one being stored / prefetched
   s.w1 = take(STAGES * s.w1_bytes);
   s.w2 = take(STAGES * s.w2_bytes);
   s.consts = take(3 * DP * 4);    // b2, ln weight, ln bias
-  s.bars = take(32 * 8);
+  s.bars = take(40 * 8);
   s.tmem = take(16);
   s.total = o;
   return s;
@@ -62,17 +66,16 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
                  const float* __restrict__ lnb, int64_t M, int d, int n_chunks, int64_t n_pairs, float eps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const FfnSmem sm = ffn_smem(DP, d);
-  const int tile_stride = (sm.tile_bytes + 127) / 128 * 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);
   uint64_t* w1_full = bars;                 // [STAGES] tx
   uint64_t* w1_empty = bars + STAGES;       // [STAGES] commit
   uint64_t* w2_full = bars + 2 * STAGES;    // [STAGES] tx
   uint64_t* w2_empty = bars + 3 * STAGES;   // [STAGES] commit
-  uint64_t* t_full = bars + 4 * STAGES;     // [2] tx: fp32 tile landed in shared memory
-  uint64_t* t_empty = t_full + 2;           // [2] 1 arrival: tile buffer stored back and reusable
-  uint64_t* x_full = t_empty + 2;           // [2] 128 arrivals: bf16 X_s written to TMEM
+  uint64_t* t_full = bars + 4 * STAGES;     // [4] tx: fp32 tile landed in buffer (pair parity, tile)
+  uint64_t* y_ready = t_full + 4;           // [4] 128 arrivals: LayerNorm output sits in the tile buffer
+  uint64_t* x_full = y_ready + 4;           // [2] 128 arrivals: bf16 X_s written to TMEM
   uint64_t* h_full = x_full + 2;            // [2] commit
-  uint64_t* p_full = h_full + 2;            // [2] 128 arrivals
+  uint64_t* p_full = h_full + 2;            // [2] 256 arrivals (both column halves)
   uint64_t* y_full = p_full + 2;            // [2] commit
   uint64_t* y_empty = y_full + 2;           // [2] 128 arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sm.tmem);
@@ -90,12 +93,14 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
       mbar_init(&w2_full[i], 1);
       mbar_init(&w2_empty[i], 1);
     }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&y_ready[i], 128);
+    }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&t_full[s], 1);
-      mbar_init(&t_empty[s], 1);
       mbar_init(&x_full[s], 128);
       mbar_init(&h_full[s], 1);
-      mbar_init(&p_full[s], 128);
+      mbar_init(&p_full[s], 256);
       mbar_init(&y_full[s], 1);
       mbar_init(&y_empty[s], 128);
     }
@@ -129,24 +134,55 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
         bulk_load(smem + sm.w2 + st * sm.w2_bytes, w2img + (size_t)j * sm.w2_bytes, sm.w2_bytes, &w2_full[st]);
         ++k2;
       };
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++npair) {
+      auto rows_of = [&](int64_t pair, int s) -> int64_t {
+        const int64_t row0 = (pair * 2 + s) * TILE_M;
+        return M - row0 < TILE_M ? (M - row0 > 0 ? M - row0 : 0) : TILE_M;
+      };
+      auto load_pair = [&](int64_t pair, uint32_t np) {
         for (int s = 0; s < 2; ++s) {
-          const int64_t row0 = (pair * 2 + s) * TILE_M;
-          const int64_t rows = M - row0 < TILE_M ? (M - row0 > 0 ? M - row0 : 0) : TILE_M;
-          mbar_wait(&t_empty[s], (npair & 1) ^ 1);
+          const int buf = (np & 1) * 2 + s;
+          const int64_t rows = rows_of(pair, s);
           if (rows > 0) {
-            const uint32_t bytes = (uint32_t)(rows * d * 4);
-            mbar_expect_tx(&t_full[s], bytes);
-            bulk_load(smem + sm.x32 + s * tile_stride, x + row0 * d, bytes, &t_full[s]);
+            mbar_expect_tx(&t_full[buf], (uint32_t)(rows * d * 4));
+            bulk_load(smem + sm.x32 + buf * sm.tile_stride, x + (pair * 2 + s) * TILE_M * d, (uint32_t)(rows * d * 4),
+                      &t_full[buf]);
           } else {
-            mbar_arrive(&t_full[s]);
+            mbar_arrive(&t_full[buf]);
           }
         }
-        load_w1(0);  // same order as the MMA warp consumes: W1_0, then W2_j, W1_{j+1}
-        for (int j = 0; j < n_chunks; ++j) {
+      };
+      auto store_pair = [&](int64_t pair, uint32_t np) {
+        for (int s = 0; s < 2; ++s) {
+          const int buf = (np & 1) * 2 + s;
+          const int64_t rows = rows_of(pair, s);
+          mbar_wait(&y_ready[buf], (np >> 1) & 1);
+          if (rows > 0) {
+            bulk_store(y + (pair * 2 + s) * TILE_M * d, smem + sm.x32 + buf * sm.tile_stride, (uint32_t)(rows * d * 4));
+            bulk_commit();
+          }
+        }
+        bulk_wait_read();
+      };
+      if ((int64_t)blockIdx.x < n_pairs) load_pair(blockIdx.x, 0);
+      if ((int64_t)blockIdx.x + gridDim.x < n_pairs) load_pair((int64_t)blockIdx.x + gridDim.x, 1);
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++npair) {
+        // same order as the MMA warp consumes: W1_0, then W2_j, W1_{j+1}
+        load_w1(0);
+        load_w2(0);
+        if (n_chunks > 1) load_w1(1);
+        if (npair > 0) {
+          // the previous pair: store it, then refill its buffers with the pair after this one
+          store_pair(pair - gridDim.x, npair - 1);
+          if (pair + gridDim.x < n_pairs) load_pair(pair + gridDim.x, npair + 1);
+        }
+        for (int j = 1; j < n_chunks; ++j) {
           load_w2(j);
           if (j + 1 < n_chunks) load_w1(j + 1);
         }
+      }
+      if (npair > 0) {
+        store_pair((int64_t)blockIdx.x + (int64_t)(npair - 1) * gridDim.x, npair - 1);
+        bulk_wait_all();
       }
     }
   } else if (warp == 1) {
@@ -162,8 +198,12 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
                                make_desc(w1addr, CHUNK * 16, 128), (2 * CHUNK * 16) >> 4, IDESC1, 0);
       };
       auto gemm2 = [&](int s, uint32_t w2addr, bool first) {
-        umma_ts_chain<CHUNK / 16>(tmem_base + COL_Y + s * 128, tmem_base + COL_H + s * 128, 8,
-                                  make_desc(w2addr, DP * 16, 128), (2 * DP * 16) >> 4, IDESC2, first ? 0u : 1u);
+        // relu(H) is packed per column half: K-steps 0..3 at H_s + 0.., K-steps 4..7 at H_s + 64..
+        const uint64_t bd = make_desc(w2addr, DP * 16, 128);
+        umma_ts_chain<4>(tmem_base + COL_Y + s * 128, tmem_base + COL_H + s * 128, 8, bd, (2 * DP * 16) >> 4, IDESC2,
+                         first ? 0u : 1u);
+        umma_ts_chain<4>(tmem_base + COL_Y + s * 128, tmem_base + COL_H + s * 128 + 64, 8,
+                         bd + 4 * (uint64_t)((2 * DP * 16) >> 4), (2 * DP * 16) >> 4, IDESC2, 1u);
       };
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++npair) {
         // prologue: GEMM1 of slice 0 for both tiles
@@ -212,125 +252,126 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
       }
     }
   } else {
-    // ================= epilogue warps: tile s = 0 (warps 2..5) or 1 (warps 6..9) =================
-    const int s = (warp - 2) >> 2;
+    // ================= epilogue groups: tile s = g & 1, column half hf = g >> 1 =================
+    const int g = (warp - 2) >> 2;
+    const int s = g & 1, hf = g >> 1;
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;      // row inside the 128-token tile
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    float* tile = reinterpret_cast<float*>(smem + sm.x32 + s * tile_stride);
-    float4* myrow = reinterpret_cast<float4*>(tile + row * d);
-    const uint32_t hcol = tmem_base + lane_base + COL_H + s * 128;
+    const uint32_t hcol = tmem_base + lane_base + COL_H + s * 128 + hf * 64;  // this group's 64 fp32 columns
     uint32_t nchunk = 0, npair = 0;
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++npair) {
-      const int64_t row0 = (pair * 2 + s) * TILE_M;
-      const bool valid = row0 + row < M;
-      // ---- X_s: fp32 row from the tile buffer -> bf16 pairs -> TMEM (A operand of GEMM1);
-      //      columns d, d+1 are the constant-1 bias columns ----
-      mbar_wait(&t_full[s], npair & 1);
-      {
-        uint32_t xp[XC];
+
+    // bf16 X_s -> TMEM (A operand of GEMM1) from the fp32 tile buffer; columns d, d+1 are the constant-1 bias
+    // columns.  Done by the upper-half group of each tile.
+    auto stage_x = [&](int64_t pair, uint32_t np) {
+      const int buf = (np & 1) * 2 + s;
+      const float4* src = reinterpret_cast<const float4*>(smem + sm.x32 + buf * sm.tile_stride) + (size_t)row * (d / 4);
+      const bool valid = (pair * 2 + s) * TILE_M + row < M;
+      mbar_wait(&t_full[buf], (np >> 1) & 1);
+      uint32_t xp[XC];
 #pragma unroll
-        for (int i = 0; i < XC / 2; ++i) {  // 4 columns -> 2 packed words
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int c = i * 4;
-          if (c < d) {
-            if (valid) v = myrow[i];
-          } else {
-            if (c == d) v.x = 1.f, v.y = 1.f;
-          }
-          xp[2 * i] = pack_bf16(v.x, v.y);
-          xp[2 * i + 1] = pack_bf16(v.z, v.w);
+      for (int i = 0; i < XC / 2; ++i) {  // 4 columns -> 2 packed words
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = i * 4;
+        if (c < d) {
+          if (valid) v = src[i];
+        } else if (c == d) {
+          v.x = 1.f, v.y = 1.f;
         }
-#pragma unroll
-        for (int c0 = 0; c0 < XC; c0 += 16) FFD_TMEM_ST16(tmem_base + lane_base + COL_X + s * 128 + c0, (xp + c0));
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&x_full[s]);
+        xp[2 * i] = pack_bf16(v.x, v.y);
+        xp[2 * i + 1] = pack_bf16(v.z, v.w);
       }
-      // ---- per slice: H_s (TMEM fp32) -> relu -> bf16, written back in place ----
+#pragma unroll
+      for (int c0 = 0; c0 < XC; c0 += 16) FFD_TMEM_ST16(tmem_base + lane_base + COL_X + s * 128 + c0, (xp + c0));
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&x_full[s]);
+    };
+
+    if (hf == 1 && (int64_t)blockIdx.x < n_pairs) stage_x(blockIdx.x, 0);
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++npair) {
+      // ---- per slice: this group's half of H_s (TMEM fp32) -> relu -> bf16, written back in place ----
       for (int j = 0; j < n_chunks; ++j, ++nchunk) {
         mbar_wait(&h_full[s], nchunk & 1);
         tc_fence_after();
+        uint32_t r[64], pk[32];
+        FFD_TMEM_LD16(hcol, r);
+        FFD_TMEM_LD16(hcol + 16, (r + 16));
+        FFD_TMEM_LD16(hcol + 32, (r + 32));
+        FFD_TMEM_LD16(hcol + 48, (r + 48));
+        tmem_ld_wait();
 #pragma unroll
-        for (int c0 = 0; c0 < CHUNK; c0 += 64) {
-          uint32_t r[64], pk[32];
-          FFD_TMEM_LD16(hcol + c0, r);
-          FFD_TMEM_LD16(hcol + c0 + 16, (r + 16));
-          FFD_TMEM_LD16(hcol + c0 + 32, (r + 32));
-          FFD_TMEM_LD16(hcol + c0 + 48, (r + 48));
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) pk[e] = relu_pack_bf16(r[2 * e], r[2 * e + 1]);
-          // 64 fp32 columns [c0, c0+64) -> 32 packed columns [c0/2, c0/2+32): all already consumed
-          FFD_TMEM_ST16(hcol + (c0 >> 1), pk);
-          FFD_TMEM_ST16(hcol + (c0 >> 1) + 16, (pk + 16));
-        }
+        for (int e = 0; e < 32; ++e) pk[e] = relu_pack_bf16(r[2 * e], r[2 * e + 1]);
+        // 64 fp32 columns -> 32 packed columns at the start of this group's own half
+        FFD_TMEM_ST16(hcol, pk);
+        FFD_TMEM_ST16(hcol + 16, (pk + 16));
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[s]);
       }
-      // ---- final: Y_s + b2 + residual -> LayerNorm -> tile buffer -> one bulk store ----
-      mbar_wait(&y_full[s], npair & 1);
-      tc_fence_after();
-      float v[DP];
+      if (hf == 1) {
+        // ---- the next pair's activations can go to TMEM as soon as this pair's last GEMM1 has read X_s ----
+        if (pair + gridDim.x < n_pairs) {
+          mbar_wait(&y_full[s], npair & 1);  // all MMAs of this pair (GEMM1 included) are complete
+          stage_x(pair + gridDim.x, npair + 1);
+        }
+      } else {
+        // ---- final: Y_s + b2 + residual -> LayerNorm -> tile buffer (two sweeps keep registers low) ----
+        const int buf = (npair & 1) * 2 + s;
+        float4* myrow = reinterpret_cast<float4*>(smem + sm.x32 + buf * sm.tile_stride) + (size_t)row * (d / 4);
+        const bool valid = (pair * 2 + s) * TILE_M + row < M;
+        mbar_wait(&y_full[s], npair & 1);
+        tc_fence_after();
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int c0 = 0; c0 < DP; c0 += 16) {
-        uint32_t r[16];
-        FFD_TMEM_LD16(tmem_base + lane_base + COL_Y + s * 128 + c0, r);
-        tmem_ld_wait();
+        for (int c0 = 0; c0 < DP; c0 += 16) {
+          uint32_t r[16];
+          FFD_TMEM_LD16(tmem_base + lane_base + COL_Y + s * 128 + c0, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[c0 + e] = __uint_as_float(r[e]);
-      }
-      tc_fence_before();
-      mbar_arrive(&y_empty[s]);
-      if (valid) {
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < DP / 4; ++i) {
-          if (i * 4 < d) {
-            const float4 xr = myrow[i];
-            v[4 * i + 0] += consts[4 * i + 0] + xr.x;
-            v[4 * i + 1] += consts[4 * i + 1] + xr.y;
-            v[4 * i + 2] += consts[4 * i + 2] + xr.z;
-            v[4 * i + 3] += consts[4 * i + 3] + xr.w;
-            sum += (v[4 * i] + v[4 * i + 1]) + (v[4 * i + 2] + v[4 * i + 3]);
+          for (int i = 0; i < 4; ++i) {
+            const int c = c0 + 4 * i;
+            if (c < d) {
+              const float4 xr = valid ? myrow[c >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float a0 = __uint_as_float(r[4 * i]) + consts[c] + xr.x;
+              const float a1 = __uint_as_float(r[4 * i + 1]) + consts[c + 1] + xr.y;
+              const float a2 = __uint_as_float(r[4 * i + 2]) + consts[c + 2] + xr.z;
+              const float a3 = __uint_as_float(r[4 * i + 3]) + consts[c + 3] + xr.w;
+              s1 += (a0 + a1) + (a2 + a3);
+              s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, s2))));
+            }
           }
         }
-        const float mean = sum / (float)d;
-        float var = 0.f;
+        const float mean = s1 / (float)d;
+        const float rstd = rsqrtf(fmaxf(s2 / (float)d - mean * mean, 0.f) + eps);
 #pragma unroll
-        for (int c = 0; c < DP; ++c) {
-          if (c < d) {
-            const float t = v[c] - mean;
-            var = fmaf(t, t, var);
+        for (int c0 = 0; c0 < DP; c0 += 16) {
+          uint32_t r[16];
+          FFD_TMEM_LD16(tmem_base + lane_base + COL_Y + s * 128 + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = c0 + 4 * i;
+            if (c < d && valid) {
+              const float4 xr = myrow[c >> 2];
+              float4 o;
+              o.x = (__uint_as_float(r[4 * i]) + consts[c] + xr.x - mean) * rstd * consts[DP + c] + consts[2 * DP + c];
+              o.y = (__uint_as_float(r[4 * i + 1]) + consts[c + 1] + xr.y - mean) * rstd * consts[DP + c + 1] +
+                    consts[2 * DP + c + 1];
+              o.z = (__uint_as_float(r[4 * i + 2]) + consts[c + 2] + xr.z - mean) * rstd * consts[DP + c + 2] +
+                    consts[2 * DP + c + 2];
+              o.w = (__uint_as_float(r[4 * i + 3]) + consts[c + 3] + xr.w - mean) * rstd * consts[DP + c + 3] +
+                    consts[2 * DP + c + 3];
+              myrow[c >> 2] = o;
+            }
           }
         }
-        const float rstd = rsqrtf(var / (float)d + eps);
-#pragma unroll
-        for (int i = 0; i < DP / 4; ++i) {
-          if (i * 4 < d) {
-            float4 o;
-            o.x = (v[4 * i + 0] - mean) * rstd * consts[DP + 4 * i + 0] + consts[2 * DP + 4 * i + 0];
-            o.y = (v[4 * i + 1] - mean) * rstd * consts[DP + 4 * i + 1] + consts[2 * DP + 4 * i + 1];
-            o.z = (v[4 * i + 2] - mean) * rstd * consts[DP + 4 * i + 2] + consts[2 * DP + 4 * i + 2];
-            o.w = (v[4 * i + 3] - mean) * rstd * consts[DP + 4 * i + 3] + consts[2 * DP + 4 * i + 3];
-            myrow[i] = o;
-          }
-        }
-      }
-      fence_proxy_async();
-      named_bar_sync(1 + s, 128);
-      if (quad == 0 && lane == 0) {
-        const int64_t rows = M - row0 < TILE_M ? (M - row0 > 0 ? M - row0 : 0) : TILE_M;
-        if (rows > 0) {
-          bulk_store(y + row0 * d, tile, (uint32_t)(rows * d * 4));
-          bulk_commit();
-          bulk_wait_read();
-        }
-        mbar_arrive(&t_empty[s]);
+        tc_fence_before();
+        mbar_arrive(&y_empty[s]);
+        fence_proxy_async();
+        mbar_arrive(&y_ready[buf]);
       }
     }
-    if (quad == 0 && lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();

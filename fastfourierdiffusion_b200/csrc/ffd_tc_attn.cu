@@ -93,8 +93,8 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
   uint64_t* v_empty = v_full + KV_STAGES;        // [KV_STAGES] commit
   uint64_t* w_full = v_empty + KV_STAGES;        // [1] tx (Wq + Wo, once)
   uint64_t* t_full = w_full + 1;                 // [2] tx: fp32 tile landed
-  uint64_t* t_empty = t_full + 2;                // [2] 1 arrival: tile buffer stored back
-  uint64_t* x_full = t_empty + 2;                // [1] 512 arrivals
+  uint64_t* y_ready = t_full + 2;                // [2] 512 arrivals: LayerNorm output written to the tile buffer
+  uint64_t* x_full = y_ready + 2;                // [1] 512 arrivals
   uint64_t* q_full = x_full + 1;                 // [1] commit
   uint64_t* qbf_full = q_full + 1;               // [1] 512 arrivals
   uint64_t* s_full = qbf_full + 1;               // [2] commit
@@ -120,7 +120,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     mbar_init(w_full, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&t_full[b], 1);
-      mbar_init(&t_empty[b], 1);
+      mbar_init(&y_ready[b], 512);
     }
     mbar_init(x_full, 512);
     mbar_init(q_full, 1);
@@ -168,20 +168,42 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         bulk_load(smem + sm.vring + st * sm.v_bytes, kvimg + h * head_stride + sm.k_bytes, sm.v_bytes, &v_full[st]);
         ++nv;
       };
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
-        const uint32_t b = ntile & 1, u = ntile >> 1;
+      auto load_tile = [&](int64_t tile, uint32_t nt) {
+        const uint32_t b = nt & 1;
         const int64_t row0 = tile * TILE_M;
         const int64_t rows = M - row0 < TILE_M ? M - row0 : TILE_M;
-        mbar_wait(&t_empty[b], (u & 1) ^ 1);
         mbar_expect_tx(&t_full[b], (uint32_t)(rows * d * 4));
         bulk_load(smem + sm.x32 + b * sm.tile_stride, x + row0 * d, (uint32_t)(rows * d * 4), &t_full[b]);
+      };
+      // the producer also stores finished tiles, so no compute warp ever waits on a bulk copy
+      auto store_tile = [&](int64_t tile, uint32_t nt) {
+        const uint32_t b = nt & 1;
+        const int64_t row0 = tile * TILE_M;
+        const int64_t rows = M - row0 < TILE_M ? M - row0 : TILE_M;
+        mbar_wait(&y_ready[b], (nt >> 1) & 1);
+        bulk_store(y + row0 * d, smem + sm.x32 + b * sm.tile_stride, (uint32_t)(rows * d * 4));
+        bulk_commit();
+        bulk_wait_read();
+      };
+      if ((int64_t)blockIdx.x < n_tiles) load_tile(blockIdx.x, 0);
+      if ((int64_t)blockIdx.x + gridDim.x < n_tiles) load_tile((int64_t)blockIdx.x + gridDim.x, 1);
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
         // consumption order of the MMA warp: K0, K1, then per head h: V_h, K_{h+2}
         load_k(0);
         if (H > 1) load_k(1);
+        if (ntile > 0) {
+          // previous tile: store it, then reuse its buffer for the tile after this one
+          store_tile(tile - gridDim.x, ntile - 1);
+          if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, ntile + 1);
+        }
         for (int h = 0; h < H; ++h) {
           load_v(h);
           if (h + 2 < H) load_k(h + 2);
         }
+      }
+      if (ntile > 0) {
+        store_tile((int64_t)blockIdx.x + (int64_t)(ntile - 1) * gridDim.x, ntile - 1);
+        bulk_wait_all();
       }
     }
   } else if (warp == 1) {
@@ -509,18 +531,9 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         }
         if (warp == 10) FFD_STAMP(308);
         fence_proxy_async();
-        named_bar_sync(5, 512);
-        if (warp == 2 && lane == 0) {
-          const int64_t rows = M - row0 < TILE_M ? M - row0 : TILE_M;
-          bulk_store(y + row0 * d, tile32, (uint32_t)(rows * d * 4));
-          bulk_commit();
-          bulk_wait_read();
-          mbar_arrive(&t_empty[tb]);
-          if (dbg && blockIdx.x == 0 && ntile == 2) dbg[309] = clock64();
-        }
+        mbar_arrive(&y_ready[tb]);
       }
     }
-    if (warp == 2 && lane == 0) bulk_wait_all();
 
   }
 
