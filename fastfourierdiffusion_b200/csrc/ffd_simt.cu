@@ -24,8 +24,43 @@ __global__ void embed_kernel(const float* __restrict__ X, const float* __restric
   h[idx] = ((acc + be[j]) + pos[(int64_t)l * d + j]) + te[j];
 }
 
+// float4 variant (d % 4 == 0): one 16-byte store per thread, fully coalesced -- the kernel is a pure HBM write
+__global__ void __launch_bounds__(256)
+embed4_kernel(const float* __restrict__ X, const float* __restrict__ We, const float* __restrict__ be,
+              const float* __restrict__ pos, const float* __restrict__ te, float4* __restrict__ h, int64_t M, int L,
+              int C, int d4) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * d4) return;
+  const int64_t m = idx / d4;
+  const int j = (int)(idx - m * d4) * 4;
+  const int l = (int)(m % L);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < C; ++c) {
+    const float xv = __ldg(X + m * C + c);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] = fmaf(xv, __ldg(We + (j + e) * C + c), acc[e]);
+  }
+  const float4 b4 = *reinterpret_cast<const float4*>(be + j);
+  const float4 p4 = *reinterpret_cast<const float4*>(pos + (int64_t)l * (d4 * 4) + j);
+  const float4 t4 = *reinterpret_cast<const float4*>(te + j);
+  float4 o;
+  o.x = ((acc[0] + b4.x) + p4.x) + t4.x;
+  o.y = ((acc[1] + b4.y) + p4.y) + t4.y;
+  o.z = ((acc[2] + b4.z) + p4.z) + t4.z;
+  o.w = ((acc[3] + b4.w) + p4.w) + t4.w;
+  h[idx] = o;
+}
+
 int launch_embed(const float* X, const float* We, const float* be, const float* pos, const float* te, float* h,
                  int64_t M, int L, int C, int d, cudaStream_t s) {
+  const bool aligned = d % 4 == 0 && ((uintptr_t)be % 16 == 0) && ((uintptr_t)pos % 16 == 0) &&
+                       ((uintptr_t)te % 16 == 0) && ((uintptr_t)h % 16 == 0);
+  if (aligned) {
+    const int64_t n = M * (d / 4);
+    embed4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(X, We, be, pos, te, (float4*)h, M, L, C, d / 4);
+    FFD_CHECK_LAUNCH("embed4_kernel");
+    return FFD_OK;
+  }
   const int64_t n = M * d;
   embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(X, We, be, pos, te, h, M, L, C, d);
   FFD_CHECK_LAUNCH("embed_kernel");
@@ -425,6 +460,61 @@ unembed_step_kernel(const float* __restrict__ h, const float* __restrict__ Wu, c
   }
 }
 
+// tiled variant: a block stages 128 rows of h through shared memory with coalesced 16-byte loads, then one
+// thread per row forms the C dot products (row stride d+1 words: conflict-free) -- HBM-bound read of h.
+constexpr int UT = 128;
+__global__ void __launch_bounds__(UT)
+unembed_step_tiled_kernel(const float* __restrict__ h, const float* __restrict__ Wu, const float* __restrict__ bu,
+                          float* __restrict__ score_out, int do_step, ffd_step_coef coef,
+                          const float* __restrict__ G, const float* __restrict__ x, const float* __restrict__ z,
+                          uint64_t seed, uint64_t stream_id, float* __restrict__ x_out, int64_t M, int L, int C,
+                          int d) {
+  extern __shared__ float sm[];
+  float* hs = sm;                    // [UT][d+1]
+  float* ws = sm + UT * (d + 1);     // [C][d]
+  const int64_t row0 = (int64_t)blockIdx.x * UT;
+  const int rows = (int)((M - row0 < UT) ? (M - row0) : UT);
+  const int d4 = d / 4;
+  const float4* src = reinterpret_cast<const float4*>(h + row0 * d);
+  for (int i = threadIdx.x; i < rows * d4; i += UT) {
+    const float4 v = __ldg(src + i);
+    const int r = i / d4, c = (i - r * d4) * 4;
+    float* dst = hs + r * (d + 1) + c;
+    dst[0] = v.x, dst[1] = v.y, dst[2] = v.z, dst[3] = v.w;
+  }
+  for (int i = threadIdx.x; i < C * d; i += UT) ws[i] = Wu[i];
+  __syncthreads();
+  const int r = threadIdx.x;
+  if (r >= rows) return;
+  const int64_t row = row0 + r;
+  const float g = do_step ? G[row % L] : 0.f;
+  const float* hr = hs + r * (d + 1);
+  for (int c = 0; c < C; ++c) {
+    float p0 = 0.f, p1 = 0.f;
+    const float* w = ws + c * d;
+    int k = 0;
+    for (; k + 1 < d; k += 2) {
+      p0 = fmaf(hr[k], w[k], p0);
+      p1 = fmaf(hr[k + 1], w[k + 1], p1);
+    }
+    if (k < d) p0 = fmaf(hr[k], w[k], p0);
+    const float p = (p0 + p1) + bu[c];
+    const int64_t e = row * C + c;
+    if (score_out) score_out[e] = p;
+    if (do_step) {
+      float zz;
+      if (z) {
+        zz = z[e];
+      } else {
+        const float4 n4 = philox_normal4(seed, stream_id, (uint64_t)e >> 2);
+        const int q = (int)(e & 3);
+        zz = q == 0 ? n4.x : q == 1 ? n4.y : q == 2 ? n4.z : n4.w;
+      }
+      x_out[e] = sde_update(coef, g, x[e], p, zz);
+    }
+  }
+}
+
 int launch_unembed_step(const float* h, const float* Wu, const float* bu, float* score_out, int do_step,
                         const ffd_step_coef* coef, const float* G, const float* x, const float* z, uint64_t seed,
                         uint64_t stream_id, float* x_out, int64_t M, int L, int C, int d, cudaStream_t s) {
@@ -434,6 +524,16 @@ int launch_unembed_step(const float* h, const float* Wu, const float* bu, float*
   }
   ffd_step_coef c = {};
   if (coef) c = *coef;
+  const size_t smem = sizeof(float) * ((size_t)UT * (d + 1) + (size_t)C * d);
+  if (d % 4 == 0 && (uintptr_t)h % 16 == 0 && smem <= 96 * 1024) {
+    if (smem > 48 * 1024)
+      FFD_CHECK_CUDA(cudaFuncSetAttribute(unembed_step_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+    unembed_step_tiled_kernel<<<(unsigned)((M + UT - 1) / UT), UT, smem, s>>>(h, Wu, bu, score_out, do_step, c, G, x,
+                                                                              z, seed, stream_id, x_out, M, L, C, d);
+    FFD_CHECK_LAUNCH("unembed_step_tiled_kernel");
+    return FFD_OK;
+  }
   unembed_step_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(h, Wu, bu, score_out, do_step, c, G, x, z, seed,
                                                               stream_id, x_out, M, L, C, d);
   FFD_CHECK_LAUNCH("unembed_step_kernel");

@@ -60,8 +60,8 @@ __host__ __device__ inline AttnSmem attn_smem(int DP, int QN, int NKV, int d) {
   s.wq_bytes = QN * DP * 2;
   s.wo_bytes = DP * DP * 2;
   s.x32 = take(2 * s.tile_stride);      // fp32 token tiles (ping-pong): input, residual, output staging
-  s.xo = take(TILE_M * DP * 2);         // bf16 A operand: X for the Q projection, later O for the out-proj
-  s.qbf = take(TILE_M * QN * 2);
+  s.xo = take(TILE_M * DP * 2);         // bf16 A operand of the Q projection (X of the current/next tile)
+  s.qbf = take(TILE_M * QN * 2);        // bf16 Q head tiles; its first DP columns double as the out-proj A operand
   s.wq = take(s.wq_bytes);
   s.wo = take(s.wo_bytes);
   s.kring = take(KV_STAGES * s.k_bytes);
@@ -229,14 +229,16 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         umma_commit(&k_empty[st]);
         ++nk;
       };
-      mbar_wait(w_full, 0);
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
-        // ---- Q projection ----
-        mbar_wait(x_full, ntile & 1);
+      auto issue_q = [&](uint32_t nt) {
+        mbar_wait(x_full, nt & 1);
         tc_fence_after();
         umma_ss_chain<DP / 16>(tmem_base + COL_S1, make_desc(xo, LBO128, 128), (2 * LBO128) >> 4,
                                make_desc(wq, QN * 16, 128), (2 * QN * 16) >> 4, idesc_q, 0);
         umma_commit(q_full);
+      };
+      mbar_wait(w_full, 0);
+      if ((int64_t)blockIdx.x < n_tiles) issue_q(0);
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
         mbar_wait(qbf_full, ntile & 1);  // Q is in shared memory as bf16; its TMEM columns are free
         mbar_wait(out_empty, (ntile & 1) ^ 1);  // S0 doubles as the previous tile's out-proj accumulator
         tc_fence_after();
@@ -278,10 +280,13 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
           if (h + 2 < H) issue_s(h + 2);  // after PV_h in issue order: it overwrites P_h's columns
           FFD_STAMP(h * 8 + 4);
         }
-        // ---- output projection ----
+        // ---- the next tile's Q projection goes first: it only needs the score columns of the odd heads, which
+        //      the last P.V (in issue order) has finished with, and its latency hides behind this tile's epilogue ----
+        if (tile + gridDim.x < n_tiles) issue_q(ntile + 1);
+        // ---- output projection (A operand: the O columns the read-out warps wrote over the dead Q tiles) ----
         mbar_wait(obf_full, ntile & 1);
         tc_fence_after();
-        umma_ss_chain<DP / 16>(tmem_base + COL_OUT, make_desc(xo, LBO128, 128), (2 * LBO128) >> 4,
+        umma_ss_chain<DP / 16>(tmem_base + COL_OUT, make_desc(qbf, LBO128, 128), (2 * LBO128) >> 4,
                                make_desc(wo, DP * 16, 128), (2 * DP * 16) >> 4, IDESC_OUT, 0);
         umma_commit(out_full);
       }
@@ -292,7 +297,9 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
-    uint8_t* xo = smem + sm.xo;
+    // O goes where the Q tiles of already-consumed heads were: head h lands in 8-column groups <= (6h+5)/8, whose
+    // Q data (heads <= h/2) the score MMAs have long finished with (SS-mode operands are read in issue order)
+    uint8_t* xo = smem + sm.qbf;
     uint32_t ntile = 0, cnt0 = 0, cnt1 = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
       for (int h = 0; h < H; ++h) {
@@ -332,6 +339,10 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
           }
         }
       }
+      // constant columns of the out-proj operand: d, d+1 = 1 (bias hi/lo), the rest of the padding = 0
+      for (int c = d; c < DP; ++c)
+        *reinterpret_cast<__nv_bfloat16*>(xo + row_off + (c >> 3) * (TILE_M * 16) + (c & 7) * 2) =
+            __float2bfloat16_rn((c == d || c == d + 1) ? 1.f : 0.f);
       fence_proxy_async();
       mbar_arrive(obf_full);
     }
@@ -346,44 +357,43 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     uint8_t* qbf = smem + sm.qbf;
     uint32_t ntile = 0;
     uint32_t cnt0 = 0, cnt1 = 0;  // uses so far of score buffer / O buffer 0 and 1
+    // stage this group's share of X (k-groups of 8 columns) of tile `tile` (the nt-th of this CTA) as bf16
+    auto stage_x = [&](int64_t tile, uint32_t nt) {
+      const uint32_t tb = nt & 1;
+      const float4* src = reinterpret_cast<const float4*>(smem + sm.x32 + tb * sm.tile_stride) + (size_t)row * (d / 4);
+      const bool valid = tile * TILE_M + row < M;
+      mbar_wait(&t_full[tb], (nt >> 1) & 1);
+      constexpr int NG = DP / 8;
+      for (int kg = wg; kg < NG; kg += 4) {
+        const int c = kg * 8;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
+        if (c < d) {
+          if (valid) a = src[2 * kg];
+        } else if (c == d) {
+          a.x = 1.f, a.y = 1.f;
+        }
+        if (c + 4 < d) {
+          if (valid) b4 = src[2 * kg + 1];
+        } else if (c + 4 == d) {
+          b4.x = 1.f, b4.y = 1.f;
+        }
+        uint4 q;
+        q.x = pack_bf16(a.x, a.y);
+        q.y = pack_bf16(a.z, a.w);
+        q.z = pack_bf16(b4.x, b4.y);
+        q.w = pack_bf16(b4.z, b4.w);
+        *reinterpret_cast<uint4*>(xo + row_off + kg * (TILE_M * 16)) = q;
+      }
+      fence_proxy_async();
+      mbar_arrive(x_full);
+    };
+    if ((int64_t)blockIdx.x < n_tiles) stage_x(blockIdx.x, 0);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
       const int64_t row0 = tile * TILE_M;
       const bool valid = row0 + row < M;
       const uint32_t tb = ntile & 1;
       float* tile32 = reinterpret_cast<float*>(smem + sm.x32 + tb * sm.tile_stride);
       float4* myrow = reinterpret_cast<float4*>(tile32 + row * d);
-      if (warp == 2) FFD_STAMP(300);
-      // ---- stage this group's share of X (k-groups of 8 columns) as bf16; the buffer doubles as the
-      //      out-proj A operand, so the previous tile's out-proj must have finished reading it ----
-      mbar_wait(&t_full[tb], (ntile >> 1) & 1);
-      if (warp == 2) FFD_STAMP(301);
-      if (ntile > 0) mbar_wait(out_full, (ntile - 1) & 1);
-      if (warp == 2) FFD_STAMP(302);
-      {
-        constexpr int NG = DP / 8;
-        for (int kg = wg; kg < NG; kg += 4) {
-          const int c = kg * 8;
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
-          if (c < d) {
-            if (valid) a = myrow[2 * kg];
-          } else if (c == d) {
-            a.x = 1.f, a.y = 1.f;
-          }
-          if (c + 4 < d) {
-            if (valid) b4 = myrow[2 * kg + 1];
-          } else if (c + 4 == d) {
-            b4.x = 1.f, b4.y = 1.f;
-          }
-          uint4 q;
-          q.x = pack_bf16(a.x, a.y);
-          q.y = pack_bf16(a.z, a.w);
-          q.z = pack_bf16(b4.x, b4.y);
-          q.w = pack_bf16(b4.z, b4.w);
-          *reinterpret_cast<uint4*>(xo + row_off + kg * (TILE_M * 16)) = q;
-        }
-        fence_proxy_async();
-        mbar_arrive(x_full);
-      }
       // ---- Q: TMEM fp32 -> bf16 A-operand tiles, heads split over the four groups ----
       if (warp == 2) FFD_STAMP(303);
       mbar_wait(q_full, ntile & 1);
@@ -466,6 +476,9 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         mbar_arrive(&p_full[b]);
         if (warp == 2) FFD_STAMP(128 + h * 8 + 4);
       }
+      // the next tile's X can be staged now (this tile's Q projection is long done with the buffer), so that its
+      // Q projection runs while this tile's out-proj / LayerNorm finish
+      if (tile + gridDim.x < n_tiles) stage_x(tile + gridDim.x, ntile + 1);
       if (warp == 2) FFD_STAMP(306);
       // ---- out-proj result + residual -> LayerNorm -> tile buffer -> bulk store.  All four groups share the
       //      work: 16-column unit u of the accumulator belongs to group u & 3; the row sums are exchanged
