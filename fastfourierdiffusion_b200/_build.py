@@ -33,6 +33,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    cmd += os.environ.get("FFD_NVCC_FLAGS", "").split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]

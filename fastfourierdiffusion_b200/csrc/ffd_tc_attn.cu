@@ -26,6 +26,14 @@
 
 #include "ffd_tc_ptx.cuh"
 
+// Share of the softmax exponentials evaluated on the FMA pipe (bit mask over the 8 fp16 pairs of a 16-column
+// chunk).  Measured on B200 at ECG shapes: 0x00 -> 2.96 ms/launch, 0x88 (25 %) -> 3.09, 0x92 -> 3.23, 0xAA (50 %)
+// -> 3.47: FP32 FMA issues at half rate per sub-partition, so the polynomial costs more than the MUFU time it
+// saves.  Kept as a build-time knob (tools/polytest.sh), off by default.
+#ifndef FFD_POLY_PAIRS
+#define FFD_POLY_PAIRS 0x00u
+#endif
+
 namespace ffd {
 namespace tc {
 
@@ -33,6 +41,8 @@ constexpr int ATT_THREADS = 704;
 constexpr int KV_STAGES = 3;   // K image ring
 constexpr int V_STAGES = 2;    // V image ring (shared memory is full)
 constexpr int HP = 16;  // padded head dim (UMMA K of the score MMA, N of the PV MMA)
+// of the 8 fp16 pairs of a 16-column chunk, the pairs in this bit mask are exponentiated on the FMA pipe
+constexpr uint32_t POLY_PAIRS = FFD_POLY_PAIRS;
 
 // TMEM columns
 constexpr uint32_t COL_S1 = 0;     // Q accumulators, then score buffer of the odd heads
@@ -455,18 +465,24 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
           uint32_t pk[8];
 #pragma unroll
           for (int e = 0; e < 16; e += 2)
-            pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[e]) - mb, __uint_as_float(r[e + 1]) - mb);
+            pk[e >> 1] = ((POLY_PAIRS >> (e >> 1)) & 1)
+                             ? ex2_pack_f16_poly(__uint_as_float(r[e]) - mb, __uint_as_float(r[e + 1]) - mb)
+                             : ex2_pack_f16(__uint_as_float(r[e]) - mb, __uint_as_float(r[e + 1]) - mb);
           FFD_TMEM_ST8(scol, pk);
           if (NQ > 16) {
 #pragma unroll
             for (int e = 0; e < 16; e += 2)
-              pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[16 + e]) - mb, __uint_as_float(r[17 + e]) - mb);
+              pk[e >> 1] = ((POLY_PAIRS >> (e >> 1)) & 1)
+                               ? ex2_pack_f16_poly(__uint_as_float(r[16 + e]) - mb, __uint_as_float(r[17 + e]) - mb)
+                               : ex2_pack_f16(__uint_as_float(r[16 + e]) - mb, __uint_as_float(r[17 + e]) - mb);
             FFD_TMEM_ST8(scol + 8, pk);
           }
           if (NQ > 32) {
 #pragma unroll
             for (int e = 0; e < 16; e += 2)
-              pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[32 + e]) - mb, __uint_as_float(r[33 + e]) - mb);
+              pk[e >> 1] = ((POLY_PAIRS >> (e >> 1)) & 1)
+                               ? ex2_pack_f16_poly(__uint_as_float(r[32 + e]) - mb, __uint_as_float(r[33 + e]) - mb)
+                               : ex2_pack_f16(__uint_as_float(r[32 + e]) - mb, __uint_as_float(r[33 + e]) - mb);
             FFD_TMEM_ST8(scol + 16, pk);
           }
         }

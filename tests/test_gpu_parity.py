@@ -421,3 +421,40 @@ def test_entry_points_run(tmp_path):
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert (out / "benchmark_results.csv").exists()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("shape", [dict(max_len=200, n_channels=3, d_model=24, num_layers=2, n_head=4),
+                                   dict(max_len=37, n_channels=5, d_model=60, num_layers=2, n_head=12)])
+def test_other_shapes_against_oracle(prec, shape):
+    """Shapes outside the tensor-core attention kernel's range (L > 192) or with other paddings (d=60, hd=5,
+    multi-channel): every branch against the numpy oracle with seeded weights (no reference run needed)."""
+    import fastfourierdiffusion_b200 as F
+
+    m = build_seeded_model(shape, 5, precision=prec)
+    if prec not in _precisions():
+        pytest.skip("tensor path not available")
+    if prec == "bf16" and not m._tc_ok():
+        pytest.skip("model shape not supported by the tcgen05 kernels")
+    sd = {k: v.detach().numpy().copy() for k, v in m.state_dict().items()}
+    m = m.to("cuda").eval()
+    L, C = shape["max_len"], shape["n_channels"]
+    w = O.ModelWeights.from_state_dict(sd, shape["n_head"])
+    om = O.OracleScoreModel(w, L, C)
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((3, L, C)).astype(np.float32)
+    t = 0.61
+    ts = torch.full((3,), t, dtype=torch.float32, device="cuda")
+    Xd = torch.from_numpy(X).cuda()
+    tol = TOL[prec]["score"]
+    got = m(F.DiffusableBatch(X=Xd, timesteps=ts))
+    assert rel(got.cpu().numpy(), om.forward(X, t)) < tol
+    m.enable_caching(K=3, R=10)
+    m.cache.reset()
+    store = O.KVStore(shape["num_layers"], L)
+    for i, S in enumerate([range(L), [], range(6), [], [2, 9, 30], []]):
+        score, crf = m(F.DiffusableBatch(X=Xd + 0.02 * i, timesteps=ts), recompute_tokens=set(S), step=i,
+                       return_crf=True)
+        want, wcrf = om.forward_cached(X + np.float32(0.02 * i), t, list(S), store)
+        assert rel(score.cpu().numpy(), want) < tol, i
+        assert rel(crf.cpu().numpy(), wcrf) < tol, i
