@@ -6,8 +6,9 @@
 Times ``DiffusionSampler.sample`` (wall clock around the call, as benchmark_cache.py:92-99 does) without
 the cache and with the cache for the reference's sweeps: default kwargs, K in {0,3,5,10}, R in {5,10,20,50},
 tau_0 in {.05,.1,.2,.5}, freq_decomp_interval in {5,10,20,50} (benchmark_cache.py:172-391; only K and R change
-the schedule).  The reference runs at batch size 1; that default is kept, any batch size can be given.
-FreSca sections are skipped (not built yet).  Writes ``benchmark_results.csv``.
+the schedule), plus the FreSca sections (cache + FreSca, benchmark_cache.py:203-212, and the high_scale sweep,
+:394-422).  The reference runs at batch size 1; that default is kept, any batch size can be given.
+Writes ``benchmark_results.csv``.
 """
 
 from __future__ import annotations
@@ -25,9 +26,11 @@ import fastfourierdiffusion_b200 as F
 from fastfourierdiffusion_b200.cli import SAMPLE_DEFAULTS, build_model, parse_overrides
 
 
-def benchmark_sampling(model, num_samples, num_steps, batch_size, use_cache, cache_kwargs, noise, seed):
+def benchmark_sampling(model, num_samples, num_steps, batch_size, use_cache, cache_kwargs, noise, seed,
+                       use_fresca=False, fresca_kwargs=None):
     sampler = F.DiffusionSampler(score_model=model, sample_batch_size=batch_size, use_cache=use_cache,
-                                 cache_kwargs=cache_kwargs, noise=noise, seed=seed)
+                                 cache_kwargs=cache_kwargs, noise=noise, seed=seed, use_fresca=use_fresca,
+                                 **(fresca_kwargs or {}))
     if not use_cache:
         model.disable_caching()
     torch.manual_seed(seed)
@@ -46,15 +49,20 @@ def main(argv) -> None:
     cfg = parse_overrides(argv, defaults)
     model, _ = build_model(cfg)
     n, steps, bs = cfg["num_samples"], cfg["num_diffusion_steps"], cfg["sampler.sample_batch_size"]
-    configs = [("baseline (no cache)", False, None), ("E2-CRF default", True, {})]
-    configs += [(f"K={k}", True, {"K": k}) for k in (0, 3, 5, 10)]
-    configs += [(f"R={r}", True, {"R": r}) for r in (5, 10, 20, 50)]
-    configs += [(f"tau_0={t}", True, {"tau_0": t}) for t in (0.05, 0.1, 0.2, 0.5)]
-    configs += [(f"freq_decomp_interval={i}", True, {"freq_decomp_interval": i}) for i in (5, 10, 20, 50)]
+    configs = [("baseline (no cache)", False, None, None), ("E2-CRF default", True, {}, None),
+               ("E2-CRF + FreSca", True, {"use_fresca_in_cache": True},
+                {"fresca_high_scale": 1.5, "fresca_cutoff_ratio": 0.5})]
+    configs += [(f"K={k}", True, {"K": k}, None) for k in (0, 3, 5, 10)]
+    configs += [(f"R={r}", True, {"R": r}, None) for r in (5, 10, 20, 50)]
+    configs += [(f"tau_0={t}", True, {"tau_0": t}, None) for t in (0.05, 0.1, 0.2, 0.5)]
+    configs += [(f"freq_decomp_interval={i}", True, {"freq_decomp_interval": i}, None) for i in (5, 10, 20, 50)]
+    configs += [(f"FreSca h={h}", True, {"use_fresca_in_cache": True},
+                 {"fresca_high_scale": h, "fresca_cutoff_ratio": 0.5}) for h in (1.0, 1.2, 1.5, 2.0)]
     benchmark_sampling(model, min(n, bs), 3, bs, False, None, cfg["noise"], cfg["random_seed"])  # warm-up
     rows, base = [], None
-    for name, use_cache, kw in configs:
-        dt, X, stats = benchmark_sampling(model, n, steps, bs, use_cache, kw, cfg["noise"], cfg["random_seed"])
+    for name, use_cache, kw, fk in configs:
+        dt, X, stats = benchmark_sampling(model, n, steps, bs, use_cache, kw, cfg["noise"], cfg["random_seed"],
+                                          use_fresca=fk is not None, fresca_kwargs=fk)
         base = dt if base is None else base
         rows.append({"config": name, "time_s": dt, "speedup": base / dt, "samples_per_s": X.shape[0] / dt,
                      "cache_hit_ratio": stats.get("cache_hit_ratio", 0.0), "cache_ratio": stats.get("cache_ratio", 0.0),

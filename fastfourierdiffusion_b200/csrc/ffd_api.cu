@@ -199,6 +199,18 @@ int ffd_dft_apply(const float* T, const float* x, const float* scale, const floa
   return launch_dft_apply(T, x, scale, shift, y, B, L, C, (cudaStream_t)stream);
 }
 
+int64_t ffd_fresca_scratch_floats(int64_t B, int L, int C) { return B * L * C + (int64_t)L * C + L / 2 + 1; }
+
+int ffd_fresca(const float* U, const float* V, const float* score, float* out, float* scratch, int64_t B, int L, int C,
+               float low_scale, float high_scale, float cutoff_ratio, int strategy, ffd_stream_t stream) {
+  FFD_CHECK_ARG(U && V && score && out && scratch && B >= 0 && L > 0 && C > 0, "bad ffd_fresca arguments");
+  FFD_CHECK_ARG(strategy == 0 || strategy == 1, "unknown cutoff strategy %d (0 spatial, 1 energy)", strategy);
+  FFD_CHECK_ARG(score != out, "ffd_fresca cannot run in place");
+  if (B == 0) return FFD_OK;
+  return launch_fresca(U, V, score, out, scratch, B, L, C, low_scale, high_scale, cutoff_ratio, strategy,
+                       (cudaStream_t)stream);
+}
+
 int ffd_posemb_renorm(float* table, int L, int d, float max_norm, ffd_stream_t stream) {
   FFD_CHECK_ARG(table && L > 0 && d > 0, "bad ffd_posemb_renorm arguments");
   return launch_posemb_renorm(table, L, d, max_norm, (cudaStream_t)stream);

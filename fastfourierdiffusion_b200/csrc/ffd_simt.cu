@@ -741,4 +741,84 @@ int launch_dft_apply(const float* T, const float* x, const float* scale, const f
   return FFD_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// FreSca score filter (src/fdiff/utils/fresca.py:111-268): rfft along L, low band x l, high band x h, irfft.
+// In the real-packed DFT basis (fourier.py layout) that is a per-frequency gain between two dense transforms.
+// ------------------------------------------------------------------------------------
+// spec[k] += sum over this block's samples and all channels of |X_k| (packed layout: Re at row k, Im at nr-1+k)
+__global__ void __launch_bounds__(256)
+fresca_spectrum_kernel(const float* __restrict__ xt, float* __restrict__ spec, int64_t B, int L, int C, int n_freq) {
+  const int nr = (L + 2) / 2;  // = n_freq
+  const int64_t per = (B + gridDim.x - 1) / gridDim.x;
+  const int64_t b0 = (int64_t)blockIdx.x * per, b1 = b0 + per < B ? b0 + per : B;
+  for (int k = threadIdx.x; k < n_freq; k += blockDim.x) {
+    const bool has_im = k >= 1 && (nr - 1 + k) < L;
+    float acc = 0.f;
+    for (int64_t b = b0; b < b1; ++b)
+      for (int c = 0; c < C; ++c) {
+        const float re = xt[(b * L + k) * C + c];
+        const float im = has_im ? xt[(b * L + nr - 1 + k) * C + c] : 0.f;
+        acc += sqrtf(re * re + im * im);
+      }
+    atomicAdd(spec + k, acc);
+  }
+}
+
+// cutoff index and per-row gains.  strategy 0 = spatial (k <= r0 * n_freq), 1 = energy: first i whose cumulative
+// mean magnitude reaches r0 * total (fresca.py:41-60); gain[row, c] = l for rows of frequencies <= Rc, else h.
+__global__ void fresca_gain_kernel(const float* __restrict__ spec, float* __restrict__ gain, int L, int C, int n_freq,
+                                   float low, float high, float cutoff_ratio, int strategy, float inv_count) {
+  __shared__ int rc_s;
+  if (threadIdx.x == 0) {
+    int rc = 0;
+    if (strategy == 0) {
+      const float lim = cutoff_ratio * (float)n_freq;
+      rc = -1;
+      for (int k = 0; k < n_freq; ++k)
+        if ((float)k <= lim) rc = k;
+    } else {
+      float etot = 0.f;  // torch sums the fp32 spectrum in fp32
+      for (int k = 0; k < n_freq; ++k) etot += spec[k] * inv_count;
+      double cum = 0.0;  // the reference accumulates Python floats
+      const double thr = (double)cutoff_ratio * (double)etot;
+      for (int k = 0; k < n_freq; ++k) {
+        cum += (double)(spec[k] * inv_count);
+        if (cum >= thr) {
+          rc = k;
+          break;
+        }
+      }
+    }
+    rc_s = rc;
+  }
+  __syncthreads();
+  const int rc = rc_s, nr = n_freq;
+  for (int i = threadIdx.x; i < L * C; i += blockDim.x) {
+    const int row = i / C;
+    const int k = row < nr ? row : row - (nr - 1);
+    gain[i] = k <= rc ? low : high;
+  }
+}
+
+int launch_fresca(const float* U, const float* V, const float* score, float* out, float* scratch, int64_t B, int L,
+                  int C, float low, float high, float cutoff_ratio, int strategy, cudaStream_t s) {
+  // scratch: [B*L*C] transformed scores, then [L*C] gains, then [n_freq] spectrum
+  const int n_freq = L / 2 + 1;
+  float* xt = scratch;
+  float* gain = scratch + B * L * C;
+  float* spec = gain + (int64_t)L * C;
+  int rc;
+  if ((rc = launch_dft_apply(U, score, nullptr, nullptr, xt, B, L, C, s))) return rc;
+  if (strategy == 1) {
+    FFD_CHECK_CUDA(cudaMemsetAsync(spec, 0, sizeof(float) * n_freq, s));
+    const unsigned blocks = (unsigned)(B < 592 ? B : 592);
+    fresca_spectrum_kernel<<<blocks, 256, 0, s>>>(xt, spec, B, L, C, n_freq);
+    FFD_CHECK_LAUNCH("fresca_spectrum_kernel");
+  }
+  fresca_gain_kernel<<<1, 256, 0, s>>>(spec, gain, L, C, n_freq, low, high, cutoff_ratio, strategy,
+                                       1.0f / (float)(B * C));
+  FFD_CHECK_LAUNCH("fresca_gain_kernel");
+  return launch_dft_apply(V, xt, gain, nullptr, out, B, L, C, s);
+}
+
 }  // namespace ffd

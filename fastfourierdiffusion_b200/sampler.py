@@ -36,8 +36,6 @@ class DiffusionSampler:
         self.use_cache = use_cache
         if use_cache:
             self.score_model.enable_caching(**(cache_kwargs or {}))
-        if use_fresca:
-            raise NotImplementedError("FreSca score filtering (fresca.py) is a 'next' row (SURVEY 8f), not built yet")
         self.use_fresca = use_fresca
         self.fresca_low_scale = fresca_low_scale
         self.fresca_high_scale = fresca_high_scale
@@ -53,8 +51,9 @@ class DiffusionSampler:
 
     # -- single step (API parity; the fused loop below does not go through here) --------
     def reverse_diffusion_step(self, batch: DiffusableBatch, step: int = 0,
-                               recompute_tokens: Optional[Set[int]] = None) -> torch.Tensor:
-        """sampler.py:48-103."""
+                               recompute_tokens: Optional[Set[int]] = None,
+                               noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """sampler.py:48-103.  ``noise`` (extra, optional) injects z instead of drawing ``randn_like``."""
         X, timesteps = batch.X, batch.timesteps
         assert timesteps is not None and timesteps.size(0) == len(batch)
         assert torch.min(timesteps) == torch.max(timesteps)
@@ -66,7 +65,15 @@ class DiffusionSampler:
                 model.cache.current_step = step
         else:
             score = model(batch)
-        out = self.noise_scheduler.step(model_output=score, timestep=timesteps[0].item(), sample=X)
+        if self.use_fresca:  # sampler.py:79-93
+            from .fresca import apply_fresca_to_score
+
+            strategy = "energy" if self.fresca_cutoff_strategy == "energy" else "spatial"
+            score = apply_fresca_to_score(score, low_scale=self.fresca_low_scale, high_scale=self.fresca_high_scale,
+                                          cutoff_ratio=self.fresca_cutoff_ratio, cutoff_strategy=strategy,
+                                          timestep=timesteps[0].item(),
+                                          num_steps=getattr(self, "_num_diffusion_steps", None))
+        out = self.noise_scheduler.step(model_output=score, timestep=timesteps[0].item(), sample=X, noise=noise)
         return out.prev_sample
 
     # -- the loop ---------------------------------------------------------------------------
@@ -88,7 +95,10 @@ class DiffusionSampler:
                 if self.use_cache and model.cache is not None and batch_idx == 0:
                     model.cache.reset()
                     global_step = 0
-                X = self.run_steps(X, global_step, batch_idx=batch_idx)
+                if self.use_fresca:
+                    X = self.run_steps_unfused(X, global_step)
+                else:
+                    X = self.run_steps(X, global_step, batch_idx=batch_idx)
                 global_step += n_steps
                 all_samples.append(X.cpu())
         return torch.cat(all_samples, dim=0)
@@ -106,6 +116,27 @@ class DiffusionSampler:
     def _stream_base(self, batch_idx: int) -> int:
         # one Philox stream per (batch, step): stream 0 of a batch is its prior
         return batch_idx * (1 << 32)
+
+    def run_steps_unfused(self, X: torch.Tensor, global_step0: int = 0,
+                          noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The reference's own per-step loop (sampler.py:157-210) over ``reverse_diffusion_step``: used when the
+        FreSca filter sits between the score model and the SDE update.  Still no host synchronisation beyond
+        the ``.item()`` calls the mirrored API makes on host-side tensors."""
+        model = self.score_model
+        dev = model.device
+        X = X.to(device=dev, dtype=torch.float32).contiguous()
+        cache = model.cache if (self.use_cache and model.cache is not None) else None
+        for step_idx, t in enumerate(self.noise_scheduler.timesteps.tolist()):
+            timesteps = torch.full((X.shape[0],), t, dtype=torch.float32, device=dev)
+            batch = DiffusableBatch(X=X, y=None, timesteps=timesteps)
+            recompute = None
+            gs = global_step0 + step_idx
+            if cache is not None:
+                cache.current_step = gs
+                recompute = cache.determine_recompute_set(x_tilde=None, event_intensity=0.1, step=gs)
+            X = self.reverse_diffusion_step(batch, step=step_idx, recompute_tokens=recompute,
+                                            noise=None if noise is None else noise[step_idx])
+        return X
 
     def step_tables(self, global_step0: int):
         """Per-step host tables for one batch: SDE scalars, |recompute set|, CRF-store flag."""

@@ -7,6 +7,7 @@
  * bind (ctypes) underneath that function:
  *
  *   ffd_dft_matrix / ffd_dft_apply   src/fdiff/utils/fourier.py:8-52 (dft), :55-94 (idft)
+ *   ffd_fresca                       src/fdiff/utils/fresca.py:111-268 (apply_fresca_to_score)
  *   ffd_posemb_renorm                src/fdiff/models/transformer.py:13-15,26-28 (Embedding max_norm)
  *   ffd_time_embedding               src/fdiff/models/transformer.py:77-91 (GaussianFourierProjection)
  *   ffd_score_forward                src/fdiff/models/score_models.py:79-194 (ScoreModule.forward,
@@ -94,6 +95,14 @@ int ffd_dft_matrix(float* out, int L, int inverse, ffd_stream_t stream);
  * (cmd/sample.py:107-113 de-standardise + idft fused) */
 int ffd_dft_apply(const float* T, const float* x, const float* scale, const float* shift, float* y,
                   int64_t B, int L, int C, ffd_stream_t stream);
+
+/* FreSca score filter (src/fdiff/utils/fresca.py:111-268, called from sampler.py:79-93): rfft along L, low band
+ * scaled by low_scale, high band by high_scale, irfft.  U / V = ffd_dft_matrix(L, 0 / 1).  strategy 0 = "spatial"
+ * cut-off (k <= cutoff_ratio * n_freq), 1 = "energy" (first bin whose cumulative batch-mean magnitude reaches
+ * cutoff_ratio of the total; decided on the device, no host sync).  scratch: ffd_fresca_scratch_floats floats. */
+int64_t ffd_fresca_scratch_floats(int64_t B, int L, int C);
+int ffd_fresca(const float* U, const float* V, const float* score, float* out, float* scratch, int64_t B, int L, int C,
+               float low_scale, float high_scale, float cutoff_ratio, int strategy, ffd_stream_t stream);
 
 /* ---- embeddings (transformer.py) ---------------------------------------- */
 int ffd_posemb_renorm(float* table, int L, int d, float max_norm, ffd_stream_t stream);

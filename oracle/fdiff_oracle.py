@@ -548,6 +548,46 @@ class OracleSampler:
 
 
 # --------------------------------------------------------------------------- #
+# FreSca score filter  (src/fdiff/utils/fresca.py)
+# --------------------------------------------------------------------------- #
+
+
+def fresca_cutoff(spec: np.ndarray, cutoff_ratio: float, strategy: str) -> int:
+    """Largest low-band bin index Rc (fresca.py:38-60)."""
+    n_freq = spec.shape[0]
+    if strategy == "spatial":
+        lim = np.float32(cutoff_ratio * n_freq)
+        ks = [k for k in range(n_freq) if np.float32(k) <= lim]
+        return ks[-1] if ks else -1
+    etot = float(np.float32(spec.astype(np.float32).sum(dtype=np.float32)))
+    cum = 0.0
+    for i in range(n_freq):
+        cum += float(spec[i])
+        if cum >= cutoff_ratio * etot:
+            return i
+    return 0
+
+
+def apply_fresca_to_score(score: np.ndarray, low_scale: float = 1.0, high_scale: float = 1.0,
+                          cutoff_ratio: float = 0.5, cutoff_strategy: str = "energy",
+                          timestep: Optional[float] = None, num_steps: Optional[int] = None) -> np.ndarray:
+    """fresca.py:213-268 + frequency_scale :111-183 for score[B, L, C]."""
+    h = high_scale
+    if timestep is not None and num_steps is not None and high_scale > 1.0:
+        tn = timestep / num_steps if num_steps > 0 else 0.0
+        h = (1.0 - tn) * (high_scale - 1.0) + 1.0
+    if low_scale == 1.0 and h == 1.0:
+        return score
+    L = score.shape[1]
+    xf = np.fft.rfft(score.astype(np.float64), axis=1, norm="ortho")
+    spec = np.abs(xf).astype(np.float32).mean(axis=(0, 2))
+    rc = fresca_cutoff(spec, cutoff_ratio, cutoff_strategy)
+    low = (np.arange(xf.shape[1]) <= rc).astype(np.float64)[None, :, None]
+    xf = (low_scale * low + h * (1.0 - low)) * xf
+    return np.fft.irfft(xf, n=L, axis=1, norm="ortho").astype(score.dtype)
+
+
+# --------------------------------------------------------------------------- #
 # Counter-based noise (the product's throughput-mode generator) restated
 # --------------------------------------------------------------------------- #
 

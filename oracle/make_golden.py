@@ -124,6 +124,35 @@ def main() -> None:
         d[f"idft_{L}"] = ref.idft(x).numpy()
     np.savez_compressed(os.path.join(OUT, "fourier.npz"), **d)
 
+    # ---- FreSca score filter (fresca.py) ---------------------------------------
+    sys.path.insert(0, os.path.join(rh.REFERENCE_ROOT, "src"))
+    from fdiff.utils.fresca import apply_fresca_to_score  # type: ignore
+
+    g3 = torch.Generator().manual_seed(3)
+    d = {}
+    for L, C in ((187, 1), (100, 3), (24, 5)):
+        x = torch.randn(6, L, C, generator=g3) * (1.0 + torch.arange(L).float()[None, :, None] / L)
+        d[f"x_{L}"] = x.numpy()
+        for strat in ("spatial", "energy"):
+            for tag, kw in (("a", dict(low_scale=1.0, high_scale=1.5, cutoff_ratio=0.5, timestep=0.37, num_steps=1000)),
+                            ("b", dict(low_scale=0.8, high_scale=1.2, cutoff_ratio=0.3)),
+                            ("c", dict(low_scale=1.3, high_scale=0.9, cutoff_ratio=0.7, timestep=0.9, num_steps=20))):
+                d[f"y_{L}_{strat}_{tag}"] = apply_fresca_to_score(x, cutoff_strategy=strat, **kw).numpy()
+    np.savez_compressed(os.path.join(OUT, "fresca.npz"), **d)
+    m = rh.build_reference_model(ref, seed=11, sde="vp", fourier_noise_scaling=True, max_len=16, n_channels=2,
+                                 d_model=12, num_layers=2, n_head=2)
+    zlog, slog = [], []
+    smp = ref.DiffusionSampler(m, sample_batch_size=3, use_cache=True, cache_kwargs=dict(K=2, R=100), use_fresca=True,
+                               fresca_low_scale=1.0, fresca_high_scale=1.5, fresca_cutoff_ratio=0.5,
+                               fresca_cutoff_strategy="energy")
+    with rh.record_randn(zlog), rh.record_steps(smp, slog):
+        Xf = smp.sample(3, 12)
+    np.savez_compressed(os.path.join(OUT, "tiny_fresca_cache.npz"), final=Xf.numpy(), prior_z=zlog[0].numpy(),
+                        step_z=np.stack([z.numpy() for z in zlog[1:]]),
+                        timesteps=m.noise_scheduler.timesteps.numpy(),
+                        keep_X=np.stack([e["X"].numpy() for e in slog]),
+                        keep_Xn=np.stack([e["Xn"].numpy() for e in slog]))
+
     # ---- tiny model: weights stored ------------------------------------------
     tiny = dict(max_len=16, n_channels=2, d_model=12, num_layers=2, n_head=2)
     for tag, sde, fns, skw in (("vp_freq", "vp", True, {}), ("ve_freq", "ve", True, {"sigma_max": 2.0}),

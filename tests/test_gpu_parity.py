@@ -458,3 +458,50 @@ def test_other_shapes_against_oracle(prec, shape):
         want, wcrf = om.forward_cached(X + np.float32(0.02 * i), t, list(S), store)
         assert rel(score.cpu().numpy(), want) < tol, i
         assert rel(crf.cpu().numpy(), wcrf) < tol, i
+
+
+@pytest.mark.parametrize("L", [187, 100, 24])
+@pytest.mark.parametrize("strat", ["spatial", "energy"])
+def test_fresca_filter_against_reference_vectors(L, strat):
+    """apply_fresca_to_score (fresca.py:213-268): both cut-off strategies, odd/even L, time-dependent h."""
+    import fastfourierdiffusion_b200 as F
+
+    g = load_golden("fresca.npz")
+    kws = {"a": dict(low_scale=1.0, high_scale=1.5, cutoff_ratio=0.5, timestep=0.37, num_steps=1000),
+           "b": dict(low_scale=0.8, high_scale=1.2, cutoff_ratio=0.3),
+           "c": dict(low_scale=1.3, high_scale=0.9, cutoff_ratio=0.7, timestep=0.9, num_steps=20)}
+    x = torch.from_numpy(g[f"x_{L}"]).cuda()
+    for tag, kw in kws.items():
+        got = F.apply_fresca_to_score(x, cutoff_strategy=strat, **kw)
+        assert rel(got.cpu().numpy(), g[f"y_{L}_{strat}_{tag}"]) < 5e-6, (L, strat, tag)
+    assert F.apply_fresca_to_score(x, 1.0, 1.0) is x  # no-op short cut (fresca.py:134-135)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_tiny_sampler_trace_with_fresca(prec):
+    """DiffusionSampler(use_fresca=True) with the cache on, teacher-forced per step against the reference."""
+    import fastfourierdiffusion_b200 as F
+
+    m = build_tiny_model(precision=prec)
+    _skip_unless(prec, m)
+    g = load_golden("tiny_fresca_cache.npz")
+    s = F.DiffusionSampler(m, 3, use_cache=True, cache_kwargs=dict(K=2, R=100), use_fresca=True,
+                           fresca_low_scale=1.0, fresca_high_scale=1.5, fresca_cutoff_ratio=0.5,
+                           fresca_cutoff_strategy="energy")
+    n = g["step_z"].shape[0]
+    s._num_diffusion_steps = n
+    m.noise_scheduler.set_timesteps(n)
+    m.cache.reset()
+    for i, t in enumerate(m.noise_scheduler.timesteps.tolist()):
+        X = torch.from_numpy(g["keep_X"][i]).cuda()
+        ts = torch.full((3,), t, dtype=torch.float32, device="cuda")
+        m.cache.current_step = i
+        S = m.cache.determine_recompute_set(None, 0.1, i)
+        Xn = s.reverse_diffusion_step(F.DiffusableBatch(X=X, timesteps=ts), step=i, recompute_tokens=S,
+                                      noise=torch.from_numpy(g["step_z"][i]).cuda())
+        assert rel(Xn.cpu().numpy(), g["keep_Xn"][i]) < TOL[prec]["step"], i
+    # free run through the public loop
+    X0 = m.noise_scheduler.prior_from_noise(torch.from_numpy(g["prior_z"]))
+    m.cache.reset()
+    out = s.run_steps_unfused(X0, 0, noise=torch.from_numpy(g["step_z"]).cuda())
+    assert rel(out.cpu().numpy(), g["final"]) < TOL[prec]["traj"]

@@ -151,3 +151,17 @@ def test_torch_port_matches_reference_vectors(tiny_weights):
                 assert rel(X.numpy(), g["keep_X"][keep[i]]) < 2e-4, i
             X = port.step(X, float(ts[i]), torch.from_numpy(g["step_z"][0][i]), dt, recompute_set(i, 2, 100, 16))
     assert port.k_cache is not None and rel(X.numpy(), g["final"][:3]) < 5e-4
+
+
+FRESCA_KW = {"a": dict(low_scale=1.0, high_scale=1.5, cutoff_ratio=0.5, timestep=0.37, num_steps=1000),
+             "b": dict(low_scale=0.8, high_scale=1.2, cutoff_ratio=0.3),
+             "c": dict(low_scale=1.3, high_scale=0.9, cutoff_ratio=0.7, timestep=0.9, num_steps=20)}
+
+
+@pytest.mark.parametrize("L", [187, 100, 24])
+@pytest.mark.parametrize("strat", ["spatial", "energy"])
+def test_fresca_oracle_matches_reference(L, strat):
+    g = load_golden("fresca.npz")
+    for tag, kw in FRESCA_KW.items():
+        got = O.apply_fresca_to_score(g[f"x_{L}"], cutoff_strategy=strat, **kw)
+        assert rel(got, g[f"y_{L}_{strat}_{tag}"]) < 2e-6, (L, strat, tag)
