@@ -76,6 +76,14 @@ static inline Arena arena_of(const ffd_dims& m) {
   return a;
 }
 
+// ---- key chunking of the tcgen05 attention kernel (ffd_tc_attn.cu) ---------------
+// The cached keys of a head are processed in NCH chunks of CK keys (CK a multiple of 64, at most 192).
+static inline int attn_key_chunks(int L) { return (L + 191) / 192; }
+static inline int attn_chunk_keys(int L) {
+  const int n = attn_key_chunks(L);
+  return ((L + n - 1) / n + 63) / 64 * 64;
+}
+
 // ---- workspace carve-up --------------------------------------------------------
 struct Workspace {
   float* h;     // [M, d] residual stream
@@ -102,8 +110,8 @@ static inline Workspace carve(const ffd_dims& m, int64_t B, void* base) {
   w.attn = take(M * d);
   w.qkv = take(M * 3 * d);
   w.kvtmp = take((int64_t)m.max_len * 2 * d);
-  // [NL, H] x (K image [NKV x 16] + V image [16 x NKV]) bf16, NKV = ceil64(L)
-  w.kvimg = take((int64_t)m.n_layers * m.n_head * (((m.max_len + 63) / 64 * 64) * 16 + 1));
+  // [NL, H, NCH] x (K image [CK x 16] bf16 + V image [16 x CK] fp16)
+  w.kvimg = take((int64_t)m.n_layers * m.n_head * attn_key_chunks(m.max_len) * attn_chunk_keys(m.max_len) * 16);
   w.bytes = o;
   return w;
 }

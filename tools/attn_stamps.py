@@ -1,3 +1,4 @@
+"""Cycle timeline of one token tile of the attention kernel (build with FFD_NVCC_FLAGS=-DFFD_ATTN_STAMPS)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -19,11 +20,13 @@ torch.cuda.synchronize()
 lib.ffd_debug_set_attn_stamps(None)
 t = buf.cpu().numpy()
 t0 = t[t > 0].min()
-print("MMA thread per head: p_full, o_empty, v_full, PV issued, S issued (cycles from t0)")
-for h in range(12): print(h, [int(v - t0) if v else None for v in t[h*8:h*8+5]])
-print("softmax warp 2 per head: s_full, collected, pass1 done, barrier passed, p_full arrive")
-for h in range(12): print(h, [int(v - t0) if v else None for v in t[128+h*8:128+h*8+5]])
-print("collect_o (warp 2): after o_full wait, after ld")
-for h in range(12): print(h, [int(v - t0) if v else None for v in t[256+h*4:256+h*4+3]])
-print("tile phases (warp 2): loop start, t_full, prev out_full, x staged, q_full, qbf arrive | obf arrive, LN start (warp 10 = group 2), LN done, store read")
-print([int(v - t0) if v else None for v in t[300:310]])
+f = lambda v: int(v - t0) if v else None
+NV = 12
+print("MMA warp per head: p_full seen, PV issued, S issued, slots done (cycles from t0)")
+for h in range(NV): print(h, [f(v) for v in t[h*4:h*4+4]])
+print("softmax warp 12 per head: loop top, before next s_full wait, after it, p_full arrive")
+for h in range(NV): print(h, [f(v) for v in t[128+h*4:128+h*4+4]])
+print("read-out warp 4 per head: o_full seen, o_empty arrive")
+for h in range(NV): print(h, [f(v) for v in t[256+h*2:256+h*2+2]])
+print("tile warp 8 (phase 2): start, finish(1) done, prepare(3) done | prepare(3): x staged, t_full seen")
+print([f(v) for v in t[400:405]])
