@@ -171,6 +171,10 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // provably warp-uniform
 
+  // register budget per warpgroup (896 threads x 72 at launch): the softmax warps hold two heads' scores
+  // (set at the top of each role branch so that ptxas allocates per branch)
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // ================= K/V image producer =================
     if (lane == 0) {
@@ -327,8 +331,8 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     mbar_wait(obf_full, (my_tiles - 1) & 1);
     for (int j = 0; j < NPO; ++j) o_pass(j);
     mbar_wait(obf_empty, (my_tiles - 1) & 1);  // drain: nothing of this warp is in flight when the CTA exits
-  } else if (warp == 3) {
-    // ================= P.V MMAs =================
+  } else {
+    // ================= P.V MMAs (warp 3) =================
     constexpr uint32_t IDESC_PV = make_idesc_f16(TILE_M, HP);
     const uint32_t vring = smem_u32(smem + sm.vring);
     for (uint32_t n = 0; n < n_heads; ++n) {
@@ -356,8 +360,10 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       FFD_STAMP(n / NV == 2, 64 + (n % NV) * 2 + 1);
     }
     mbar_wait(&p_empty[(n_heads - 1) & 1], ((n_heads - 1) >> 1) & 1);  // drain
-  } else if (warp >= 4 && warp < 8) {
+  }
+  } else if (warp < 8) {
     // ================= O read-out warps =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
@@ -421,8 +427,9 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       fence_proxy_async();
       mbar_arrive(obf_full);
     }
-  } else if (warp >= 8 && warp < 12) {
+  } else if (warp < 12) {
     // ================= tile warps: prepare tile t+1 / finish tile t-1 while the heads of tile t run ==========
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
@@ -469,32 +476,26 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         mbar_wait(scr_full, cs & 1);
         ++cs;
         tc_fence_after();
-        for (int u = 0; u < N; u += 32) {
-          uint32_t r[32];
+        for (int u = 0; u < N; u += 16) {
+          uint32_t r[16];
           FFD_TMEM_LD16(scr + u, r);
-          if (u + 16 < N) FFD_TMEM_LD16(scr + u + 16, (r + 16));
           tmem_ld_wait();
-          if (u + 32 >= N) {
+          if (u + 16 >= N) {
             tc_fence_before();
             mbar_arrive(scr_empty);
           }
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            if (u + 16 * i < N) {
-              uint4 q0, q1;
-              q0.x = pack_bf16(__uint_as_float(r[16 * i + 0]), __uint_as_float(r[16 * i + 1]));
-              q0.y = pack_bf16(__uint_as_float(r[16 * i + 2]), __uint_as_float(r[16 * i + 3]));
-              q0.z = pack_bf16(__uint_as_float(r[16 * i + 4]), __uint_as_float(r[16 * i + 5]));
-              q0.w = pack_bf16(__uint_as_float(r[16 * i + 6]), __uint_as_float(r[16 * i + 7]));
-              q1.x = pack_bf16(__uint_as_float(r[16 * i + 8]), __uint_as_float(r[16 * i + 9]));
-              q1.y = pack_bf16(__uint_as_float(r[16 * i + 10]), __uint_as_float(r[16 * i + 11]));
-              q1.z = pack_bf16(__uint_as_float(r[16 * i + 12]), __uint_as_float(r[16 * i + 13]));
-              q1.w = pack_bf16(__uint_as_float(r[16 * i + 14]), __uint_as_float(r[16 * i + 15]));
-              const int kg = (n0 + u + 16 * i) >> 3;
-              *reinterpret_cast<uint4*>(qb + row_off + kg * (TILE_M * 16)) = q0;
-              *reinterpret_cast<uint4*>(qb + row_off + (kg + 1) * (TILE_M * 16)) = q1;
-            }
-          }
+          uint4 q0, q1;
+          q0.x = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));
+          q0.y = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
+          q0.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));
+          q0.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
+          q1.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));
+          q1.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
+          q1.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13]));
+          q1.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
+          const int kg = (n0 + u) >> 3;
+          *reinterpret_cast<uint4*>(qb + row_off + kg * (TILE_M * 16)) = q0;
+          *reinterpret_cast<uint4*>(qb + row_off + (kg + 1) * (TILE_M * 16)) = q1;
         }
       }
       fence_proxy_async();
@@ -510,19 +511,18 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         mbar_wait(scr_full, cs & 1);
         ++cs;
         tc_fence_after();
-        for (int u = 0; u < N; u += 32) {
-          uint32_t r[32];
+        for (int u = 0; u < N; u += 16) {
+          uint32_t r[16];
           FFD_TMEM_LD16(scr + u, r);
-          if (u + 16 < N) FFD_TMEM_LD16(scr + u + 16, (r + 16));
           tmem_ld_wait();
-          if (u + 32 >= N) {
+          if (u + 16 >= N) {
             tc_fence_before();
             mbar_arrive(scr_empty);
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             const int c = n0 + u + 4 * j;
-            if (c < d && u + 4 * j < N) {
+            if (c < d) {
               float4 v = myrow[c >> 2];
               v.x += __uint_as_float(r[4 * j]);
               v.y += __uint_as_float(r[4 * j + 1]);
@@ -558,15 +558,19 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       FFD_STAMP(warp == 8 && t == 2, 402);
     }
     finish(my_tiles - 1);
-  } else if (warp >= 12) {
+  } else {
     // ================= softmax groups: heads and nothing else =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     const int wg = (warp - 12) >> 2;       // 0..3: quarter of the key columns
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t scol = tmem_base + lane_base + COL_S + wg * NQ;  // this group's score columns
     const uint32_t pcol0 = tmem_base + lane_base + COL_P0 + wg * NP;  // ... and its packed P columns
-    uint32_t r[16 * KQ];
+    // KQ + 1 groups of 16 score registers: the current head's KQ chunks and one spare group, so that ALL of the
+    // next head's scores can be loaded (and the score buffer released) while this head's last chunk is still in
+    // use.  The last chunk and the spare group swap roles from one head to the next (loop unrolled by two).
+    uint32_t r[16 * (KQ + 1)];
     auto chunk_max = [&](int j, float m) {
 #pragma unroll
       for (int e = 0; e < 16; e += 2) m = max3(m, __uint_as_float(r[16 * j + e]), __uint_as_float(r[16 * j + e + 1]));
@@ -583,60 +587,64 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     float mb = -INFINITY;
 #pragma unroll
     for (int j = 0; j < KQ; ++j) mb = chunk_max(j, mb);
-    for (uint32_t n = 0; n < n_heads; ++n) {
-      const uint32_t b = n & 1;
-      const uint32_t pcol = pcol0 + b * (COL_P1 - COL_P0);
-      const bool has_next = n + 1 < n_heads;
-      const float mc = mb;
-      // p = exp2(s - m_q) as fp16 pairs with m_q the row maximum over THIS group's quarter of the keys: 16 score
-      // columns -> 8 packed columns.  Padded keys need no mask: slot 15 of every Q tile is the constant 1 and
-      // slot 15 of a padded K row is -29952 (a quarter made only of padding gets m_q = -29952 and weight
-      // exp2(m_q - max) = 0 in the combine).
-      mq[((n & 3) * 4 + wg) * TILE_M + row] = mc;
-      FFD_STAMP(warp == 12 && n / NV == 2, 128 + (n % NV) * 4 + 0);
-      mbar_wait(&p_empty[b], ((n >> 1) & 1) ^ 1);  // the P.V MMA two heads back has read this P buffer
-      tc_fence_after();
-      uint32_t pk[8];
-#pragma unroll
-      for (int j = 0; j < KQ - 1; ++j) {
-#pragma unroll
-        for (int e = 0; e < 16; e += 2)
-          pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[16 * j + e]) - mc, __uint_as_float(r[16 * j + e + 1]) - mc);
-        FFD_TMEM_ST8(pcol + 8 * j, pk);
-      }
-      // the next virtual head's scores replace the consumed registers while this head's last exponentials are
-      // still queued on the MUFU pipe
-      if (has_next) {
-        FFD_STAMP(warp == 12 && n / NV == 2, 128 + (n % NV) * 4 + 1);
-        mbar_wait(s_full, (n + 1) & 1);
-        tc_fence_after();
-        FFD_STAMP(warp == 12 && n / NV == 2, 128 + (n % NV) * 4 + 2);
-#pragma unroll
-        for (int j = 0; j < KQ - 1; ++j) FFD_TMEM_LD16(scol + 16 * j, (r + 16 * j));
-      }
-#pragma unroll
-      for (int e = 0; e < 16; e += 2)
-        pk[e >> 1] = ex2_pack_f16(__uint_as_float(r[16 * (KQ - 1) + e]) - mc,
-                                  __uint_as_float(r[16 * (KQ - 1) + e + 1]) - mc);
-      float mn = -INFINITY;
-      if (has_next && KQ > 1) {
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < KQ - 1; ++j) mn = chunk_max(j, mn);
-      }
-      FFD_TMEM_ST8(pcol + 8 * (KQ - 1), pk);
-      if (has_next) FFD_TMEM_LD16(scol + 16 * (KQ - 1), (r + 16 * (KQ - 1)));
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_full[b]);
-      FFD_STAMP(warp == 12 && n / NV == 2, 128 + (n % NV) * 4 + 3);
-      if (has_next) {
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(s_empty);  // the score buffer may be overwritten
-        mb = chunk_max(KQ - 1, mn);
-      }
+    // p = exp2(s - m_q) as fp16 pairs with m_q the row maximum over THIS group's quarter of the keys: 16 score
+    // columns -> 8 packed columns.  Padded keys need no mask: slot 15 of every Q tile is the constant 1 and slot
+    // 15 of a padded K row is -29952 (a quarter made only of padding gets m_q = -29952 and weight
+    // exp2(m_q - max) = 0 in the combine).
+#define FFD_EXP16(G_, mc_, pk_)                                                                   \
+  _Pragma("unroll") for (int e = 0; e < 16; e += 2)                                               \
+      pk_[e >> 1] = ex2_pack_f16(__uint_as_float(r[16 * (G_) + e]) - (mc_), __uint_as_float(r[16 * (G_) + e + 1]) - (mc_))
+#define FFD_SOFTMAX_HEAD(LAST, SPARE, n_)                                                          \
+  {                                                                                               \
+    const uint32_t n = (n_);                                                                      \
+    const uint32_t b = n & 1;                                                                     \
+    const uint32_t pcol = pcol0 + b * (COL_P1 - COL_P0);                                          \
+    const bool has_next = n + 1 < n_heads;                                                        \
+    const float mc = mb;                                                                          \
+    mq[((n & 3) * 4 + wg) * TILE_M + row] = mc;                                                   \
+    FFD_STAMP(warp == 12 && n / NV == 2, 128 + (n % NV) * 4 + 0);                                 \
+    uint32_t pk[8];                                                                               \
+    _Pragma("unroll") for (int j = 0; j < KQ - 1; ++j) {                                          \
+      FFD_EXP16(j, mc, pk);                                                                       \
+      if (j == 0) {                                                                               \
+        mbar_wait(&p_empty[b], ((n >> 1) & 1) ^ 1); /* the P.V MMA two heads back has read this buffer */ \
+        tc_fence_after();                                                                         \
+      }                                                                                           \
+      FFD_TMEM_ST8(pcol + 8 * j, pk);                                                             \
+    }                                                                                             \
+    if (has_next) {                                                                               \
+      FFD_STAMP(warp == 12 && n / NV == 2, 128 + (n % NV) * 4 + 1);                               \
+      mbar_wait(s_full, (n + 1) & 1);                                                             \
+      tc_fence_after();                                                                           \
+      FFD_STAMP(warp == 12 && n / NV == 2, 128 + (n % NV) * 4 + 2);                               \
+      _Pragma("unroll") for (int j = 0; j < KQ - 1; ++j) FFD_TMEM_LD16(scol + 16 * j, (r + 16 * j)); \
+      FFD_TMEM_LD16(scol + 16 * (KQ - 1), (r + 16 * (SPARE)));                                    \
+    }                                                                                             \
+    FFD_EXP16(LAST, mc, pk);                                                                      \
+    if (has_next) {                                                                               \
+      tmem_ld_wait();                                                                             \
+      tc_fence_before();                                                                          \
+      mbar_arrive(s_empty); /* the score buffer may be overwritten */                             \
+      mb = -INFINITY;                                                                             \
+      _Pragma("unroll") for (int j = 0; j < KQ - 1; ++j) mb = chunk_max(j, mb);                   \
+      mb = chunk_max(SPARE, mb);                                                                  \
+    }                                                                                             \
+    if (KQ == 1) {                                                                                \
+      mbar_wait(&p_empty[b], ((n >> 1) & 1) ^ 1);                                                 \
+      tc_fence_after();                                                                           \
+    }                                                                                             \
+    FFD_TMEM_ST8(pcol + 8 * (KQ - 1), pk);                                                        \
+    tmem_st_wait();                                                                               \
+    tc_fence_before();                                                                            \
+    mbar_arrive(&p_full[b]);                                                                      \
+    FFD_STAMP(warp == 12 && n / NV == 2, 128 + (n % NV) * 4 + 3);                                 \
+  }
+    for (uint32_t n2 = 0; n2 < n_heads; n2 += 2) {
+      FFD_SOFTMAX_HEAD(KQ - 1, KQ, n2);
+      if (n2 + 1 < n_heads) FFD_SOFTMAX_HEAD(KQ, KQ - 1, n2 + 1);
     }
+#undef FFD_SOFTMAX_HEAD
+#undef FFD_EXP16
   }
 
   tc_fence_before();

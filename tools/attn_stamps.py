@@ -22,8 +22,10 @@ t = buf.cpu().numpy()
 t0 = t[t > 0].min()
 f = lambda v: int(v - t0) if v else None
 NV = 12
-print("MMA warp per head: p_full seen, PV issued, S issued, slots done (cycles from t0)")
-for h in range(NV): print(h, [f(v) for v in t[h*4:h*4+4]])
+print("score warp per S issued: S issued, slots done (cycles from t0)")
+for h in range(NV): print(h, [f(v) for v in t[h*2:h*2+2]])
+print("P.V warp per head: p_full seen, PV issued")
+for h in range(NV): print(h, [f(v) for v in t[64+h*2:64+h*2+2]])
 print("softmax warp 12 per head: loop top, before next s_full wait, after it, p_full arrive")
 for h in range(NV): print(h, [f(v) for v in t[128+h*4:128+h*4+4]])
 print("read-out warp 4 per head: o_full seen, o_empty arrive")
