@@ -108,10 +108,8 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
   uint64_t* w_full = v_empty + V_STAGES;         // [1] tx (Wq + Wo, once)
   uint64_t* t_full = w_full + 1;                 // [2] tx: fp32 tile landed
   uint64_t* y_ready = t_full + 2;                // [2] 128 arrivals: LayerNorm output written to the tile buffer
-  uint64_t* x_full = y_ready + 2;                // [1] 128 arrivals: bf16 X staged
-  uint64_t* scr_full = x_full + 1;               // [1] commit: a scratch pass has been computed
-  uint64_t* scr_empty = scr_full + 1;            // [1] 128 arrivals: the tile warps have read it
-  uint64_t* qbf_full = scr_empty + 1;            // [2] 128 arrivals: bf16 Q tiles of a token tile written
+  uint64_t* scr_full = y_ready + 2;              // [1] commit: a scratch pass has been computed
+  uint64_t* qbf_full = scr_full + 1;             // [2] 128 arrivals: bf16 Q tiles of a token tile written
   uint64_t* s_full = qbf_full + 2;               // [1] commit: scores of a virtual head computed
   uint64_t* s_empty = s_full + 1;                // [1] 512 arrivals: every softmax warp holds them in registers
   uint64_t* p_full = s_empty + 1;                // [2] 512 arrivals (all four groups)
@@ -150,9 +148,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       mbar_init(&p_full[b], 512);
       mbar_init(&p_empty[b], 1);
     }
-    mbar_init(x_full, 128);
     mbar_init(scr_full, 1);
-    mbar_init(scr_empty, 128);
     mbar_init(s_full, 1);
     mbar_init(s_empty, 512);
     mbar_init(o_full, 1);
@@ -185,14 +181,14 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       const size_t img_stride = (size_t)sm.k_bytes + sm.v_bytes;
       auto load_k = [&](uint32_t v) {
         const uint32_t st = nk % K_STAGES, u = nk / K_STAGES;
-        mbar_wait(&k_empty[st], (u & 1) ^ 1);
+        mbar_wait_relaxed(&k_empty[st], (u & 1) ^ 1, 200);
         mbar_expect_tx(&k_full[st], sm.k_bytes);
         bulk_load(smem + sm.kring + st * sm.k_bytes, kvimg + v * img_stride, sm.k_bytes, &k_full[st]);
         ++nk;
       };
       auto load_v = [&](uint32_t v) {
         const uint32_t st = nv % V_STAGES, u = nv / V_STAGES;
-        mbar_wait(&v_empty[st], (u & 1) ^ 1);
+        mbar_wait_relaxed(&v_empty[st], (u & 1) ^ 1, 200);
         mbar_expect_tx(&v_full[st], sm.v_bytes);
         bulk_load(smem + sm.vring + st * sm.v_bytes, kvimg + v * img_stride + sm.k_bytes, sm.v_bytes, &v_full[st]);
         ++nv;
@@ -236,54 +232,15 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       bulk_wait_all();
     }
   } else if (warp == 1) {
-    // ================= score MMAs + scratch passes (whole warp converged, one elected lane issues) ===========
+    // ================= score MMAs (whole warp converged, one elected lane issues) ===========
     const uint32_t idesc_s = make_idesc(TILE_M, CK);
     constexpr uint32_t LBO128 = 128 * 16;
-    const uint32_t xo = smem_u32(smem + sm.xo), obf = smem_u32(smem + sm.obf), qbf = smem_u32(smem + sm.qbf);
-    const uint32_t wq = smem_u32(smem + sm.wq), wo = smem_u32(smem + sm.wo);
+    const uint32_t qbf = smem_u32(smem + sm.qbf);
     const uint32_t kring = smem_u32(smem + sm.kring);
-    constexpr int NPO = (DP + SCR_COLS - 1) / SCR_COLS;   // out-projection passes
-    const int NPQ = (QN + SCR_COLS - 1) / SCR_COLS;       // Q projection passes
-    uint32_t cs = 0;  // scratch passes issued
-    // one pass (<= 64 accumulator columns) of the Q projection of the staged X
-    auto q_pass = [&](int j) {
-      const int n0 = j * SCR_COLS;
-      const int N = QN - n0 < SCR_COLS ? QN - n0 : SCR_COLS;
-      mbar_wait(scr_empty, (cs & 1) ^ 1);
-      tc_fence_after();
-      umma_ss_chain<DP / 16>(tmem_base + COL_SCR, make_desc(xo, LBO128, 128), (2 * LBO128) >> 4,
-                             make_desc(wq + (n0 >> 3) * 128, QN * 16, 128), (2 * QN * 16) >> 4,
-                             make_idesc(TILE_M, N), 0);
-      umma_commit(scr_full);
-      ++cs;
-    };
-    // one pass of the out-projection (A operand: the normalised O columns written by the read-out warps)
-    auto o_pass = [&](int j) {
-      const int n0 = j * SCR_COLS;
-      const int N = DP - n0 < SCR_COLS ? DP - n0 : SCR_COLS;
-      mbar_wait(scr_empty, (cs & 1) ^ 1);
-      tc_fence_after();
-      umma_ss_chain<DP / 16>(tmem_base + COL_SCR, make_desc(obf, LBO128, 128), (2 * LBO128) >> 4,
-                             make_desc(wo + (n0 >> 3) * 128, DP * 16, 128), (2 * DP * 16) >> 4,
-                             make_idesc(TILE_M, N), 0);
-      umma_commit(scr_full);
-      ++cs;
-      if (j == NPO - 1) umma_commit(obf_empty);
-    };
-    // Scratch work of the neighbouring tiles rides on this tile's score issues, one pass per virtual head, where
-    // its inputs are ready without waiting: out-proj of tile t-1 from head vO on, Q projection of tile t+1 from
-    // head vQ on.  With too few virtual heads per tile all passes are issued (and waited for) at head 1.
-    const bool spread = NV >= NPO + NPQ + 6;
-    const int vO = spread ? 2 : 1;
-    const int vQ = spread ? NV - 4 - NPQ : 1;
-    mbar_wait(w_full, 0);
-    mbar_wait(x_full, 0);
-    for (int j = 0; j < NPQ; ++j) q_pass(j);
-    // S_0
     uint32_t t = 0, nk = 0;
     int v = 0, c = 0, g = 0, qt = 0;  // position of the score MMA being issued: tile, virtual head, chunk, place
     for (uint32_t m = 0; m < n_heads; ++m) {
-      if (m > 0) mbar_wait(s_empty, (m - 1) & 1);  // all softmax warps hold S_{m-1} in registers
+      if (m > 0) mbar_wait_relaxed(s_empty, (m - 1) & 1, 40);  // all softmax warps hold S_{m-1} in registers
       if (v == 0) mbar_wait(&qbf_full[t & 1], (t >> 1) & 1);  // this tile's Q tiles are in shared memory
       const uint32_t st = nk % K_STAGES;
       mbar_wait(&k_full[st], (nk / K_STAGES) & 1);
@@ -294,28 +251,6 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       umma_commit(&k_empty[st]);
       ++nk;
       FFD_STAMP(t == 2, v * 2 + 0);
-      // scratch passes
-      if (spread) {
-        if (t >= 1 && v >= vO && v < vO + NPO) {
-          if (v == vO) mbar_wait(obf_full, (t - 1) & 1);
-          o_pass(v - vO);
-        }
-        if (t + 1 < my_tiles && v >= vQ && v < vQ + NPQ) {
-          if (v == vQ) mbar_wait(x_full, (t + 1) & 1);
-          q_pass(v - vQ);
-        }
-      } else if (v == vO || NV == 1) {
-        if (t >= 1) {
-          mbar_wait(obf_full, (t - 1) & 1);
-          for (int j = 0; j < NPO; ++j) o_pass(j);
-        }
-        if (t + 1 < my_tiles) {
-          mbar_wait(x_full, (t + 1) & 1);
-          for (int j = 0; j < NPQ; ++j) q_pass(j);
-        }
-      }
-      FFD_STAMP(t == 2, v * 2 + 1);
-      // advance
       if (++c == NCH) {
         c = 0;
         if (++g == G) {
@@ -328,9 +263,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         ++t;
       }
     }
-    mbar_wait(obf_full, (my_tiles - 1) & 1);
-    for (int j = 0; j < NPO; ++j) o_pass(j);
-    mbar_wait(obf_empty, (my_tiles - 1) & 1);  // drain: nothing of this warp is in flight when the CTA exits
+    mbar_wait(s_full, (n_heads - 1) & 1);  // drain: nothing of this warp is in flight when the CTA exits
   } else {
     // ================= P.V MMAs (warp 3) =================
     constexpr uint32_t IDESC_PV = make_idesc_f16(TILE_M, HP);
@@ -338,8 +271,8 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     for (uint32_t n = 0; n < n_heads; ++n) {
       const uint32_t b = n & 1;
       const uint32_t st = n % V_STAGES;
-      mbar_wait(&p_full[b], (n >> 1) & 1);   // P_n (fp16 pairs) is complete
-      FFD_STAMP(n / NV == 2, 64 + (n % NV) * 2 + 0);
+      mbar_wait_relaxed(&p_full[b], (n >> 1) & 1, 100);   // P_n (fp16 pairs) is complete
+      FFD_STAMP(n - 2u * NV < (uint32_t)NV, 64 + (n - 2u * NV) * 2 + 0);
       mbar_wait(o_empty, (n & 1) ^ 1);       // O of the previous virtual head has been read out
       mbar_wait(&v_full[st], (n / V_STAGES) & 1);
       tc_fence_after();
@@ -357,13 +290,13 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       umma_commit(o_full);
       umma_commit(&p_empty[b]);
       umma_commit(&v_empty[st]);
-      FFD_STAMP(n / NV == 2, 64 + (n % NV) * 2 + 1);
+      FFD_STAMP(n - 2u * NV < (uint32_t)NV, 64 + (n - 2u * NV) * 2 + 1);
     }
     mbar_wait(&p_empty[(n_heads - 1) & 1], ((n_heads - 1) >> 1) & 1);  // drain
   }
   } else if (warp < 8) {
     // ================= O read-out warps =================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
@@ -379,7 +312,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         float acc[HP];
         float mrun = 0.f;
         for (int c = 0; c < NCH; ++c, ++n) {
-          mbar_wait(o_full, n & 1);
+          mbar_wait_relaxed(o_full, n & 1, 100);
           tc_fence_after();
           FFD_STAMP(warp == 4 && t == 2, 256 + (h * NCH + c) * 2 + 0);
           // combine the four quarters: weights exp2(m_q - max m_q); slot 15 of each O_q is that quarter's row sum
@@ -387,19 +320,29 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
           const float q0 = mh[0], q1 = mh[TILE_M], q2 = mh[2 * TILE_M], q3 = mh[3 * TILE_M];
           float mm = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
           if (c > 0) mm = fmaxf(mm, mrun);
-          const float w0 = exp2_fma(q0 - mm), w1 = exp2_fma(q1 - mm), w2 = exp2_fma(q2 - mm), w3 = exp2_fma(q3 - mm);
+          const float w0 = exp2_poly3(q0 - mm), w1 = exp2_poly3(q1 - mm), w2 = exp2_poly3(q2 - mm),
+                      w3 = exp2_poly3(q3 - mm);
+          // only the head's hd dims and slot 15 (the row sum) carry data: with hd <= 7 the upper half of every
+          // accumulator except its last pair is padding
+          const int jmax = hd <= 7 ? 8 : HP - 2;
+          if (c == 0) {
+#pragma unroll
+            for (int j = 0; j < HP; ++j) acc[j] = 0.f;
+          } else {
+            const float wp = exp2_poly3(mrun - mm);
+#pragma unroll
+            for (int j = 0; j < HP; ++j) acc[j] *= wp;
+          }
           uint32_t r[32];
           FFD_TMEM_LD16(tmem_base + lane_base + COL_O, r);
           FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 16, (r + 16));
           tmem_ld_wait();
-          if (c == 0) {
 #pragma unroll
-            for (int j = 0; j < HP; ++j) acc[j] = w0 * __uint_as_float(r[j]) + w1 * __uint_as_float(r[16 + j]);
-          } else {
-            const float wp = exp2_fma(mrun - mm);
-#pragma unroll
-            for (int j = 0; j < HP; ++j)
-              acc[j] = fmaf(wp, acc[j], w0 * __uint_as_float(r[j]) + w1 * __uint_as_float(r[16 + j]));
+          for (int j = 0; j < HP; j += 2) {
+            if (j < jmax || j == HP - 2) {
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[j]), __uint_as_float(r[j + 1]), w0, acc[j], acc[j + 1]);
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[16 + j]), __uint_as_float(r[17 + j]), w1, acc[j], acc[j + 1]);
+            }
           }
           FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 32, r);
           FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 48, (r + 16));
@@ -408,8 +351,12 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
           mbar_arrive(o_empty);
           FFD_STAMP(warp == 4 && t == 2, 256 + (h * NCH + c) * 2 + 1);
 #pragma unroll
-          for (int j = 0; j < HP; ++j)
-            acc[j] = fmaf(w2, __uint_as_float(r[j]), fmaf(w3, __uint_as_float(r[16 + j]), acc[j]));
+          for (int j = 0; j < HP; j += 2) {
+            if (j < jmax || j == HP - 2) {
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[j]), __uint_as_float(r[j + 1]), w2, acc[j], acc[j + 1]);
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[16 + j]), __uint_as_float(r[17 + j]), w3, acc[j], acc[j + 1]);
+            }
+          }
           mrun = mm;
         }
         const float inv = rcp_fma(acc[HP - 1]);
@@ -429,24 +376,60 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     }
   } else if (warp < 12) {
     // ================= tile warps: prepare tile t+1 / finish tile t-1 while the heads of tile t run ==========
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
     const uint32_t scr = tmem_base + lane_base + COL_SCR;
     uint8_t* xo = smem + sm.xo;
-    uint32_t cs = 0;  // scratch passes consumed
-    // stage X of local tile t as the bf16 A operand, then turn its Q projection into bf16 Q tiles
+    const bool lead = warp == 8;  // issues the scratch MMAs of the group (whole warp converged)
+    constexpr uint32_t LBO128 = 128 * 16;
+    const uint32_t xo_a = smem_u32(smem + sm.xo), obf_a = smem_u32(smem + sm.obf);
+    const uint32_t wq_a = smem_u32(smem + sm.wq), wo_a = smem_u32(smem + sm.wo);
+    uint32_t cs = 0;  // scratch passes so far
+    if (lead) mbar_wait(w_full, 0);
+    // One scratch pass: C[128 x N] = A[128 x DP] . W[n0.., :]^T into the scratch columns.  The group barrier makes
+    // the previous pass's reads (and this pass's operand writes) complete before the lead warp issues.
+    auto scratch_pass = [&](uint32_t a_addr, uint32_t w_addr, int w_rows, int n0, int N, uint64_t* also_commit) {
+      tc_fence_before();
+      named_bar_sync(1, 128);
+      if (lead) {
+        tc_fence_after();
+        umma_ss_chain<DP / 16>(tmem_base + COL_SCR, make_desc(a_addr, LBO128, 128), (2 * LBO128) >> 4,
+                               make_desc(w_addr + (n0 >> 3) * 128, w_rows * 16, 128), (2 * w_rows * 16) >> 4,
+                               make_idesc(TILE_M, N), 0);
+        umma_commit(scr_full);
+        if (also_commit) umma_commit(also_commit);
+      }
+      mbar_wait(scr_full, cs & 1);
+      ++cs;
+      tc_fence_after();
+    };
+    // 16 fp32 accumulator columns -> two bf16 k-groups of the Q operand
+    auto store_q16 = [&](const uint32_t (&r)[16], uint8_t* dst) {
+      uint4 q0, q1;
+      q0.x = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));
+      q0.y = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
+      q0.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));
+      q0.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
+      q1.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));
+      q1.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
+      q1.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13]));
+      q1.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
+      *reinterpret_cast<uint4*>(dst) = q0;
+      *reinterpret_cast<uint4*>(dst + TILE_M * 16) = q1;
+    };
+    // stage X of local tile t as the bf16 A operand, project it, and turn the result into bf16 Q tiles
     auto prepare = [&](uint32_t t) {
       const uint32_t tb = t & 1;
       const int64_t grow = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + row;
       const bool valid = grow < M;
       const float4* src = reinterpret_cast<const float4*>(smem + sm.x32 + tb * sm.tile_stride) + (size_t)row * (d / 4);
-      mbar_wait(&t_full[tb], (t >> 1) & 1);
+      mbar_wait_relaxed(&t_full[tb], (t >> 1) & 1, 200);
       FFD_STAMP(warp == 8 && t == 3, 404);
       constexpr int NG = DP / 8;
-#pragma unroll 2
+#pragma unroll 5
       for (int kg = 0; kg < NG; ++kg) {
         const int c = kg * 8;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
@@ -468,62 +451,51 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         *reinterpret_cast<uint4*>(xo + row_off + kg * (TILE_M * 16)) = q;
       }
       fence_proxy_async();
-      mbar_arrive(x_full);
       FFD_STAMP(warp == 8 && t == 3, 403);
       uint8_t* qb = smem + sm.qbf + tb * sm.qbf_bytes;
       for (int n0 = 0; n0 < QN; n0 += SCR_COLS) {
         const int N = QN - n0 < SCR_COLS ? QN - n0 : SCR_COLS;
-        mbar_wait(scr_full, cs & 1);
-        ++cs;
-        tc_fence_after();
-        for (int u = 0; u < N; u += 16) {
-          uint32_t r[16];
-          FFD_TMEM_LD16(scr + u, r);
+        scratch_pass(xo_a, wq_a, QN, n0, N, nullptr);
+        // two 16-column units in flight per TMEM round trip
+        for (int u = 0; u < N; u += 32) {
+          uint32_t ra[16], rb[16];
+          const bool two = u + 16 < N;
+          FFD_TMEM_LD16(scr + u, ra);
+          if (two) FFD_TMEM_LD16(scr + u + 16, rb);
           tmem_ld_wait();
-          if (u + 16 >= N) {
-            tc_fence_before();
-            mbar_arrive(scr_empty);
-          }
-          uint4 q0, q1;
-          q0.x = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));
-          q0.y = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
-          q0.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));
-          q0.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
-          q1.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));
-          q1.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
-          q1.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13]));
-          q1.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
           const int kg = (n0 + u) >> 3;
-          *reinterpret_cast<uint4*>(qb + row_off + kg * (TILE_M * 16)) = q0;
-          *reinterpret_cast<uint4*>(qb + row_off + (kg + 1) * (TILE_M * 16)) = q1;
+          store_q16(ra, qb + row_off + kg * (TILE_M * 16));
+          if (two) store_q16(rb, qb + row_off + (kg + 2) * (TILE_M * 16));
         }
       }
       fence_proxy_async();
       mbar_arrive(&qbf_full[tb]);
     };
-    // out-proj result + residual -> LayerNorm, in place in the fp32 tile buffer (one thread owns a row)
+    // out-projection of local tile t (A operand: the normalised O columns written by the read-out warps) +
+    // residual -> LayerNorm, in place in the fp32 tile buffer (one thread owns a row)
     auto finish = [&](uint32_t t) {
       const uint32_t tb = t & 1;
       float4* myrow = reinterpret_cast<float4*>(smem + sm.x32 + tb * sm.tile_stride) + (size_t)row * (d / 4);
       float s1 = 0.f, s2 = 0.f;
+      if (lead) mbar_wait_relaxed(obf_full, t & 1, 100);
       for (int n0 = 0; n0 < DP; n0 += SCR_COLS) {
         const int N = DP - n0 < SCR_COLS ? DP - n0 : SCR_COLS;
-        mbar_wait(scr_full, cs & 1);
-        ++cs;
-        tc_fence_after();
+        scratch_pass(obf_a, wo_a, DP, n0, N, n0 + SCR_COLS >= DP ? obf_empty : nullptr);
         for (int u = 0; u < N; u += 16) {
           uint32_t r[16];
           FFD_TMEM_LD16(scr + u, r);
-          tmem_ld_wait();
-          if (u + 16 >= N) {
-            tc_fence_before();
-            mbar_arrive(scr_empty);
+          float4 res[4];  // residual: issued before the TMEM round trip completes
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = n0 + u + 4 * j;
+            res[j] = c < d ? myrow[c >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int c = n0 + u + 4 * j;
             if (c < d) {
-              float4 v = myrow[c >> 2];
+              float4 v = res[j];
               v.x += __uint_as_float(r[4 * j]);
               v.y += __uint_as_float(r[4 * j + 1]);
               v.z += __uint_as_float(r[4 * j + 2]);
@@ -537,6 +509,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       }
       const float mean = s1 / (float)d;
       const float rstd = rsqrtf(fmaxf(s2 / (float)d - mean * mean, 0.f) + eps);
+#pragma unroll 6
       for (int c = 0; c < d; c += 4) {
         const float4 v = myrow[c >> 2];
         float4 o;
@@ -558,6 +531,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       FFD_STAMP(warp == 8 && t == 2, 402);
     }
     finish(my_tiles - 1);
+    if (lead) mbar_wait(obf_empty, (my_tiles - 1) & 1);  // drain
   } else {
     // ================= softmax groups: heads and nothing else =================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
@@ -593,16 +567,16 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     // exp2(m_q - max) = 0 in the combine).
 #define FFD_EXP16(G_, mc_, pk_)                                                                   \
   _Pragma("unroll") for (int e = 0; e < 16; e += 2)                                               \
-      pk_[e >> 1] = ex2_pack_f16(__uint_as_float(r[16 * (G_) + e]) - (mc_), __uint_as_float(r[16 * (G_) + e + 1]) - (mc_))
+      pk_[e >> 1] = ex2_pack_f16_shift(__uint_as_float(r[16 * (G_) + e]), __uint_as_float(r[16 * (G_) + e + 1]), (mc_))
 #define FFD_SOFTMAX_HEAD(LAST, SPARE, n_)                                                          \
   {                                                                                               \
     const uint32_t n = (n_);                                                                      \
     const uint32_t b = n & 1;                                                                     \
     const uint32_t pcol = pcol0 + b * (COL_P1 - COL_P0);                                          \
     const bool has_next = n + 1 < n_heads;                                                        \
-    const float mc = mb;                                                                          \
-    mq[((n & 3) * 4 + wg) * TILE_M + row] = mc;                                                   \
-    FFD_STAMP(warp == 12 && n / NV == 2, 128 + (n % NV) * 4 + 0);                                 \
+    const float mc = -mb;                                                                         \
+    mq[((n & 3) * 4 + wg) * TILE_M + row] = mb;                                                   \
+    FFD_STAMP(warp == 12 && n - 2u * NV < (uint32_t)NV, 128 + (n - 2u * NV) * 4 + 0);                                 \
     uint32_t pk[8];                                                                               \
     _Pragma("unroll") for (int j = 0; j < KQ - 1; ++j) {                                          \
       FFD_EXP16(j, mc, pk);                                                                       \
@@ -613,10 +587,10 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       FFD_TMEM_ST8(pcol + 8 * j, pk);                                                             \
     }                                                                                             \
     if (has_next) {                                                                               \
-      FFD_STAMP(warp == 12 && n / NV == 2, 128 + (n % NV) * 4 + 1);                               \
+      FFD_STAMP(warp == 12 && n - 2u * NV < (uint32_t)NV, 128 + (n - 2u * NV) * 4 + 1);                               \
       mbar_wait(s_full, (n + 1) & 1);                                                             \
       tc_fence_after();                                                                           \
-      FFD_STAMP(warp == 12 && n / NV == 2, 128 + (n % NV) * 4 + 2);                               \
+      FFD_STAMP(warp == 12 && n - 2u * NV < (uint32_t)NV, 128 + (n - 2u * NV) * 4 + 2);                               \
       _Pragma("unroll") for (int j = 0; j < KQ - 1; ++j) FFD_TMEM_LD16(scol + 16 * j, (r + 16 * j)); \
       FFD_TMEM_LD16(scol + 16 * (KQ - 1), (r + 16 * (SPARE)));                                    \
     }                                                                                             \
@@ -637,7 +611,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     tmem_st_wait();                                                                               \
     tc_fence_before();                                                                            \
     mbar_arrive(&p_full[b]);                                                                      \
-    FFD_STAMP(warp == 12 && n / NV == 2, 128 + (n % NV) * 4 + 3);                                 \
+    FFD_STAMP(warp == 12 && n - 2u * NV < (uint32_t)NV, 128 + (n - 2u * NV) * 4 + 3);                                 \
   }
     for (uint32_t n2 = 0; n2 < n_heads; n2 += 2) {
       FFD_SOFTMAX_HEAD(KQ - 1, KQ, n2);

@@ -42,6 +42,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++polls > (1u << 24)) __trap();
   }
 }
+// Same for the roles that wait long and are not latency-critical (producers, tile warps): sleep between polls so
+// that they do not compete with the softmax warps for issue slots (the hardware wakes a suspended try_wait on
+// every barrier event of the CTA, so plain try_wait loops poll at a high rate).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(sleep_ns);
+    if (++polls > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -286,6 +296,28 @@ __device__ __forceinline__ uint32_t ex2_pack_f16(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(ex2_approx(hi)), "f"(ex2_approx(lo)));
   return r;
+}
+// exp2(lo + nm), exp2(hi + nm) packed as an fp16 pair; the two additions are ONE packed fp32x2 instruction
+// (FADD2 on sm_100), which matters because the softmax loop is bound by issue slots as much as by MUFU
+__device__ __forceinline__ uint32_t ex2_pack_f16_shift(float lo, float hi, float nm) {
+  uint64_t x, mm, y;
+  float a, b;
+  uint32_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(lo), "f"(hi));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(mm) : "f"(nm));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(y) : "l"(x), "l"(mm));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(y));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(ex2_approx(b)), "f"(ex2_approx(a)));
+  return r;
+}
+// d = a * w + c on two fp32 lanes at once (FFMA2)
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float w, float c0, float c1) {
+  uint64_t a, ww, c, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(ww), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float y;
