@@ -44,6 +44,15 @@ constexpr int K_STAGES = 3;    // K image ring
 constexpr int V_STAGES = 2;    // V image ring
 constexpr int HP = 16;         // slots per Q tile (UMMA K of the score MMA, N of the PV MMA)
 constexpr int SCR_COLS = 64;   // TMEM scratch columns (Q projection / out-proj passes)
+// Share of the softmax exponentials evaluated on the FMA pipe instead of MUFU: bit mask over the 8 fp16 pairs of
+// a 16-column chunk (tools/polytest.sh sweeps it).
+#ifndef FFD_STAGGER_NS
+#define FFD_STAGGER_NS 250
+#endif
+#ifndef FFD_POLY_PAIRS
+#define FFD_POLY_PAIRS 0x00u
+#endif
+constexpr uint32_t POLY_PAIRS = FFD_POLY_PAIRS;
 
 // TMEM columns
 constexpr uint32_t COL_S = 0;       // scores of the current virtual head (up to 192 fp32 columns)
@@ -223,7 +232,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         const uint32_t b = t & 1;
         const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M;
         const int64_t rows = M - row0 < TILE_M ? M - row0 : TILE_M;
-        mbar_wait(&y_ready[b], (t >> 1) & 1);
+        mbar_wait_relaxed(&y_ready[b], (t >> 1) & 1, 100);
         bulk_store(y + row0 * d, smem + sm.x32 + b * sm.tile_stride, (uint32_t)(rows * d * 4));
         bulk_commit();
         bulk_wait_read();
@@ -241,7 +250,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     int v = 0, c = 0, g = 0, qt = 0;  // position of the score MMA being issued: tile, virtual head, chunk, place
     for (uint32_t m = 0; m < n_heads; ++m) {
       if (m > 0) mbar_wait_relaxed(s_empty, (m - 1) & 1, 40);  // all softmax warps hold S_{m-1} in registers
-      if (v == 0) mbar_wait(&qbf_full[t & 1], (t >> 1) & 1);  // this tile's Q tiles are in shared memory
+      if (v == 0) mbar_wait_relaxed(&qbf_full[t & 1], (t >> 1) & 1, 60);  // this tile's Q tiles are in shared memory
       const uint32_t st = nk % K_STAGES;
       mbar_wait(&k_full[st], (nk / K_STAGES) & 1);
       tc_fence_after();
@@ -263,7 +272,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         ++t;
       }
     }
-    mbar_wait(s_full, (n_heads - 1) & 1);  // drain: nothing of this warp is in flight when the CTA exits
+    mbar_wait_relaxed(s_full, (n_heads - 1) & 1, 200);  // drain: nothing of this warp is in flight when the CTA exits
   } else {
     // ================= P.V MMAs (warp 3) =================
     constexpr uint32_t IDESC_PV = make_idesc_f16(TILE_M, HP);
@@ -271,9 +280,9 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     for (uint32_t n = 0; n < n_heads; ++n) {
       const uint32_t b = n & 1;
       const uint32_t st = n % V_STAGES;
-      mbar_wait_relaxed(&p_full[b], (n >> 1) & 1, 100);   // P_n (fp16 pairs) is complete
+      mbar_wait_relaxed(&p_full[b], (n >> 1) & 1, 32);   // P_n (fp16 pairs) is complete
       FFD_STAMP(n - 2u * NV < (uint32_t)NV, 64 + (n - 2u * NV) * 2 + 0);
-      mbar_wait(o_empty, (n & 1) ^ 1);       // O of the previous virtual head has been read out
+      mbar_wait_relaxed(o_empty, (n & 1) ^ 1, 20);       // O of the previous virtual head has been read out
       mbar_wait(&v_full[st], (n / V_STAGES) & 1);
       tc_fence_after();
       const uint32_t pcol = tmem_base + (b ? COL_P1 : COL_P0);
@@ -292,7 +301,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       umma_commit(&v_empty[st]);
       FFD_STAMP(n - 2u * NV < (uint32_t)NV, 64 + (n - 2u * NV) * 2 + 1);
     }
-    mbar_wait(&p_empty[(n_heads - 1) & 1], ((n_heads - 1) >> 1) & 1);  // drain
+    mbar_wait_relaxed(&p_empty[(n_heads - 1) & 1], ((n_heads - 1) >> 1) & 1, 200);  // drain
   }
   } else if (warp < 8) {
     // ================= O read-out warps =================
@@ -309,65 +318,100 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     uint32_t n = 0;
     for (uint32_t t = 0; t < my_tiles; ++t) {
       for (int h = 0; h < H; ++h) {
-        float acc[HP];
-        float mrun = 0.f;
-        for (int c = 0; c < NCH; ++c, ++n) {
-          mbar_wait_relaxed(o_full, n & 1, 100);
-          tc_fence_after();
-          FFD_STAMP(warp == 4 && t == 2, 256 + (h * NCH + c) * 2 + 0);
-          // combine the four quarters: weights exp2(m_q - max m_q); slot 15 of each O_q is that quarter's row sum
-          const float* mh = mq + ((n & 3) * 4) * TILE_M + row;
-          const float q0 = mh[0], q1 = mh[TILE_M], q2 = mh[2 * TILE_M], q3 = mh[3 * TILE_M];
-          float mm = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
-          if (c > 0) mm = fmaxf(mm, mrun);
-          const float w0 = exp2_poly3(q0 - mm), w1 = exp2_poly3(q1 - mm), w2 = exp2_poly3(q2 - mm),
-                      w3 = exp2_poly3(q3 - mm);
-          // only the head's hd dims and slot 15 (the row sum) carry data: with hd <= 7 the upper half of every
-          // accumulator except its last pair is padding
-          const int jmax = hd <= 7 ? 8 : HP - 2;
-          if (c == 0) {
+        // With hd <= 7 the row sum sits in slot 7 (pack_kv_kernel), so the low 8 columns of every quarter
+        // accumulator hold everything: ONE TMEM round trip per virtual head.  (The P.V MMA of the next head waits
+        // for this read: the round trip is on the kernel's critical loop.)
+        if (hd <= 7) {
+          float acc[8];
+          float mrun = 0.f;
+          for (int c = 0; c < NCH; ++c, ++n) {
+            mbar_wait_relaxed(o_full, n & 1, 32);
+            tc_fence_after();
+            FFD_STAMP(warp == 4 && t == 2, 256 + (h * NCH + c) * 2 + 0);
+            uint32_t r[32];
+            FFD_TMEM_LD8(tmem_base + lane_base + COL_O, r);
+            FFD_TMEM_LD8(tmem_base + lane_base + COL_O + 16, (r + 8));
+            FFD_TMEM_LD8(tmem_base + lane_base + COL_O + 32, (r + 16));
+            FFD_TMEM_LD8(tmem_base + lane_base + COL_O + 48, (r + 24));
+            // combine the four quarters: weights exp2(m_q - max m_q)
+            const float* mh = mq + ((n & 3) * 4) * TILE_M + row;
+            const float q0 = mh[0], q1 = mh[TILE_M], q2 = mh[2 * TILE_M], q3 = mh[3 * TILE_M];
+            float mm = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
+            if (c > 0) mm = fmaxf(mm, mrun);
+            const float w0 = exp2_poly3(q0 - mm), w1 = exp2_poly3(q1 - mm), w2 = exp2_poly3(q2 - mm),
+                        w3 = exp2_poly3(q3 - mm);
+            const float wp = c > 0 ? exp2_poly3(mrun - mm) : 0.f;
 #pragma unroll
-            for (int j = 0; j < HP; ++j) acc[j] = 0.f;
-          } else {
-            const float wp = exp2_poly3(mrun - mm);
+            for (int j = 0; j < 8; ++j) acc[j] = c > 0 ? acc[j] * wp : 0.f;
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(o_empty);
+            FFD_STAMP(warp == 4 && t == 2, 256 + (h * NCH + c) * 2 + 1);
 #pragma unroll
-            for (int j = 0; j < HP; ++j) acc[j] *= wp;
+            for (int j = 0; j < 8; j += 2) {
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[j]), __uint_as_float(r[j + 1]), w0, acc[j], acc[j + 1]);
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[8 + j]), __uint_as_float(r[9 + j]), w1, acc[j], acc[j + 1]);
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[16 + j]), __uint_as_float(r[17 + j]), w2, acc[j], acc[j + 1]);
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[24 + j]), __uint_as_float(r[25 + j]), w3, acc[j], acc[j + 1]);
+            }
+            mrun = mm;
           }
-          uint32_t r[32];
-          FFD_TMEM_LD16(tmem_base + lane_base + COL_O, r);
-          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 16, (r + 16));
-          tmem_ld_wait();
+          const float inv = rcp_fma(acc[7]);
+          // the out-projection of the previous tile must have read its operand before the first overwrite
+          if (h == 0 && t >= 1) mbar_wait_relaxed(obf_empty, (t - 1) & 1, 60);
 #pragma unroll
-          for (int j = 0; j < HP; j += 2) {
-            if (j < jmax || j == HP - 2) {
+          for (int j = 0; j < 7; ++j) {
+            if (j < hd) {
+              const int col = h * hd + j;
+              *reinterpret_cast<__nv_bfloat16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                  __float2bfloat16_rn(acc[j] * inv);
+            }
+          }
+        } else {
+          float acc[HP];
+          float mrun = 0.f;
+          for (int c = 0; c < NCH; ++c, ++n) {
+            mbar_wait_relaxed(o_full, n & 1, 32);
+            tc_fence_after();
+            uint32_t r[32];
+            FFD_TMEM_LD16(tmem_base + lane_base + COL_O, r);
+            FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 16, (r + 16));
+            const float* mh = mq + ((n & 3) * 4) * TILE_M + row;
+            const float q0 = mh[0], q1 = mh[TILE_M], q2 = mh[2 * TILE_M], q3 = mh[3 * TILE_M];
+            float mm = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
+            if (c > 0) mm = fmaxf(mm, mrun);
+            const float w0 = exp2_poly3(q0 - mm), w1 = exp2_poly3(q1 - mm), w2 = exp2_poly3(q2 - mm),
+                        w3 = exp2_poly3(q3 - mm);
+            const float wp = c > 0 ? exp2_poly3(mrun - mm) : 0.f;
+#pragma unroll
+            for (int j = 0; j < HP; ++j) acc[j] = c > 0 ? acc[j] * wp : 0.f;
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < HP; j += 2) {
               fma2(acc[j], acc[j + 1], __uint_as_float(r[j]), __uint_as_float(r[j + 1]), w0, acc[j], acc[j + 1]);
               fma2(acc[j], acc[j + 1], __uint_as_float(r[16 + j]), __uint_as_float(r[17 + j]), w1, acc[j], acc[j + 1]);
             }
-          }
-          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 32, r);
-          FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 48, (r + 16));
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(o_empty);
-          FFD_STAMP(warp == 4 && t == 2, 256 + (h * NCH + c) * 2 + 1);
+            FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 32, r);
+            FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 48, (r + 16));
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(o_empty);
 #pragma unroll
-          for (int j = 0; j < HP; j += 2) {
-            if (j < jmax || j == HP - 2) {
+            for (int j = 0; j < HP; j += 2) {
               fma2(acc[j], acc[j + 1], __uint_as_float(r[j]), __uint_as_float(r[j + 1]), w2, acc[j], acc[j + 1]);
               fma2(acc[j], acc[j + 1], __uint_as_float(r[16 + j]), __uint_as_float(r[17 + j]), w3, acc[j], acc[j + 1]);
             }
+            mrun = mm;
           }
-          mrun = mm;
-        }
-        const float inv = rcp_fma(acc[HP - 1]);
-        // the out-projection of the previous tile must have read its operand before the first overwrite
-        if (h == 0 && t >= 1) mbar_wait(obf_empty, (t - 1) & 1);
+          const float inv = rcp_fma(acc[HP - 1]);
+          if (h == 0 && t >= 1) mbar_wait_relaxed(obf_empty, (t - 1) & 1, 60);
 #pragma unroll
-        for (int j = 0; j < HP - 1; ++j) {
-          if (j < hd) {
-            const int col = h * hd + j;
-            *reinterpret_cast<__nv_bfloat16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
-                __float2bfloat16_rn(acc[j] * inv);
+          for (int j = 0; j < HP - 1; ++j) {
+            if (j < hd) {
+              const int col = h * hd + j;
+              *reinterpret_cast<__nv_bfloat16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                  __float2bfloat16_rn(acc[j] * inv);
+            }
           }
         }
       }
@@ -531,7 +575,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       FFD_STAMP(warp == 8 && t == 2, 402);
     }
     finish(my_tiles - 1);
-    if (lead) mbar_wait(obf_empty, (my_tiles - 1) & 1);  // drain
+    if (lead) mbar_wait_relaxed(obf_empty, (my_tiles - 1) & 1, 200);  // drain
   } else {
     // ================= softmax groups: heads and nothing else =================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
@@ -550,8 +594,11 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       for (int e = 0; e < 16; e += 2) m = max3(m, __uint_as_float(r[16 * j + e]), __uint_as_float(r[16 * j + e + 1]));
       return m;
     };
-    // first virtual head: load its scores and reduce the row maximum
+    // The four softmax warps of a sub-partition (one per group) do identical work; started together they stay in
+    // lockstep and their non-MUFU sections (row maximum, TMEM stores, barrier traffic) leave the MUFU pipe idle
+    // together.  Start them a quarter of a head apart.
     mbar_wait(s_full, 0);
+    __nanosleep(wg * FFD_STAGGER_NS);
     tc_fence_after();
 #pragma unroll
     for (int j = 0; j < KQ; ++j) FFD_TMEM_LD16(scol + 16 * j, (r + 16 * j));
@@ -567,7 +614,9 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     // exp2(m_q - max) = 0 in the combine).
 #define FFD_EXP16(G_, mc_, pk_)                                                                   \
   _Pragma("unroll") for (int e = 0; e < 16; e += 2)                                               \
-      pk_[e >> 1] = ex2_pack_f16_shift(__uint_as_float(r[16 * (G_) + e]), __uint_as_float(r[16 * (G_) + e + 1]), (mc_))
+      pk_[e >> 1] = ((POLY_PAIRS >> (e >> 1)) & 1)                                                   \
+                        ? ex2_pack_f16_shift_poly(__uint_as_float(r[16 * (G_) + e]), __uint_as_float(r[16 * (G_) + e + 1]), (mc_)) \
+                        : ex2_pack_f16_shift(__uint_as_float(r[16 * (G_) + e]), __uint_as_float(r[16 * (G_) + e + 1]), (mc_))
 #define FFD_SOFTMAX_HEAD(LAST, SPARE, n_)                                                          \
   {                                                                                               \
     const uint32_t n = (n_);                                                                      \
@@ -588,20 +637,29 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     }                                                                                             \
     if (has_next) {                                                                               \
       FFD_STAMP(warp == 12 && n - 2u * NV < (uint32_t)NV, 128 + (n - 2u * NV) * 4 + 1);                               \
-      mbar_wait(s_full, (n + 1) & 1);                                                             \
+      mbar_wait_relaxed(s_full, (n + 1) & 1, 32);                                                 \
       tc_fence_after();                                                                           \
       FFD_STAMP(warp == 12 && n - 2u * NV < (uint32_t)NV, 128 + (n - 2u * NV) * 4 + 2);                               \
       _Pragma("unroll") for (int j = 0; j < KQ - 1; ++j) FFD_TMEM_LD16(scol + 16 * j, (r + 16 * j)); \
       FFD_TMEM_LD16(scol + 16 * (KQ - 1), (r + 16 * (SPARE)));                                    \
     }                                                                                             \
-    FFD_EXP16(LAST, mc, pk);                                                                      \
+    /* first half of the last chunk's exponentials, then (same basic block, so that ptxas interleaves them) */ \
+    /* the second half together with the row maximum of the next head's scores                              */ \
+    _Pragma("unroll") for (int e = 0; e < 8; e += 2)                                              \
+        pk[e >> 1] = ex2_pack_f16_shift(__uint_as_float(r[16 * (LAST) + e]), __uint_as_float(r[16 * (LAST) + e + 1]), mc); \
     if (has_next) {                                                                               \
       tmem_ld_wait();                                                                             \
       tc_fence_before();                                                                          \
       mbar_arrive(s_empty); /* the score buffer may be overwritten */                             \
-      mb = -INFINITY;                                                                             \
-      _Pragma("unroll") for (int j = 0; j < KQ - 1; ++j) mb = chunk_max(j, mb);                   \
-      mb = chunk_max(SPARE, mb);                                                                  \
+    }                                                                                             \
+    _Pragma("unroll") for (int e = 8; e < 16; e += 2)                                             \
+        pk[e >> 1] = ex2_pack_f16_shift(__uint_as_float(r[16 * (LAST) + e]), __uint_as_float(r[16 * (LAST) + e + 1]), mc); \
+    { /* unconditional (stale registers after the last head: unused), to stay in the same basic block */ \
+      float mj[KQ]; /* independent chains: the reduction is latency-bound otherwise */            \
+      _Pragma("unroll") for (int j = 0; j < KQ - 1; ++j) mj[j] = chunk_max(j, -INFINITY);         \
+      mj[KQ - 1] = chunk_max(SPARE, -INFINITY);                                                   \
+      mb = mj[0];                                                                                 \
+      _Pragma("unroll") for (int j = 1; j < KQ; ++j) mb = fmaxf(mb, mj[j]);                       \
     }                                                                                             \
     if (KQ == 1) {                                                                                \
       mbar_wait(&p_empty[b], ((n >> 1) & 1) ^ 1);                                                 \
@@ -670,8 +728,8 @@ __global__ void pack_attn_kernel(const float* __restrict__ in_w, const float* __
 // Images per (layer, head h, key chunk c), keys [c CK, (c+1) CK):
 //   K: B operand [CK n(key) x 16 k(slot)], bf16: head h's dims in the slots of its place g = h % G inside its Q
 //      tile, zeros in the slots of its tile mates; slot 15 of a padded key row is -29952 (slot 15 of Q is 1).
-//   V: B operand [16 n(dim) x CK k(key)], fp16 (P is fp16), with row 15 set to 1 for the valid keys so that
-//      column 15 of O = P . V^T is the softmax row sum.
+//   V: B operand [16 n(dim) x CK k(key)], fp16 (P is fp16), with row 7 (hd <= 7) or row 15 set to 1 for the valid
+//      keys so that this column of O = P . V^T is the softmax row sum.
 __global__ void pack_kv_kernel(const float* __restrict__ kc, const float* __restrict__ vc,
                                uint16_t* __restrict__ img, int n_lh, int L, int hd, int H, int G, int NCH, int CK) {
   const int per = CK * HP;  // elements per image
@@ -690,7 +748,7 @@ __global__ void pack_kv_kernel(const float* __restrict__ kc, const float* __rest
     float v = 0.f;
     if (is_v) {
       if (key < L && slot < hd) v = vc[((int64_t)lh * L + key) * hd + slot];
-      if (key < L && slot == HP - 1) v = 1.f;        // O[:, 15] = softmax row sum
+      if (key < L && slot == (hd <= 7 ? 7 : HP - 1)) v = 1.f;  // that column of O = softmax row sum
     } else {
       const int dim = slot - g * hd;
       if (key < L && slot < HP - 1 && dim >= 0 && dim < hd) v = kc[((int64_t)lh * L + key) * hd + dim];
