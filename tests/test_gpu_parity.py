@@ -425,10 +425,15 @@ def test_entry_points_run(tmp_path):
 
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("shape", [dict(max_len=200, n_channels=3, d_model=24, num_layers=2, n_head=4),
-                                   dict(max_len=37, n_channels=5, d_model=60, num_layers=2, n_head=12)])
+                                   dict(max_len=37, n_channels=5, d_model=60, num_layers=2, n_head=12),
+                                   # BASELINE.json configs 3 and 4: NASA-charge, NASDAQ, USDroughts (default model)
+                                   dict(max_len=251, n_channels=4, d_model=72, num_layers=2, n_head=12),
+                                   dict(max_len=252, n_channels=5, d_model=72, num_layers=2, n_head=12),
+                                   dict(max_len=365, n_channels=13, d_model=72, num_layers=2, n_head=12)])
 def test_other_shapes_against_oracle(prec, shape):
-    """Shapes outside the tensor-core attention kernel's range (L > 192) or with other paddings (d=60, hd=5,
-    multi-channel): every branch against the numpy oracle with seeded weights (no reference run needed)."""
+    """Other geometries of the tensor-core attention kernel -- several key chunks per head (L > 192: 2 x 128 or
+    2 x 192 keys), three heads per Q tile (d=60, hd=5), one 64-key chunk, multi-channel -- every branch against the
+    numpy oracle with seeded weights (no reference run needed)."""
     import fastfourierdiffusion_b200 as F
 
     m = build_seeded_model(shape, 5, precision=prec)
