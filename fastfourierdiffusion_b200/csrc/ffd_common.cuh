@@ -92,6 +92,7 @@ struct Workspace {
   float* qkv;   // [M, 3d]
   float* kvtmp; // [L, 2d] sample-0 K/V of a full step
   void* kvimg;  // bf16 K/V operand images of the cache for the tcgen05 attention kernel
+  void* kvimg_own;  // the same per sample (stock attention on the tcgen05 kernel)
   int64_t bytes;
 };
 
@@ -112,6 +113,8 @@ static inline Workspace carve(const ffd_dims& m, int64_t B, void* base) {
   w.kvtmp = take((int64_t)m.max_len * 2 * d);
   // [NL, H, NCH] x (K image [CK x 16] bf16 + V image [16 x CK] fp16)
   w.kvimg = take((int64_t)m.n_layers * m.n_head * attn_key_chunks(m.max_len) * attn_chunk_keys(m.max_len) * 16);
+  // [B, H, NCH] x (K image + V image): 64 bytes per key slot
+  w.kvimg_own = take(B * m.n_head * attn_key_chunks(m.max_len) * attn_chunk_keys(m.max_len) * 16);
   w.bytes = o;
   return w;
 }

@@ -57,4 +57,11 @@ int tc_pack_kv(const ffd_dims& m, const float* kc, const float* vc, void* kvimg,
 int tc_attn_cached(const ffd_dims& m, const void* attn_img, const void* kvimg, const float* weights, int layer,
                    const float* x, float* y, int64_t M, cudaStream_t s);
 
+// stock attention block (every sample attends to its own keys): K/V rows are read from kv_src[(b L + key) * ld +
+// k_off / v_off + ...] (fp32), packed into per-sample operand images (kvimg_own, tc_kv_own_image_bytes) and fed
+// to the same kernel with sample-aligned tiles.  y may alias x.
+int64_t tc_kv_own_image_bytes(const ffd_dims& m, int64_t B);
+int tc_attn_own(const ffd_dims& m, const void* attn_img, void* kvimg_own, const float* kv_src, int ld, int k_off,
+                int v_off, const float* weights, int layer, const float* x, float* y, int64_t M, cudaStream_t s);
+
 }  // namespace ffd

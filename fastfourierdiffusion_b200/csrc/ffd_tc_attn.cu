@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t* __restrict__ wqimg,
                       const uint8_t* __restrict__ woimg, const uint8_t* __restrict__ kvimg,
                       const float* __restrict__ lnw, const float* __restrict__ lnb, int64_t M, int d, int H, int hd,
-                      int G, int QN, int NCH, int64_t n_tiles, float eps, long long* __restrict__ dbg) {
+                      int G, int QN, int NCH, int64_t n_tiles, float eps, int Lown, int tps,
+                      long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int CK = 64 * KQ;   // keys per chunk
   constexpr int NQ = 16 * KQ;   // key columns per softmax group
@@ -133,6 +134,23 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t my_tiles = (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);  // >= 1
+  // Rows of this CTA's t-th tile.  Lown == 0: K/V are the shared cache, tiles are consecutive 128-row blocks of
+  // [0, M).  Lown > 0 (stock attention, cached_transformer.py:123-134 / nn.MultiheadAttention): every sample
+  // attends to its OWN keys, so tiles are aligned to samples (tps tiles of <= 128 rows per sample of Lown rows)
+  // and the K/V images are per sample.
+  auto tile_rows = [&](uint32_t t, int64_t& row0, int& rows, int64_t& sample) {
+    const int64_t gt = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+    if (Lown == 0) {
+      sample = 0;
+      row0 = gt * TILE_M;
+      rows = (int)(M - row0 < TILE_M ? M - row0 : TILE_M);
+    } else {
+      sample = gt / tps;
+      const int part = (int)(gt - sample * tps);
+      row0 = sample * Lown + (int64_t)part * TILE_M;
+      rows = Lown - part * TILE_M < TILE_M ? Lown - part * TILE_M : TILE_M;
+    }
+  };
   const uint32_t n_heads = my_tiles * (uint32_t)NV;  // virtual heads this CTA runs through
 #ifdef FFD_ATTN_STAMPS  // timeline of local tile 2 of CTA 0 (tools/attn_stamps.py)
 #define FFD_STAMP(cond, slot) do { if (dbg && blockIdx.x == 0 && lane == 0 && (cond)) dbg[slot] = clock64(); } while (0)
@@ -188,31 +206,46 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       bulk_load(smem + sm.wo, woimg, sm.wo_bytes, w_full);
       uint32_t nk = 0, nv = 0;
       const size_t img_stride = (size_t)sm.k_bytes + sm.v_bytes;
-      auto load_k = [&](uint32_t v) {
+      const size_t sample_stride = Lown ? (size_t)NV * img_stride : 0;
+      auto load_k = [&](const uint8_t* base, uint32_t v) {
         const uint32_t st = nk % K_STAGES, u = nk / K_STAGES;
         mbar_wait_relaxed(&k_empty[st], (u & 1) ^ 1, 200);
         mbar_expect_tx(&k_full[st], sm.k_bytes);
-        bulk_load(smem + sm.kring + st * sm.k_bytes, kvimg + v * img_stride, sm.k_bytes, &k_full[st]);
+        bulk_load(smem + sm.kring + st * sm.k_bytes, base + v * img_stride, sm.k_bytes, &k_full[st]);
         ++nk;
       };
-      auto load_v = [&](uint32_t v) {
+      auto load_v = [&](const uint8_t* base, uint32_t v) {
         const uint32_t st = nv % V_STAGES, u = nv / V_STAGES;
         mbar_wait_relaxed(&v_empty[st], (u & 1) ^ 1, 200);
         mbar_expect_tx(&v_full[st], sm.v_bytes);
-        bulk_load(smem + sm.vring + st * sm.v_bytes, kvimg + v * img_stride + sm.k_bytes, sm.v_bytes, &v_full[st]);
+        bulk_load(smem + sm.vring + st * sm.v_bytes, base + v * img_stride + sm.k_bytes, sm.v_bytes, &v_full[st]);
         ++nv;
       };
+      auto tile_base = [&](uint32_t t) {
+        int64_t row0, sample;
+        int rows;
+        tile_rows(t, row0, rows, sample);
+        return kvimg + (size_t)sample * sample_stride;
+      };
       // K images run two virtual heads ahead of the V images (the score MMAs run ahead of the P.V MMAs)
-      uint32_t vk = 0, vv = 0;  // virtual-head index inside a tile of the next K / V image
+      uint32_t vk = 0, vv = 0, tk = 0, tv = 0;  // virtual head inside its tile / tile of the next K and V image
+      const uint8_t* kbase = tile_base(0);
+      const uint8_t* vbase = kbase;
       auto next_k = [&]() {
-        load_k(vk);
-        if (++vk == (uint32_t)NV) vk = 0;
+        load_k(kbase, vk);
+        if (++vk == (uint32_t)NV) {
+          vk = 0;
+          if (++tk < my_tiles) kbase = tile_base(tk);
+        }
       };
       next_k();
       if (n_heads > 1) next_k();
       for (uint32_t n = 0; n < n_heads; ++n) {
-        load_v(vv);
-        if (++vv == (uint32_t)NV) vv = 0;
+        load_v(vbase, vv);
+        if (++vv == (uint32_t)NV) {
+          vv = 0;
+          if (++tv < my_tiles) vbase = tile_base(tv);
+        }
         if (n + 2 < n_heads) next_k();
       }
     }
@@ -221,8 +254,9 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     if (lane == 0) {
       auto load_tile = [&](uint32_t t) {
         const uint32_t b = t & 1;
-        const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M;
-        const int64_t rows = M - row0 < TILE_M ? M - row0 : TILE_M;
+        int64_t row0, sample;
+        int rows;
+        tile_rows(t, row0, rows, sample);
         mbar_expect_tx(&t_full[b], (uint32_t)(rows * d * 4));
         bulk_load(smem + sm.x32 + b * sm.tile_stride, x + row0 * d, (uint32_t)(rows * d * 4), &t_full[b]);
       };
@@ -230,8 +264,9 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       if (my_tiles > 1) load_tile(1);
       for (uint32_t t = 0; t < my_tiles; ++t) {
         const uint32_t b = t & 1;
-        const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M;
-        const int64_t rows = M - row0 < TILE_M ? M - row0 : TILE_M;
+        int64_t row0, sample;
+        int rows;
+        tile_rows(t, row0, rows, sample);
         mbar_wait_relaxed(&y_ready[b], (t >> 1) & 1, 100);
         bulk_store(y + row0 * d, smem + sm.x32 + b * sm.tile_stride, (uint32_t)(rows * d * 4));
         bulk_commit();
@@ -467,8 +502,10 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     // stage X of local tile t as the bf16 A operand, project it, and turn the result into bf16 Q tiles
     auto prepare = [&](uint32_t t) {
       const uint32_t tb = t & 1;
-      const int64_t grow = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + row;
-      const bool valid = grow < M;
+      int64_t row0, sample;
+      int rows;
+      tile_rows(t, row0, rows, sample);
+      const bool valid = row < rows;
       const float4* src = reinterpret_cast<const float4*>(smem + sm.x32 + tb * sm.tile_stride) + (size_t)row * (d / 4);
       mbar_wait_relaxed(&t_full[tb], (t >> 1) & 1, 200);
       FFD_STAMP(warp == 8 && t == 3, 404);
@@ -758,6 +795,53 @@ __global__ void pack_kv_kernel(const float* __restrict__ kc, const float* __rest
   }
 }
 
+// The same images for every sample's OWN keys (stock attention): K/V rows come from the projected tokens
+// src[(b L + key) * ld + k_off / v_off + h hd + dim].  One thread writes one 16-byte core-matrix row.
+__global__ void pack_kv_own_kernel(const float* __restrict__ src, int ld, int k_off, int v_off,
+                                   uint4* __restrict__ img, int64_t B, int L, int hd, int H, int G, int NCH, int CK) {
+  const int units = 4 * CK;  // per (sample, head, chunk): 2 CK of the K image, then 2 CK of the V image
+  const int64_t total = B * H * NCH * units;
+  const int rs = hd <= 7 ? 7 : HP - 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int u = (int)(i % units);
+    const int64_t bhc = i / units;
+    const int ch = (int)(bhc % NCH);
+    const int h = (int)((bhc / NCH) % H);
+    const int64_t b = bhc / ((int64_t)NCH * H);
+    const int g = h % G;
+    float v[8];
+    if (u < 2 * CK) {
+      const int kg = u / CK, key = ch * CK + u % CK;
+      const float* row = src + (b * L + key) * ld + k_off + h * hd;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int slot = kg * 8 + j, dim = slot - g * hd;
+        v[j] = 0.f;
+        if (key < L && slot < HP - 1 && dim >= 0 && dim < hd) v[j] = row[dim];
+        if (key >= L && slot == HP - 1) v[j] = -29952.f;
+      }
+      uint4 q;
+      q.x = pack_bf16(v[0], v[1]), q.y = pack_bf16(v[2], v[3]), q.z = pack_bf16(v[4], v[5]), q.w = pack_bf16(v[6], v[7]);
+      img[i] = q;
+    } else {
+      const int uu = u - 2 * CK;
+      const int kg = uu / HP, dim = uu % HP;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int key = ch * CK + kg * 8 + j;
+        v[j] = 0.f;
+        if (key < L) v[j] = dim < hd ? src[(b * L + key) * ld + v_off + h * hd + dim] : (dim == rs ? 1.f : 0.f);
+      }
+      uint4 q;
+      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v[1]), "f"(v[0]));
+      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v[3]), "f"(v[2]));
+      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(v[5]), "f"(v[4]));
+      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(v[7]), "f"(v[6]));
+      img[i] = q;
+    }
+  }
+}
+
 }  // namespace tc
 
 // Geometry of the attention kernel for a model: G heads per Q tile, QN Q columns, NCH key chunks of CK keys.
@@ -822,7 +906,8 @@ long long* g_attn_dbg = nullptr;  // optional device buffer of clock64 stamps (p
 
 template <int DP, int KQ>
 static int launch_attn(const ffd_dims& m, const AttnGeom& g, const uint8_t* wqimg, const uint8_t* kvimg_layer,
-                       const float* lnw, const float* lnb, const float* x, float* y, int64_t M, cudaStream_t s) {
+                       const float* lnw, const float* lnb, const float* x, float* y, int64_t M, int own,
+                       cudaStream_t s) {
   static int n_sm = 0;
   const tc::AttnSmem sm = tc::attn_smem(DP, g.QN, g.CK, m.d_model);
   if (n_sm == 0) {
@@ -832,24 +917,40 @@ static int launch_attn(const ffd_dims& m, const AttnGeom& g, const uint8_t* wqim
   }
   FFD_CHECK_CUDA(cudaFuncSetAttribute(tc::attn_cached_tc_kernel<DP, KQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       sm.total));
-  const int64_t n_tiles = (M + tc::TILE_M - 1) / tc::TILE_M;
+  // own = 1: per-sample K/V images, tiles aligned to samples
+  const int tps = (m.max_len + tc::TILE_M - 1) / tc::TILE_M;
+  const int64_t n_tiles = own ? M / m.max_len * tps : (M + tc::TILE_M - 1) / tc::TILE_M;
   const unsigned grid = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);
   tc::attn_cached_tc_kernel<DP, KQ><<<grid, tc::ATT_THREADS, sm.total, s>>>(
       x, y, wqimg, wqimg + (size_t)g.QN * DP * 2, kvimg_layer, lnw, lnb, M, m.d_model, m.n_head, g.hd, g.G, g.QN,
-      g.NCH, n_tiles, 1e-5f, g_attn_dbg);
+      g.NCH, n_tiles, 1e-5f, own ? m.max_len : 0, tps, g_attn_dbg);
   FFD_CHECK_LAUNCH("attn_cached_tc_kernel");
   return FFD_OK;
 }
 
 template <int DP>
 static int launch_attn_kq(const ffd_dims& m, const AttnGeom& g, const uint8_t* wqimg, const uint8_t* kvimg_layer,
-                          const float* lnw, const float* lnb, const float* x, float* y, int64_t M, cudaStream_t s) {
+                          const float* lnw, const float* lnb, const float* x, float* y, int64_t M, int own,
+                          cudaStream_t s) {
   switch (g.KQ) {
-    case 1: return launch_attn<DP, 1>(m, g, wqimg, kvimg_layer, lnw, lnb, x, y, M, s);
-    case 2: return launch_attn<DP, 2>(m, g, wqimg, kvimg_layer, lnw, lnb, x, y, M, s);
-    case 3: return launch_attn<DP, 3>(m, g, wqimg, kvimg_layer, lnw, lnb, x, y, M, s);
+    case 1: return launch_attn<DP, 1>(m, g, wqimg, kvimg_layer, lnw, lnb, x, y, M, own, s);
+    case 2: return launch_attn<DP, 2>(m, g, wqimg, kvimg_layer, lnw, lnb, x, y, M, own, s);
+    case 3: return launch_attn<DP, 3>(m, g, wqimg, kvimg_layer, lnw, lnb, x, y, M, own, s);
   }
   set_error("tensor-core attention: unsupported key chunk %d", g.CK);
+  return FFD_ERR_UNSUPPORTED;
+}
+
+static int attn_dispatch(const ffd_dims& m, const AttnGeom& g, const uint8_t* wq, const uint8_t* kvl, const float* w,
+                         const Arena& ar, const float* x, float* y, int64_t M, int own, cudaStream_t s) {
+  switch (tc::dp_of(m.d_model)) {
+    case 16: return launch_attn_kq<16>(m, g, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, own, s);
+    case 32: return launch_attn_kq<32>(m, g, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, own, s);
+    case 48: return launch_attn_kq<48>(m, g, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, own, s);
+    case 64: return launch_attn_kq<64>(m, g, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, own, s);
+    case 80: return launch_attn_kq<80>(m, g, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, own, s);
+  }
+  set_error("tensor-core attention: unsupported d_model %d", m.d_model);
   return FFD_ERR_UNSUPPORTED;
 }
 
@@ -859,16 +960,24 @@ int tc_attn_cached(const ffd_dims& m, const void* attn_img, const void* kvimg, c
   const AttnGeom g = attn_geom(m);
   const float* w = weights + ar.layer0 + (int64_t)layer * ar.layer_stride;
   const uint8_t* kvl = (const uint8_t*)kvimg + (size_t)layer * g.NV * 2 * g.CK * tc::HP * 2;
-  const uint8_t* wq = (const uint8_t*)attn_img;
-  switch (tc::dp_of(m.d_model)) {
-    case 16: return launch_attn_kq<16>(m, g, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
-    case 32: return launch_attn_kq<32>(m, g, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
-    case 48: return launch_attn_kq<48>(m, g, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
-    case 64: return launch_attn_kq<64>(m, g, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
-    case 80: return launch_attn_kq<80>(m, g, wq, kvl, w + ar.n1w, w + ar.n1b, x, y, M, s);
-  }
-  set_error("tensor-core attention: unsupported d_model %d", m.d_model);
-  return FFD_ERR_UNSUPPORTED;
+  return attn_dispatch(m, g, (const uint8_t*)attn_img, kvl, w, ar, x, y, M, 0, s);
+}
+
+int64_t tc_kv_own_image_bytes(const ffd_dims& m, int64_t B) {
+  const AttnGeom g = attn_geom(m);
+  return B * g.NV * 2 * g.CK * tc::HP * 2;
+}
+
+int tc_attn_own(const ffd_dims& m, const void* attn_img, void* kvimg_own, const float* kv_src, int ld, int k_off,
+                int v_off, const float* weights, int layer, const float* x, float* y, int64_t M, cudaStream_t s) {
+  const Arena ar = arena_of(m);
+  const AttnGeom g = attn_geom(m);
+  const float* w = weights + ar.layer0 + (int64_t)layer * ar.layer_stride;
+  const int64_t B = M / m.max_len;
+  tc::pack_kv_own_kernel<<<148 * 16, 256, 0, s>>>(kv_src, ld, k_off, v_off, (uint4*)kvimg_own, B, m.max_len, g.hd,
+                                                   m.n_head, g.G, g.NCH, g.CK);
+  FFD_CHECK_LAUNCH("pack_kv_own_kernel");
+  return attn_dispatch(m, g, (const uint8_t*)attn_img, (const uint8_t*)kvimg_own, w, ar, x, y, M, 1, s);
 }
 
 }  // namespace ffd
