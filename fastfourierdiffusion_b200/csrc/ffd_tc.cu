@@ -28,7 +28,7 @@ namespace tc {
 
 constexpr int CHUNK = 128;    // hidden units per slice (UMMA N of GEMM1, K extent of GEMM2)
 constexpr int STAGES = 2;     // weight ring depth (shared memory holds two tile pairs + the rings)
-constexpr int NUM_THREADS = 576;
+constexpr int NUM_THREADS = 608;
 
 // ---- shared-memory plan ------------------------------------------------------------------------
 struct FfnSmem {
@@ -89,9 +89,9 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&w1_full[i], 1);
-      mbar_init(&w1_empty[i], 1);
+      mbar_init(&w1_empty[i], 2);  // one commit from each tile's issuing warp
       mbar_init(&w2_full[i], 1);
-      mbar_init(&w2_empty[i], 1);
+      mbar_init(&w2_empty[i], 2);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&t_full[i], 1);
@@ -185,19 +185,22 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
         bulk_wait_all();
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer (whole warp converged, one elected lane issues) =================
+  } else if (warp == 1 || warp == 18) {
+    // ================= MMA issuers: warp 1 drives tile 0 of every pair, warp 18 tile 1 (whole warp converged, one
+    // elected lane issues).  Two independent issue streams: neither tile's chain waits behind the other tile's
+    // barrier, and the per-instruction issue cost (~45 cycles per tcgen05.mma) is paid in parallel. ==============
     {
       constexpr uint32_t IDESC1 = make_idesc(TILE_M, CHUNK);
       constexpr uint32_t IDESC2 = make_idesc(TILE_M, DP);
+      const int s = warp == 1 ? 0 : 1;
       uint32_t c1 = 0, c2 = 0;  // ring consumption counters
-      uint32_t nchunk = 0;      // slices processed so far by this CTA (both tiles advance together)
+      uint32_t nchunk = 0;      // slices processed so far by this CTA
       uint32_t npair = 0;
-      auto gemm1 = [&](int s, uint32_t w1addr) {
+      auto gemm1 = [&](uint32_t w1addr) {
         umma_ts_chain<DP / 16>(tmem_base + COL_H + s * 128, tmem_base + COL_X + s * 128, 8,
                                make_desc(w1addr, CHUNK * 16, 128), (2 * CHUNK * 16) >> 4, IDESC1, 0);
       };
-      auto gemm2 = [&](int s, uint32_t w2addr, bool first) {
+      auto gemm2 = [&](uint32_t w2addr, bool first) {
         // relu(H) is packed per column half: K-steps 0..3 at H_s + 0.., K-steps 4..7 at H_s + 64..
         const uint64_t bd = make_desc(w2addr, DP * 16, 128);
         umma_ts_chain<4>(tmem_base + COL_Y + s * 128, tmem_base + COL_H + s * 128, 8, bd, (2 * DP * 16) >> 4, IDESC2,
@@ -206,17 +209,15 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
                          bd + 4 * (uint64_t)((2 * DP * 16) >> 4), (2 * DP * 16) >> 4, IDESC2, 1u);
       };
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++npair) {
-        // prologue: GEMM1 of slice 0 for both tiles
+        // prologue: GEMM1 of slice 0
         {
           const uint32_t st = c1 % STAGES, u = c1 / STAGES;
           mbar_wait(&w1_full[st], u & 1);
           const uint32_t w1addr = smem_u32(smem + sm.w1 + st * sm.w1_bytes);
-          for (int s = 0; s < 2; ++s) {
-            mbar_wait(&x_full[s], npair & 1);
-            tc_fence_after();
-            gemm1(s, w1addr);
-            umma_commit(&h_full[s]);
-          }
+          mbar_wait(&x_full[s], npair & 1);
+          tc_fence_after();
+          gemm1(w1addr);
+          umma_commit(&h_full[s]);
           umma_commit(&w1_empty[st]);
           ++c1;
         }
@@ -231,16 +232,14 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
             mbar_wait(&w1_full[st1], (c1 / STAGES) & 1);
             w1addr = smem_u32(smem + sm.w1 + st1 * sm.w1_bytes);
           }
-          for (int s = 0; s < 2; ++s) {
-            mbar_wait(&p_full[s], nchunk & 1);  // relu(H_s) of slice j sits (bf16) in the H_s columns
-            if (j == 0) mbar_wait(&y_empty[s], (npair & 1) ^ 1);  // previous pair's Y_s has been read out
-            tc_fence_after();
-            gemm2(s, w2addr, j == 0);
-            if (!more) umma_commit(&y_full[s]);
-            if (more) {
-              gemm1(s, w1addr);  // issued after GEMM2: it overwrites the columns GEMM2 reads
-              umma_commit(&h_full[s]);
-            }
+          mbar_wait(&p_full[s], nchunk & 1);  // relu(H_s) of slice j sits (bf16) in the H_s columns
+          if (j == 0) mbar_wait(&y_empty[s], (npair & 1) ^ 1);  // previous pair's Y_s has been read out
+          tc_fence_after();
+          gemm2(w2addr, j == 0);
+          if (!more) umma_commit(&y_full[s]);
+          if (more) {
+            gemm1(w1addr);  // issued after GEMM2: it overwrites the columns GEMM2 reads
+            umma_commit(&h_full[s]);
           }
           umma_commit(&w2_empty[st2]);
           ++c2;
@@ -253,7 +252,7 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
     }
   } else {
     // ================= epilogue groups: tile s = g & 1, column half hf = g >> 1 =================
-    const int g = (warp - 2) >> 2;
+    const int g = (warp - 2) >> 2;  // warps 2..17
     const int s = g & 1, hf = g >> 1;
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;      // row inside the 128-token tile
