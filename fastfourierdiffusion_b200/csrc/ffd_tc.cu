@@ -10,16 +10,19 @@
 //   epilogue warps: tcgen05.ld H_s -> relu -> bf16 -> tcgen05.st, in place over H_s
 //   GEMM2  Y_s += relu(H_s)[128 x 128] . W2_j^T   A operand again from TMEM; accumulates over all slices
 // so the [tokens x F] hidden activation never leaves the SM and only the weight slices stream through shared
-// memory (pre-packed UMMA core-matrix images, one bulk copy each, 3-stage rings, shared by both token tiles).
+// memory (pre-packed UMMA core-matrix images, one bulk copy each, 2-stage rings, shared by both token tiles).
 // b1 rides in two spare K columns of W1 (hi + lo bf16 parts against constant-1 columns of X), so the slice
-// epilogue is relu + convert only.  The last epilogue adds b2 and the fp32 residual, applies LayerNorm per row
-// (one thread owns a row) into the tile buffer, which one bulk copy stores back.
+// epilogue is relu + convert only.
 //
-// Warp roles (18 warps): 0 = bulk-copy producer (weight slices, token tiles in, finished tiles out),
-// 1 = TMEM allocator + MMA issuer, 2..17 = four epilogue groups of four warps: group g serves tile g & 1 and the
-// (g >> 1)-th half of every 128-column slice, so a slice is converted by eight warps at once (the kernel is bound
-// by the epilogue's latency, not its instruction count).  At the end of a tile pair the lower-half group does the
-// LayerNorm epilogue while the upper-half group already stages the next pair's activations.
+// v5: the slice loop (measured 1350 cycles per slice for both tiles, against 1280 of tensor-pipe time) never
+// stops at a pair boundary.  Four "tile warps" stage the NEXT pair's activations into TMEM as soon as this
+// pair's last GEMM1 has read X_s, and turn Y_s + b2 + residual into the LayerNorm output (in place in the fp32
+// tile buffer, one bulk copy stores it) while the next pair's slices already run; the 16 epilogue warps do
+// nothing but slices.
+//
+// Warp roles (28 warps): 0 = weight-slice producer, 1 / 2 = MMA issuers of tile 0 / tile 1 (two independent issue
+// streams), 3 = token tiles in / finished tiles out, 4..7 / 8..11 = tile warps of tile 0 / 1, 12..27 = four
+// epilogue groups of four warps: group g serves tile g & 1 and the (g >> 1)-th half of every 128-column slice.
 #include "ffd_tc_ptx.cuh"
 
 namespace ffd {
@@ -28,7 +31,7 @@ namespace tc {
 
 constexpr int CHUNK = 128;    // hidden units per slice (UMMA N of GEMM1, K extent of GEMM2)
 constexpr int STAGES = 2;     // weight ring depth (shared memory holds two tile pairs + the rings)
-constexpr int NUM_THREADS = 608;
+constexpr int NUM_THREADS = 896;
 
 // ---- shared-memory plan ------------------------------------------------------------------------
 struct FfnSmem {
@@ -63,18 +66,25 @@ template <int DP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t* __restrict__ w1img,
                  const uint8_t* __restrict__ w2img, const float* __restrict__ b2, const float* __restrict__ lnw,
-                 const float* __restrict__ lnb, int64_t M, int d, int n_chunks, int64_t n_pairs, float eps) {
+                 const float* __restrict__ lnb, int64_t M, int d, int n_chunks, int64_t n_pairs, float eps,
+                 long long* __restrict__ dbg) {
+#ifdef FFD_FFN_STAMPS  // timeline of the third tile pair of CTA 0 (tools/ffn_stamps.py)
+#define FFN_STAMP(cond, slot) do { if (dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (cond)) dbg[slot] = clock64(); } while (0)
+#else
+#define FFN_STAMP(cond, slot) do { } while (0)
+#endif
   extern __shared__ __align__(1024) uint8_t smem[];
   const FfnSmem sm = ffn_smem(DP, d);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);
   uint64_t* w1_full = bars;                 // [STAGES] tx
-  uint64_t* w1_empty = bars + STAGES;       // [STAGES] commit
+  uint64_t* w1_empty = bars + STAGES;       // [STAGES] 2 commits (one per issuing warp)
   uint64_t* w2_full = bars + 2 * STAGES;    // [STAGES] tx
-  uint64_t* w2_empty = bars + 3 * STAGES;   // [STAGES] commit
+  uint64_t* w2_empty = bars + 3 * STAGES;   // [STAGES] 2 commits
   uint64_t* t_full = bars + 4 * STAGES;     // [4] tx: fp32 tile landed in buffer (pair parity, tile)
   uint64_t* y_ready = t_full + 4;           // [4] 128 arrivals: LayerNorm output sits in the tile buffer
   uint64_t* x_full = y_ready + 4;           // [2] 128 arrivals: bf16 X_s written to TMEM
-  uint64_t* h_full = x_full + 2;            // [2] commit
+  uint64_t* x_free = x_full + 2;            // [2] commit: the pair's last GEMM1 has read X_s
+  uint64_t* h_full = x_free + 2;            // [2] commit
   uint64_t* p_full = h_full + 2;            // [2] 256 arrivals (both column halves)
   uint64_t* y_full = p_full + 2;            // [2] commit
   uint64_t* y_empty = y_full + 2;           // [2] 128 arrivals
@@ -85,11 +95,12 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
   constexpr int XC = (DP / 2 + 15) / 16 * 16;       // TMEM columns of the packed bf16 X operand
   constexpr uint32_t COL_H = 0, COL_Y = 256, COL_X = 256 + DP;  // + 128 * s
   static_assert(256 + DP + XC <= 384, "TMEM plan");
+  const uint32_t my_pairs = (uint32_t)((n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x);  // >= 1
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&w1_full[i], 1);
-      mbar_init(&w1_empty[i], 2);  // one commit from each tile's issuing warp
+      mbar_init(&w1_empty[i], 2);
       mbar_init(&w2_full[i], 1);
       mbar_init(&w2_empty[i], 2);
     }
@@ -99,6 +110,7 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&x_full[s], 128);
+      mbar_init(&x_free[s], 1);
       mbar_init(&h_full[s], 1);
       mbar_init(&p_full[s], 256);
       mbar_init(&y_full[s], 1);
@@ -116,86 +128,87 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // provably warp-uniform
 
-  if (warp == 0) {
-    // ================= bulk-copy producer =================
-    if (lane == 0) {
-      uint32_t k1 = 0, k2 = 0, npair = 0;
-      auto load_w1 = [&](int j) {
-        const uint32_t st = k1 % STAGES, u = k1 / STAGES;
-        mbar_wait(&w1_empty[st], (u & 1) ^ 1);
-        mbar_expect_tx(&w1_full[st], sm.w1_bytes);
-        bulk_load(smem + sm.w1 + st * sm.w1_bytes, w1img + (size_t)j * sm.w1_bytes, sm.w1_bytes, &w1_full[st]);
-        ++k1;
-      };
-      auto load_w2 = [&](int j) {
-        const uint32_t st = k2 % STAGES, u = k2 / STAGES;
-        mbar_wait(&w2_empty[st], (u & 1) ^ 1);
-        mbar_expect_tx(&w2_full[st], sm.w2_bytes);
-        bulk_load(smem + sm.w2 + st * sm.w2_bytes, w2img + (size_t)j * sm.w2_bytes, sm.w2_bytes, &w2_full[st]);
-        ++k2;
-      };
-      auto rows_of = [&](int64_t pair, int s) -> int64_t {
-        const int64_t row0 = (pair * 2 + s) * TILE_M;
-        return M - row0 < TILE_M ? (M - row0 > 0 ? M - row0 : 0) : TILE_M;
-      };
-      auto load_pair = [&](int64_t pair, uint32_t np) {
-        for (int s = 0; s < 2; ++s) {
-          const int buf = (np & 1) * 2 + s;
-          const int64_t rows = rows_of(pair, s);
-          if (rows > 0) {
-            mbar_expect_tx(&t_full[buf], (uint32_t)(rows * d * 4));
-            bulk_load(smem + sm.x32 + buf * sm.tile_stride, x + (pair * 2 + s) * TILE_M * d, (uint32_t)(rows * d * 4),
-                      &t_full[buf]);
-          } else {
-            mbar_arrive(&t_full[buf]);
+  // register budget per warpgroup (896 threads x 72 at launch); set at the top of each role branch so that ptxas
+  // allocates per branch
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ================= bulk-copy producer =================
+      if (lane == 0) {
+        uint32_t k1 = 0, k2 = 0;
+        auto load_w1 = [&](int j) {
+          const uint32_t st = k1 % STAGES, u = k1 / STAGES;
+          mbar_wait(&w1_empty[st], (u & 1) ^ 1);
+          mbar_expect_tx(&w1_full[st], sm.w1_bytes);
+          bulk_load(smem + sm.w1 + st * sm.w1_bytes, w1img + (size_t)j * sm.w1_bytes, sm.w1_bytes, &w1_full[st]);
+          ++k1;
+        };
+        auto load_w2 = [&](int j) {
+          const uint32_t st = k2 % STAGES, u = k2 / STAGES;
+          mbar_wait(&w2_empty[st], (u & 1) ^ 1);
+          mbar_expect_tx(&w2_full[st], sm.w2_bytes);
+          bulk_load(smem + sm.w2 + st * sm.w2_bytes, w2img + (size_t)j * sm.w2_bytes, sm.w2_bytes, &w2_full[st]);
+          ++k2;
+        };
+        for (uint32_t np = 0; np < my_pairs; ++np) {
+          // same order as the MMA warps consume: W1_0, then W2_j, W1_{j+1}
+          load_w1(0);
+          for (int j = 0; j < n_chunks; ++j) {
+            load_w2(j);
+            if (j + 1 < n_chunks) load_w1(j + 1);
           }
-        }
-      };
-      auto store_pair = [&](int64_t pair, uint32_t np) {
-        for (int s = 0; s < 2; ++s) {
-          const int buf = (np & 1) * 2 + s;
-          const int64_t rows = rows_of(pair, s);
-          mbar_wait(&y_ready[buf], (np >> 1) & 1);
-          if (rows > 0) {
-            bulk_store(y + (pair * 2 + s) * TILE_M * d, smem + sm.x32 + buf * sm.tile_stride, (uint32_t)(rows * d * 4));
-            bulk_commit();
-          }
-        }
-        bulk_wait_read();
-      };
-      if ((int64_t)blockIdx.x < n_pairs) load_pair(blockIdx.x, 0);
-      if ((int64_t)blockIdx.x + gridDim.x < n_pairs) load_pair((int64_t)blockIdx.x + gridDim.x, 1);
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++npair) {
-        // same order as the MMA warp consumes: W1_0, then W2_j, W1_{j+1}
-        load_w1(0);
-        load_w2(0);
-        if (n_chunks > 1) load_w1(1);
-        if (npair > 0) {
-          // the previous pair: store it, then refill its buffers with the pair after this one
-          store_pair(pair - gridDim.x, npair - 1);
-          if (pair + gridDim.x < n_pairs) load_pair(pair + gridDim.x, npair + 1);
-        }
-        for (int j = 1; j < n_chunks; ++j) {
-          load_w2(j);
-          if (j + 1 < n_chunks) load_w1(j + 1);
         }
       }
-      if (npair > 0) {
-        store_pair((int64_t)blockIdx.x + (int64_t)(npair - 1) * gridDim.x, npair - 1);
+    } else if (warp == 3) {
+      // ================= token-tile load / store =================
+      if (lane == 0) {
+        auto pair_of = [&](uint32_t np) { return (int64_t)blockIdx.x + (int64_t)np * gridDim.x; };
+        auto rows_of = [&](int64_t pair, int s) -> int64_t {
+          const int64_t row0 = (pair * 2 + s) * TILE_M;
+          return M - row0 < TILE_M ? (M - row0 > 0 ? M - row0 : 0) : TILE_M;
+        };
+        auto load_pair = [&](uint32_t np) {
+          const int64_t pair = pair_of(np);
+          for (int s = 0; s < 2; ++s) {
+            const int buf = (np & 1) * 2 + s;
+            const int64_t rows = rows_of(pair, s);
+            if (rows > 0) {
+              mbar_expect_tx(&t_full[buf], (uint32_t)(rows * d * 4));
+              bulk_load(smem + sm.x32 + buf * sm.tile_stride, x + (pair * 2 + s) * TILE_M * d,
+                        (uint32_t)(rows * d * 4), &t_full[buf]);
+            } else {
+              mbar_arrive(&t_full[buf]);
+            }
+          }
+        };
+        load_pair(0);
+        if (my_pairs > 1) load_pair(1);
+        for (uint32_t np = 0; np < my_pairs; ++np) {
+          const int64_t pair = pair_of(np);
+          for (int s = 0; s < 2; ++s) {
+            const int buf = (np & 1) * 2 + s;
+            const int64_t rows = rows_of(pair, s);
+            mbar_wait_relaxed(&y_ready[buf], (np >> 1) & 1, 100);
+            if (rows > 0) {
+              bulk_store(y + (pair * 2 + s) * TILE_M * d, smem + sm.x32 + buf * sm.tile_stride,
+                         (uint32_t)(rows * d * 4));
+              bulk_commit();
+            }
+          }
+          bulk_wait_read();
+          if (np + 2 < my_pairs) load_pair(np + 2);  // the pair's buffers are free again
+        }
         bulk_wait_all();
       }
-    }
-  } else if (warp == 1 || warp == 18) {
-    // ================= MMA issuers: warp 1 drives tile 0 of every pair, warp 18 tile 1 (whole warp converged, one
-    // elected lane issues).  Two independent issue streams: neither tile's chain waits behind the other tile's
-    // barrier, and the per-instruction issue cost (~45 cycles per tcgen05.mma) is paid in parallel. ==============
-    {
+    } else if (warp == 1 || warp == 2) {
+      // ================= MMA issuers: warp 1 drives tile 0 of every pair, warp 2 tile 1 (whole warp converged,
+      // one elected lane issues).  Two independent issue streams: neither tile's chain waits behind the other
+      // tile's barrier, and the per-instruction issue cost (~45 cycles per tcgen05.mma) is paid in parallel. =====
       constexpr uint32_t IDESC1 = make_idesc(TILE_M, CHUNK);
       constexpr uint32_t IDESC2 = make_idesc(TILE_M, DP);
-      const int s = warp == 1 ? 0 : 1;
+      const int s = warp - 1;
       uint32_t c1 = 0, c2 = 0;  // ring consumption counters
       uint32_t nchunk = 0;      // slices processed so far by this CTA
-      uint32_t npair = 0;
       auto gemm1 = [&](uint32_t w1addr) {
         umma_ts_chain<DP / 16>(tmem_base + COL_H + s * 128, tmem_base + COL_X + s * 128, 8,
                                make_desc(w1addr, CHUNK * 16, 128), (2 * CHUNK * 16) >> 4, IDESC1, 0);
@@ -208,8 +221,9 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
         umma_ts_chain<4>(tmem_base + COL_Y + s * 128, tmem_base + COL_H + s * 128 + 64, 8,
                          bd + 4 * (uint64_t)((2 * DP * 16) >> 4), (2 * DP * 16) >> 4, IDESC2, 1u);
       };
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++npair) {
-        // prologue: GEMM1 of slice 0
+      for (uint32_t npair = 0; npair < my_pairs; ++npair) {
+        // prologue: GEMM1 of slice 0 (its H columns are free: the previous pair's last GEMM2 precedes it in
+        // issue order)
         {
           const uint32_t st = c1 % STAGES, u = c1 / STAGES;
           mbar_wait(&w1_full[st], u & 1);
@@ -218,6 +232,7 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
           tc_fence_after();
           gemm1(w1addr);
           umma_commit(&h_full[s]);
+          if (n_chunks == 1) umma_commit(&x_free[s]);
           umma_commit(&w1_empty[st]);
           ++c1;
         }
@@ -233,13 +248,17 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
             w1addr = smem_u32(smem + sm.w1 + st1 * sm.w1_bytes);
           }
           mbar_wait(&p_full[s], nchunk & 1);  // relu(H_s) of slice j sits (bf16) in the H_s columns
+          FFN_STAMP(npair == 2 && s == 0, j * 8 + 0);
           if (j == 0) mbar_wait(&y_empty[s], (npair & 1) ^ 1);  // previous pair's Y_s has been read out
           tc_fence_after();
           gemm2(w2addr, j == 0);
+          FFN_STAMP(npair == 2 && s == 0, j * 8 + 1);
           if (!more) umma_commit(&y_full[s]);
           if (more) {
             gemm1(w1addr);  // issued after GEMM2: it overwrites the columns GEMM2 reads
             umma_commit(&h_full[s]);
+            if (j + 2 == n_chunks) umma_commit(&x_free[s]);  // that was the pair's last GEMM1
+            FFN_STAMP(npair == 2 && s == 0, j * 8 + 2);
           }
           umma_commit(&w2_empty[st2]);
           ++c2;
@@ -249,24 +268,25 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
           }
         }
       }
+      mbar_wait(&y_full[s], (my_pairs - 1) & 1);  // drain
     }
-  } else {
-    // ================= epilogue groups: tile s = g & 1, column half hf = g >> 1 =================
-    const int g = (warp - 2) >> 2;  // warps 2..17
-    const int s = g & 1, hf = g >> 1;
+  } else if (warp < 12) {
+    // ================= tile warps (group s = tile s of every pair): stage the next pair's X, finish this pair's
+    // LayerNorm =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    const int s = (warp - 4) >> 2;
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;      // row inside the 128-token tile
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const uint32_t hcol = tmem_base + lane_base + COL_H + s * 128 + hf * 64;  // this group's 64 fp32 columns
-    uint32_t nchunk = 0, npair = 0;
-
     // bf16 X_s -> TMEM (A operand of GEMM1) from the fp32 tile buffer; columns d, d+1 are the constant-1 bias
-    // columns.  Done by the upper-half group of each tile.
-    auto stage_x = [&](int64_t pair, uint32_t np) {
+    // columns
+    auto stage_x = [&](uint32_t np) {
+      const int64_t pair = (int64_t)blockIdx.x + (int64_t)np * gridDim.x;
       const int buf = (np & 1) * 2 + s;
       const float4* src = reinterpret_cast<const float4*>(smem + sm.x32 + buf * sm.tile_stride) + (size_t)row * (d / 4);
       const bool valid = (pair * 2 + s) * TILE_M + row < M;
-      mbar_wait(&t_full[buf], (np >> 1) & 1);
+      mbar_wait_relaxed(&t_full[buf], (np >> 1) & 1, 100);
+      // convert first (registers), so that only the TMEM stores remain once X_s is free
       uint32_t xp[XC];
 #pragma unroll
       for (int i = 0; i < XC / 2; ++i) {  // 4 columns -> 2 packed words
@@ -280,96 +300,122 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
         xp[2 * i] = pack_bf16(v.x, v.y);
         xp[2 * i + 1] = pack_bf16(v.z, v.w);
       }
+      if (np > 0) {
+        mbar_wait_relaxed(&x_free[s], (np - 1) & 1, 20);  // the previous pair's last GEMM1 has read X_s
+        tc_fence_after();
+      }
 #pragma unroll
       for (int c0 = 0; c0 < XC; c0 += 16) FFD_TMEM_ST16(tmem_base + lane_base + COL_X + s * 128 + c0, (xp + c0));
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&x_full[s]);
     };
-
-    if (hf == 1 && (int64_t)blockIdx.x < n_pairs) stage_x(blockIdx.x, 0);
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++npair) {
-      // ---- per slice: this group's half of H_s (TMEM fp32) -> relu -> bf16, written back in place ----
-      for (int j = 0; j < n_chunks; ++j, ++nchunk) {
-        mbar_wait(&h_full[s], nchunk & 1);
-        tc_fence_after();
-        uint32_t r[64], pk[32];
-        FFD_TMEM_LD16(hcol, r);
-        FFD_TMEM_LD16(hcol + 16, (r + 16));
-        FFD_TMEM_LD16(hcol + 32, (r + 32));
-        FFD_TMEM_LD16(hcol + 48, (r + 48));
+    // Y_s + b2 + residual -> LayerNorm, in place in the fp32 tile buffer (one thread owns a row).  Y_s is released
+    // after one sweep, so the next pair's first GEMM2 is not held up.
+    auto finish = [&](uint32_t np) {
+      const int buf = (np & 1) * 2 + s;
+      float4* myrow = reinterpret_cast<float4*>(smem + sm.x32 + buf * sm.tile_stride) + (size_t)row * (d / 4);
+      mbar_wait_relaxed(&y_full[s], np & 1, 40);
+      tc_fence_after();
+      float s1 = 0.f, s2 = 0.f;
+      // 16 accumulator columns + b2 + residual -> the tile buffer, row statistics
+      auto unit = [&](const uint32_t (&r)[16], const float4 (&res)[4], int c0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = c0 + 4 * i;
+          if (c < d) {
+            float4 v;
+            v.x = __uint_as_float(r[4 * i]) + consts[c] + res[i].x;
+            v.y = __uint_as_float(r[4 * i + 1]) + consts[c + 1] + res[i].y;
+            v.z = __uint_as_float(r[4 * i + 2]) + consts[c + 2] + res[i].z;
+            v.w = __uint_as_float(r[4 * i + 3]) + consts[c + 3] + res[i].w;
+            myrow[c >> 2] = v;
+            s1 += (v.x + v.y) + (v.z + v.w);
+            s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+          }
+        }
+      };
+      // two 16-column units per TMEM round trip; the residual loads are issued before the round trip completes
+#pragma unroll
+      for (int c0 = 0; c0 < DP; c0 += 32) {
+        uint32_t ra[16], rb[16];
+        float4 e[4];
+        constexpr bool kTwoAlways = (DP % 32) == 0;
+        const bool two = kTwoAlways || c0 + 16 < DP;
+        FFD_TMEM_LD16(tmem_base + lane_base + COL_Y + s * 128 + c0, ra);
+        if (two) FFD_TMEM_LD16(tmem_base + lane_base + COL_Y + s * 128 + c0 + 16, rb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = c0 + 4 * i;
+          e[i] = c < d ? myrow[c >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) pk[e] = relu_pack_bf16(r[2 * e], r[2 * e + 1]);
-        // 64 fp32 columns -> 32 packed columns at the start of this group's own half
-        FFD_TMEM_ST16(hcol, pk);
-        FFD_TMEM_ST16(hcol + 16, (pk + 16));
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[s]);
-      }
-      if (hf == 1) {
-        // ---- the next pair's activations can go to TMEM as soon as this pair's last GEMM1 has read X_s ----
-        if (pair + gridDim.x < n_pairs) {
-          mbar_wait(&y_full[s], npair & 1);  // all MMAs of this pair (GEMM1 included) are complete
-          stage_x(pair + gridDim.x, npair + 1);
+        if (c0 + 32 >= DP) {
+          tc_fence_before();
+          mbar_arrive(&y_empty[s]);
         }
-      } else {
-        // ---- final: Y_s + b2 + residual -> LayerNorm -> tile buffer (two sweeps keep registers low) ----
-        const int buf = (npair & 1) * 2 + s;
-        float4* myrow = reinterpret_cast<float4*>(smem + sm.x32 + buf * sm.tile_stride) + (size_t)row * (d / 4);
-        const bool valid = (pair * 2 + s) * TILE_M + row < M;
-        mbar_wait(&y_full[s], npair & 1);
-        tc_fence_after();
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int c0 = 0; c0 < DP; c0 += 16) {
-          uint32_t r[16];
-          FFD_TMEM_LD16(tmem_base + lane_base + COL_Y + s * 128 + c0, r);
-          tmem_ld_wait();
+        unit(ra, e, c0);
+        if (two) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int c = c0 + 4 * i;
-            if (c < d) {
-              const float4 xr = valid ? myrow[c >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
-              const float a0 = __uint_as_float(r[4 * i]) + consts[c] + xr.x;
-              const float a1 = __uint_as_float(r[4 * i + 1]) + consts[c + 1] + xr.y;
-              const float a2 = __uint_as_float(r[4 * i + 2]) + consts[c + 2] + xr.z;
-              const float a3 = __uint_as_float(r[4 * i + 3]) + consts[c + 3] + xr.w;
-              s1 += (a0 + a1) + (a2 + a3);
-              s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, s2))));
-            }
+            const int c = c0 + 16 + 4 * i;
+            e[i] = c < d ? myrow[c >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          unit(rb, e, c0 + 16);
         }
-        const float mean = s1 / (float)d;
-        const float rstd = rsqrtf(fmaxf(s2 / (float)d - mean * mean, 0.f) + eps);
-#pragma unroll
-        for (int c0 = 0; c0 < DP; c0 += 16) {
-          uint32_t r[16];
-          FFD_TMEM_LD16(tmem_base + lane_base + COL_Y + s * 128 + c0, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c = c0 + 4 * i;
-            if (c < d && valid) {
-              const float4 xr = myrow[c >> 2];
-              float4 o;
-              o.x = (__uint_as_float(r[4 * i]) + consts[c] + xr.x - mean) * rstd * consts[DP + c] + consts[2 * DP + c];
-              o.y = (__uint_as_float(r[4 * i + 1]) + consts[c + 1] + xr.y - mean) * rstd * consts[DP + c + 1] +
-                    consts[2 * DP + c + 1];
-              o.z = (__uint_as_float(r[4 * i + 2]) + consts[c + 2] + xr.z - mean) * rstd * consts[DP + c + 2] +
-                    consts[2 * DP + c + 2];
-              o.w = (__uint_as_float(r[4 * i + 3]) + consts[c + 3] + xr.w - mean) * rstd * consts[DP + c + 3] +
-                    consts[2 * DP + c + 3];
-              myrow[c >> 2] = o;
-            }
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(&y_empty[s]);
-        fence_proxy_async();
-        mbar_arrive(&y_ready[buf]);
       }
+      const float mean = s1 / (float)d;
+      const float rstd = rsqrtf(fmaxf(s2 / (float)d - mean * mean, 0.f) + eps);
+#pragma unroll 6
+      for (int c = 0; c < d; c += 4) {
+        const float4 v = myrow[c >> 2];
+        float4 o;
+        o.x = (v.x - mean) * rstd * consts[DP + c] + consts[2 * DP + c];
+        o.y = (v.y - mean) * rstd * consts[DP + c + 1] + consts[2 * DP + c + 1];
+        o.z = (v.z - mean) * rstd * consts[DP + c + 2] + consts[2 * DP + c + 2];
+        o.w = (v.w - mean) * rstd * consts[DP + c + 3] + consts[2 * DP + c + 3];
+        myrow[c >> 2] = o;
+      }
+      fence_proxy_async();
+      mbar_arrive(&y_ready[buf]);
+    };
+    stage_x(0);
+    for (uint32_t np = 0; np < my_pairs; ++np) {
+      FFN_STAMP(warp == 4 && np == 2, 200);
+      if (np + 1 < my_pairs) stage_x(np + 1);
+      FFN_STAMP(warp == 4 && np == 2, 201);
+      finish(np);
+      FFN_STAMP(warp == 4 && np == 2, 202);
+    }
+  } else {
+    // ================= epilogue groups (slices only): tile s = g & 1, column half hf = g >> 1 =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
+    const int g = (warp - 12) >> 2;
+    const int s = g & 1, hf = g >> 1;
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t hcol = tmem_base + lane_base + COL_H + s * 128 + hf * 64;  // this group's 64 fp32 columns
+    const uint32_t n_slices = my_pairs * (uint32_t)n_chunks;
+    // this group's half of H_s (TMEM fp32) -> relu -> bf16, written back in place
+    for (uint32_t nchunk = 0; nchunk < n_slices; ++nchunk) {
+      mbar_wait_relaxed(&h_full[s], nchunk & 1, 20);
+      tc_fence_after();
+      FFN_STAMP(warp == 12 && nchunk - 2u * n_chunks < (uint32_t)n_chunks, (nchunk - 2u * n_chunks) * 8 + 3);
+      uint32_t r[64], pk[32];
+      FFD_TMEM_LD16(hcol, r);
+      FFD_TMEM_LD16(hcol + 16, (r + 16));
+      FFD_TMEM_LD16(hcol + 32, (r + 32));
+      FFD_TMEM_LD16(hcol + 48, (r + 48));
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) pk[e] = relu_pack_bf16(r[2 * e], r[2 * e + 1]);
+      // 64 fp32 columns -> 32 packed columns at the start of this group's own half
+      FFD_TMEM_ST16(hcol, pk);
+      FFD_TMEM_ST16(hcol + 16, (pk + 16));
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[s]);
+      FFN_STAMP(warp == 12 && nchunk - 2u * n_chunks < (uint32_t)n_chunks, (nchunk - 2u * n_chunks) * 8 + 4);
     }
   }
 
@@ -454,6 +500,8 @@ int tc_pack_weights(const ffd_dims& m, const float* weights, void* packed, cudaS
   return FFD_OK;
 }
 
+extern long long* g_attn_dbg;  // optional clock64 stamp buffer (ffd_debug_set_attn_stamps)
+
 template <int DP>
 static int launch_ffn_tc(const ffd_dims& m, const uint8_t* img, const float* w, const Arena& ar, const float* x,
                          float* y, int64_t M, cudaStream_t s) {
@@ -473,7 +521,7 @@ static int launch_ffn_tc(const ffd_dims& m, const uint8_t* img, const float* w, 
   const uint8_t* w2img = img + (size_t)n_chunks * sm.w1_bytes;
   tc::ffn_ln_tc_kernel<DP><<<grid, tc::NUM_THREADS, sm.total, s>>>(x, y, w1img, w2img, w + ar.b2, w + ar.n2w,
                                                                     w + ar.n2b, M, m.d_model, n_chunks, n_pairs,
-                                                                    1e-5f);
+                                                                    1e-5f, g_attn_dbg);
   FFD_CHECK_LAUNCH("ffn_ln_tc_kernel");
   return FFD_OK;
 }
