@@ -311,7 +311,7 @@ def run_ours(args):
         n_exp = float(M) * ECG["n_head"] * ECG["max_len"]
         mufu_peak = 148 * 16 * (clocks.summary().get("sm_mhz") or 1965.0) * 1e6
         attn_flops = M * (4.0 * 72 * 72 + 4.0 * ECG["max_len"] * 72)
-        attn_entry = {"kernel": "attn_cached_tc_kernel<80> (+ K/V image pack)", "bound": "sfu (MUFU.EX2)",
+        attn_entry = {"kernel": "attn_cached_tc_kernel<80, 3> (+ K/V image pack)", "bound": "sfu (MUFU.EX2)",
                       "achieved": n_exp / (attn_ms * 1e-3) / 1e12, "peak": mufu_peak / 1e12, "unit": "Texp/s",
                       "frac": n_exp / (attn_ms * 1e-3) / mufu_peak, "ms_per_launch": attn_ms,
                       "tensor_tflops_algorithmic": attn_flops / (attn_ms * 1e-3) / 1e12,
