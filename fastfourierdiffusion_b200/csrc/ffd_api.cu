@@ -46,12 +46,17 @@ static int run_layer(const ffd_forward_args& a, const Arena& ar, const Workspace
     return tc_ffn_ln(m, a.packed, a.weights, layer, ws.h, ws.h, M, s);
   }
   if (branch == 0 && a.precision == FFD_PREC_BF16 && tc_attn_supported(m)) {
-    // stock attention (all K/V own) on the same tensor-core kernel: K/V projection (fp32), per-sample operand
-    // images, attention block, FFN block.  Q is projected inside the kernel.
-    if ((rc = launch_linear(ws.h, d, w + ar.in_w + (int64_t)d * d, d, w + ar.in_b + d, ws.qkv + d, 3 * d, M, 2 * d, d,
-                            0, s)))
-      return rc;
-    if ((rc = tc_attn_own(m, tc_attn_image(m, a.packed, layer), ws.kvimg_own, ws.qkv, 3 * d, d, 2 * d, a.weights,
+    // stock attention (all K/V own) on the same tensor-core kernel: K/V projection + per-sample operand images
+    // (one tcgen05 kernel; fp32 projection + pack kernel for head dims > 7), attention block, FFN block.  Q is
+    // projected inside the attention kernel.
+    const float* kv_src = nullptr;
+    if (!tc_attn_own_fused(m)) {
+      if ((rc = launch_linear(ws.h, d, w + ar.in_w + (int64_t)d * d, d, w + ar.in_b + d, ws.qkv + d, 3 * d, M, 2 * d,
+                              d, 0, s)))
+        return rc;
+      kv_src = ws.qkv;
+    }
+    if ((rc = tc_attn_own(m, tc_attn_image(m, a.packed, layer), ws.kvimg_own, kv_src, 3 * d, d, 2 * d, a.weights,
                           layer, ws.h, ws.h, M, s)))
       return rc;
     return tc_ffn_ln(m, a.packed, a.weights, layer, ws.h, ws.h, M, s);

@@ -59,8 +59,10 @@ int tc_attn_cached(const ffd_dims& m, const void* attn_img, const void* kvimg, c
 
 // stock attention block (every sample attends to its own keys): K/V rows are read from kv_src[(b L + key) * ld +
 // k_off / v_off + ...] (fp32), packed into per-sample operand images (kvimg_own, tc_kv_own_image_bytes) and fed
-// to the same kernel with sample-aligned tiles.  y may alias x.
+// to the same kernel with sample-aligned tiles.  y may alias x.  With kv_src == nullptr (allowed when
+// tc_attn_own_fused(m)) the K/V projection runs on the tensor cores inside the image build, straight from x.
 int64_t tc_kv_own_image_bytes(const ffd_dims& m, int64_t B);
+bool tc_attn_own_fused(const ffd_dims& m);
 int tc_attn_own(const ffd_dims& m, const void* attn_img, void* kvimg_own, const float* kv_src, int ld, int k_off,
                 int v_off, const float* weights, int layer, const float* x, float* y, int64_t M, cudaStream_t s);
 

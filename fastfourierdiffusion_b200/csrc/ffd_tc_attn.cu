@@ -762,6 +762,215 @@ __global__ void pack_attn_kernel(const float* __restrict__ in_w, const float* __
   }
 }
 
+// Weight images of the fused K/V projection (stock attention, hd <= 7), bf16 core-matrix order, bias hi/lo in
+// columns d, d+1:
+//   WkP [QN n x DP k]: row 16 qt + s = Wk[(qt G + s / hd) hd + s % hd, :] for s < G hd: the K rows of the G heads
+//       of Q tile qt, already in the slot order of their K images (zero rows elsewhere);
+//   WvP [8 H n x DP k]:  row 8 h + c = Wv[h hd + c, :] (c < hd); row 8 h + 7 picks the constant-1 column of X (the
+//       row-sum slot of the V image).
+__global__ void pack_kvproj_kernel(const float* __restrict__ in_w, const float* __restrict__ in_b,
+                                   __nv_bfloat16* __restrict__ wk, __nv_bfloat16* __restrict__ wv, int d, int H,
+                                   int DP, int G, int QN) {
+  const int hd = d / H, NK = QN, NVR = 8 * H;
+  const int total = (NK + NVR) * DP;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const bool is_v = i >= NK * DP;
+    const int e = is_v ? i - NK * DP : i;
+    const int rows = is_v ? NVR : NK;
+    const int kg = e / (rows * 8), rem = e % (rows * 8);
+    const int n = (rem / 64) * 8 + (rem % 64) / 8, k = kg * 8 + rem % 8;
+    float v = 0.f;
+    int r = -1;  // row of in_proj (K rows at d.., V rows at 2d..)
+    if (!is_v) {
+      const int qt = n / 16, slot = n % 16, h = qt * G + slot / hd;
+      if (slot < G * hd && h < H) r = d + h * hd + slot % hd;
+    } else {
+      const int h = n / 8, c = n % 8;
+      if (c < hd) r = 2 * d + h * hd + c;
+      else if (c == 7) v = (k == d) ? 1.f : 0.f;
+    }
+    if (r >= 0) {
+      const float b = in_b[r];
+      if (k < d) v = in_w[(int64_t)r * d + k];
+      else if (k == d) v = __bfloat162float(__float2bfloat16_rn(b));
+      else if (k == d + 1) v = b - __bfloat162float(__float2bfloat16_rn(b));
+    }
+    (is_v ? wv : wk)[e] = __float2bfloat16_rn(v);
+  }
+}
+
+// Fused K/V projection + operand-image build for stock attention (hd <= 7): one CTA per 128-row tile of a sample.
+//   K slots[128 x QN] = X[128 x DP] . WkP^T,  V dims[128 x 8 H] = X . WvP^T     (tcgen05, fp32 accumulate in TMEM)
+// and every thread (= key row) writes its rows of the per-sample images (pack_kv_own_kernel's layout): two 16-byte
+// K units per head from the accumulator (the MMA already produced the slot order; each head keeps its own slots,
+// its tile mates' are zeroed), the V units after an 8 x 8 transpose through shared memory (a V unit holds 8
+// consecutive keys of one dim).
+template <int DP>
+__global__ void __launch_bounds__(128, 2)
+kv_own_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wkimg, uint8_t* __restrict__ img, int d,
+                 int H, int hd, int G, int QN, int L, int NCH, int CK, int tps) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int NK = QN, NVR = 8 * H;
+  const int wk_bytes = NK * DP * 2, wv_bytes = NVR * DP * 2;
+  uint8_t* xo = smem;                                   // bf16 A operand [128 x DP]
+  uint8_t* wk = xo + TILE_M * DP * 2;                   // WkP, then WvP
+  uint8_t* stage = wk + wk_bytes + wv_bytes;            // [4 warps][32 keys][8 dims] fp16
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 4 * 32 * 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* w_full = bars;
+  uint64_t* k_done = bars + 1;
+  uint64_t* v_done = bars + 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = threadIdx.x;
+  const int64_t sample = blockIdx.x / tps;
+  const int part = (int)(blockIdx.x - sample * tps);
+  const int rows = L - part * TILE_M < TILE_M ? L - part * TILE_M : TILE_M;
+  const bool valid = row < rows;
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    mbar_init(k_done, 1);
+    mbar_init(v_done, 1);
+    fence_barrier_init();
+    mbar_expect_tx(w_full, wk_bytes + wv_bytes);
+    bulk_load(wk, wkimg, wk_bytes + wv_bytes, w_full);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  // stage this tile's rows as the bf16 A operand; rows beyond the sample are all zero (their constant columns too,
+  // so that their V row-sum slot stays 0)
+  {
+    const float4* src = reinterpret_cast<const float4*>(x + (sample * L + (int64_t)part * TILE_M + row) * d);
+    const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
+    constexpr int NG = DP / 8;
+#pragma unroll 5
+    for (int kg = 0; kg < NG; ++kg) {
+      const int c = kg * 8;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
+      if (valid) {
+        if (c < d) a = src[2 * kg];
+        else if (c == d) a.x = 1.f, a.y = 1.f;
+        if (c + 4 < d) b4 = src[2 * kg + 1];
+        else if (c + 4 == d) b4.x = 1.f, b4.y = 1.f;
+      }
+      uint4 q;
+      q.x = pack_bf16(a.x, a.y);
+      q.y = pack_bf16(a.z, a.w);
+      q.z = pack_bf16(b4.x, b4.y);
+      q.w = pack_bf16(b4.z, b4.w);
+      *reinterpret_cast<uint4*>(xo + row_off + kg * (TILE_M * 16)) = q;
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t LBO128 = 128 * 16;
+  if (warp == 0) {
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    umma_ss_chain<DP / 16>(tmem_base, make_desc(smem_u32(xo), LBO128, 128), (2 * LBO128) >> 4,
+                           make_desc(smem_u32(wk), NK * 16, 128), (2 * NK * 16) >> 4, make_idesc(TILE_M, NK), 0);
+    umma_commit(k_done);
+    umma_ss_chain<DP / 16>(tmem_base + 128, make_desc(smem_u32(xo), LBO128, 128), (2 * LBO128) >> 4,
+                           make_desc(smem_u32(wk + wk_bytes), NVR * 16, 128), (2 * NVR * 16) >> 4,
+                           make_idesc(TILE_M, NVR), 0);
+    umma_commit(v_done);
+  }
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const size_t k_bytes = (size_t)CK * HP * 2, img_stride = 2 * k_bytes;
+  uint8_t* simg = img + (size_t)sample * H * NCH * img_stride;
+  // keys this thread writes: its own row, plus (last tile of the sample) the padded keys beyond the tiles
+  const int key = part * TILE_M + row;
+  const int n_keys = NCH * CK;
+  // ---- K images ----
+  mbar_wait(k_done, 0);
+  tc_fence_after();
+  for (int qt = 0; qt * 16 < NK; ++qt) {
+    uint32_t r[16];
+    FFD_TMEM_LD16(tmem_base + lane_base + 16 * qt, r);
+    tmem_ld_wait();
+    if (key < n_keys) {
+      const int ch = key / CK, kl = key - ch * CK;
+      for (int g = 0; g < G; ++g) {
+        const int h = qt * G + g;
+        if (h >= H) break;
+        const int lo = g * hd, hi = lo + hd;  // this head's slots
+        float v[16];
+#pragma unroll
+        for (int sl = 0; sl < 15; ++sl) v[sl] = (sl >= lo && sl < hi) ? __uint_as_float(r[sl]) : 0.f;
+        v[15] = valid ? 0.f : -29952.f;  // padded keys: score -29952 -> weight 0
+        uint4 q0, q1;
+        q0.x = pack_bf16(v[0], v[1]), q0.y = pack_bf16(v[2], v[3]), q0.z = pack_bf16(v[4], v[5]);
+        q0.w = pack_bf16(v[6], v[7]);
+        q1.x = pack_bf16(v[8], v[9]), q1.y = pack_bf16(v[10], v[11]), q1.z = pack_bf16(v[12], v[13]);
+        q1.w = pack_bf16(v[14], v[15]);
+        uint8_t* kimg = simg + (size_t)(h * NCH + ch) * img_stride;
+        *reinterpret_cast<uint4*>(kimg + (size_t)kl * 16) = q0;
+        *reinterpret_cast<uint4*>(kimg + (size_t)(CK + kl) * 16) = q1;
+      }
+    }
+  }
+  if (part == tps - 1) {
+    // padded keys not covered by any tile (only when NCH CK > 128 tps)
+    const uint4 z0 = make_uint4(0u, 0u, 0u, 0u);
+    uint4 z1 = z0;
+    z1.w = pack_bf16(0.f, -29952.f);
+    for (int k2 = tps * TILE_M + row; k2 < n_keys; k2 += TILE_M) {
+      const int ch = k2 / CK, kl = k2 - ch * CK;
+      for (int h = 0; h < H; ++h) {
+        uint8_t* kimg = simg + (size_t)(h * NCH + ch) * img_stride;
+        *reinterpret_cast<uint4*>(kimg + (size_t)kl * 16) = z0;
+        *reinterpret_cast<uint4*>(kimg + (size_t)(CK + kl) * 16) = z1;
+        if ((kl & 7) == 0) {  // V units of this group of 8 padded keys: 16 dims of zeros
+          uint8_t* vimg = kimg + k_bytes + (size_t)(kl >> 3) * 256;
+          for (int u = 0; u < 16; ++u) *reinterpret_cast<uint4*>(vimg + u * 16) = z0;
+        }
+      }
+    }
+  }
+  // ---- V images: 8 x 8 transpose of (key, dim) through shared memory, per group of 8 keys ----
+  mbar_wait(v_done, 0);
+  tc_fence_after();
+  uint4* my_stage = reinterpret_cast<uint4*>(stage + warp * 512);
+  const uint16_t* col = reinterpret_cast<const uint16_t*>(stage + warp * 512) + (lane & ~7) * 8 + (lane & 7);
+  for (int h0 = 0; h0 < H; h0 += 2) {
+    // two heads per TMEM load: columns 8 h0 .. 8 h0 + 15
+    uint32_t r[16];
+    FFD_TMEM_LD16(tmem_base + lane_base + 128 + 8 * h0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int h = h0 + hh;
+      if (h < H) {
+        uint4 q;
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(__uint_as_float(r[8 * hh + 1])), "f"(__uint_as_float(r[8 * hh + 0])));
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(__uint_as_float(r[8 * hh + 3])), "f"(__uint_as_float(r[8 * hh + 2])));
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(__uint_as_float(r[8 * hh + 5])), "f"(__uint_as_float(r[8 * hh + 4])));
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(__uint_as_float(r[8 * hh + 7])), "f"(__uint_as_float(r[8 * hh + 6])));
+        __syncwarp();
+        my_stage[lane] = q;  // [key][8 dims]
+        __syncwarp();
+        // lane 8 i + j gathers dim j of keys 8 i .. 8 i + 7
+        uint4 t;
+        t.x = (uint32_t)col[0] | ((uint32_t)col[8] << 16);
+        t.y = (uint32_t)col[16] | ((uint32_t)col[24] << 16);
+        t.z = (uint32_t)col[32] | ((uint32_t)col[40] << 16);
+        t.w = (uint32_t)col[48] | ((uint32_t)col[56] << 16);
+        const int key0 = part * TILE_M + (row & ~7);  // first key of this lane's group
+        if (key0 < n_keys) {
+          const int ch = key0 / CK, kl = key0 - ch * CK;
+          uint8_t* vimg = simg + (size_t)(h * NCH + ch) * img_stride + k_bytes + (size_t)(kl >> 3) * 256;
+          *reinterpret_cast<uint4*>(vimg + (lane & 7) * 16) = t;
+          *reinterpret_cast<uint4*>(vimg + (8 + (lane & 7)) * 16) = make_uint4(0u, 0u, 0u, 0u);  // dims 8..15
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
 // Images per (layer, head h, key chunk c), keys [c CK, (c+1) CK):
 //   K: B operand [CK n(key) x 16 k(slot)], bf16: head h's dims in the slots of its place g = h % G inside its Q
 //      tile, zeros in the slots of its tile mates; slot 15 of a padded key row is -29952 (slot 15 of Q is 1).
@@ -869,9 +1078,15 @@ bool tc_attn_supported(const ffd_dims& m) {
   return tc::attn_smem(tc::dp_of(m.d_model), g.QN, g.CK, m.d_model).total <= 232448;
 }
 
+// fused K/V projection images (WkP, WvP) exist for hd <= 7 and at most 16 heads (TMEM plan of kv_own_tc_kernel)
+static bool kvproj_fused(const ffd_dims& m) {
+  const AttnGeom g = attn_geom(m);
+  return g.hd <= 7 && g.QN <= 128 && 8 * m.n_head <= 128 && m.n_head % 2 == 0;
+}
+
 int64_t tc_attn_image_bytes(const ffd_dims& m) {
   const int DP = tc::dp_of(m.d_model), QN = attn_geom(m).QN;
-  return (int64_t)(QN * DP + DP * DP) * 2;
+  return (int64_t)(QN * DP + DP * DP + (kvproj_fused(m) ? (QN + 8 * m.n_head) * DP : 0)) * 2;
 }
 
 int64_t tc_kv_image_bytes(const ffd_dims& m) {
@@ -890,6 +1105,12 @@ int tc_pack_attn(const ffd_dims& m, const float* weights, void* img_base, int64_
     tc::pack_attn_kernel<<<32, 256, 0, s>>>(w + ar.in_w, w + ar.in_b, w + ar.out_w, w + ar.out_b, wq,
                                             wq + (size_t)g.QN * DP, m.d_model, m.n_head, DP, g.G, g.QN);
     FFD_CHECK_LAUNCH("pack_attn_kernel");
+    if (kvproj_fused(m)) {
+      __nv_bfloat16* wk = wq + (size_t)g.QN * DP + (size_t)DP * DP;
+      tc::pack_kvproj_kernel<<<32, 256, 0, s>>>(w + ar.in_w, w + ar.in_b, wk, wk + (size_t)g.QN * DP, m.d_model,
+                                                m.n_head, DP, g.G, g.QN);
+      FFD_CHECK_LAUNCH("pack_kvproj_kernel");
+    }
   }
   return FFD_OK;
 }
@@ -968,15 +1189,44 @@ int64_t tc_kv_own_image_bytes(const ffd_dims& m, int64_t B) {
   return B * g.NV * 2 * g.CK * tc::HP * 2;
 }
 
+template <int DP>
+static int launch_kv_own(const ffd_dims& m, const AttnGeom& g, const uint8_t* wkimg, const float* x, void* img,
+                         int64_t B, cudaStream_t s) {
+  const int smem = tc::TILE_M * DP * 2 + (g.QN + 8 * m.n_head) * DP * 2 + 4 * 32 * 16 + 64;
+  FFD_CHECK_CUDA(cudaFuncSetAttribute(tc::kv_own_tc_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int tps = (m.max_len + tc::TILE_M - 1) / tc::TILE_M;
+  tc::kv_own_tc_kernel<DP><<<(unsigned)(B * tps), 128, smem, s>>>(x, wkimg, (uint8_t*)img, m.d_model, m.n_head, g.hd,
+                                                                   g.G, g.QN, m.max_len, g.NCH, g.CK, tps);
+  FFD_CHECK_LAUNCH("kv_own_tc_kernel");
+  return FFD_OK;
+}
+
+bool tc_attn_own_fused(const ffd_dims& m) { return kvproj_fused(m); }
+
 int tc_attn_own(const ffd_dims& m, const void* attn_img, void* kvimg_own, const float* kv_src, int ld, int k_off,
                 int v_off, const float* weights, int layer, const float* x, float* y, int64_t M, cudaStream_t s) {
   const Arena ar = arena_of(m);
   const AttnGeom g = attn_geom(m);
   const float* w = weights + ar.layer0 + (int64_t)layer * ar.layer_stride;
   const int64_t B = M / m.max_len;
-  tc::pack_kv_own_kernel<<<148 * 16, 256, 0, s>>>(kv_src, ld, k_off, v_off, (uint4*)kvimg_own, B, m.max_len, g.hd,
-                                                   m.n_head, g.G, g.NCH, g.CK);
-  FFD_CHECK_LAUNCH("pack_kv_own_kernel");
+  if (kv_src == nullptr) {
+    // K/V projection fused into the image build (tcgen05): images straight from x
+    const int DP = tc::dp_of(m.d_model);
+    const uint8_t* wk = (const uint8_t*)attn_img + (size_t)(g.QN * DP + DP * DP) * 2;
+    int rc = FFD_ERR_UNSUPPORTED;
+    switch (DP) {
+      case 16: rc = launch_kv_own<16>(m, g, wk, x, kvimg_own, B, s); break;
+      case 32: rc = launch_kv_own<32>(m, g, wk, x, kvimg_own, B, s); break;
+      case 48: rc = launch_kv_own<48>(m, g, wk, x, kvimg_own, B, s); break;
+      case 64: rc = launch_kv_own<64>(m, g, wk, x, kvimg_own, B, s); break;
+      case 80: rc = launch_kv_own<80>(m, g, wk, x, kvimg_own, B, s); break;
+    }
+    if (rc) return rc;
+  } else {
+    tc::pack_kv_own_kernel<<<148 * 16, 256, 0, s>>>(kv_src, ld, k_off, v_off, (uint4*)kvimg_own, B, m.max_len, g.hd,
+                                                     m.n_head, g.G, g.NCH, g.CK);
+    FFD_CHECK_LAUNCH("pack_kv_own_kernel");
+  }
   return attn_dispatch(m, g, (const uint8_t*)attn_img, (const uint8_t*)kvimg_own, w, ar, x, y, M, 1, s);
 }
 
