@@ -9,9 +9,12 @@ max_len, head_dim) (caching.py:251-396), a CRF store written when
 written by the kernels; the schedule and the counters are deterministic, so
 they stay on the host and the step loop never synchronises.
 
-FreqCa / event-intensity code of the reference is never reached from the
-sampler and is not mirrored; the corresponding constructor
-arguments are accepted and stored so that ``cache_kwargs`` keep working.
+FreqCa code of the reference is never reached from the sampler (SURVEY 2
+row 5) and is not mirrored; the corresponding constructor arguments are
+accepted and stored so that ``cache_kwargs`` keep working.  The event
+intensity (caching.py:524-559; not called by the reference's sampler either)
+is provided as a device kernel: ``compute_event_intensity`` mirrors the
+reference call, ``event_intensity_device`` keeps the value on the device.
 """
 
 from __future__ import annotations
@@ -136,6 +139,32 @@ class E2CRFCache:
             if crf is not None and self._crf_store is not None and crf.data_ptr() != self._crf_store.data_ptr():
                 self._crf_store.copy_(crf)
             self._crf_valid = True
+
+    # -- event intensity (SURVEY 8f row 3) ------------------------------------------
+    def event_intensity_device(self, crf: torch.Tensor) -> torch.Tensor:
+        """[avg_energy, intensity] of ``crf`` against the stored CRF as a 2-element DEVICE tensor (no host sync):
+        mean over (layer, token) of ||crf - crf_cache||_2, and min(1, that / tau_0)  (caching.py:541-557)."""
+        from . import _lib
+
+        prev = self.crf_cache
+        if prev is None:
+            raise _lib.FFDError("event_intensity_device needs a stored CRF")
+        dev = _lib.require_cuda()
+        crf = crf.to(device=dev, dtype=torch.float32).contiguous()
+        if crf.shape != prev.shape:
+            raise ValueError(f"crf shape {tuple(crf.shape)} != stored {tuple(prev.shape)}")
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        d = crf.shape[-1]
+        _lib.check(_lib.load().ffd_event_intensity(_lib.ptr(crf), _lib.ptr(prev.contiguous()), crf.numel() // d, d,
+                                                   float(self.tau_0), _lib.ptr(out), _lib.stream_handle()))
+        return out
+
+    def compute_event_intensity(self, crf: torch.Tensor, step: int) -> float:
+        """caching.py:524-559: 1.0 at step 0 / 0.1 later while no CRF is stored, else min(1, mean row energy of
+        the CRF change / tau_0).  Returns a host float like the reference (one sync)."""
+        if self.crf_cache is None:
+            return 0.1 if step > 0 else 1.0
+        return float(self.event_intensity_device(crf)[1].item())
 
     def get_cache_stats(self) -> dict:
         """caching.py:599-636."""

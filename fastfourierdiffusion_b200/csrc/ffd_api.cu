@@ -227,6 +227,13 @@ int ffd_fresca(const float* U, const float* V, const float* score, float* out, f
                        (cudaStream_t)stream);
 }
 
+int ffd_event_intensity(const float* crf, const float* prev_crf, int64_t rows, int d, float tau_0, float* out,
+                        ffd_stream_t stream) {
+  FFD_CHECK_ARG(crf && prev_crf && out && rows > 0 && d > 0, "bad ffd_event_intensity arguments");
+  FFD_CHECK_ARG(tau_0 > 0.f, "tau_0 must be positive");
+  return launch_event_intensity(crf, prev_crf, rows, d, tau_0, out, (cudaStream_t)stream);
+}
+
 int ffd_posemb_renorm(float* table, int L, int d, float max_norm, ffd_stream_t stream) {
   FFD_CHECK_ARG(table && L > 0 && d > 0, "bad ffd_posemb_renorm arguments");
   return launch_posemb_renorm(table, L, d, max_norm, (cudaStream_t)stream);

@@ -35,6 +35,9 @@ int launch_dft_apply(const float* T, const float* x, const float* scale, const f
 int launch_fresca(const float* U, const float* V, const float* score, float* out, float* scratch, int64_t B, int L,
                   int C, float low, float high, float cutoff_ratio, int strategy, cudaStream_t s);
 
+int launch_event_intensity(const float* crf, const float* prev, int64_t rows, int d, float tau_0, float* out,
+                           cudaStream_t s);
+
 // ffd_tc.cu (tcgen05 path)
 int64_t tc_packed_bytes(const ffd_dims& m);
 int tc_pack_weights(const ffd_dims& m, const float* weights, void* packed, cudaStream_t s);

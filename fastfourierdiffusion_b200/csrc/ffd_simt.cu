@@ -821,4 +821,41 @@ int launch_fresca(const float* U, const float* V, const float* score, float* out
   return launch_dft_apply(V, xt, gain, nullptr, out, B, L, C, s);
 }
 
+// ---- E2-CRF event intensity (caching.py:541-557) ---------------------------------------------------
+// One block; warp w owns rows w, w + 32, ...: energy[row] = || crf[row] - prev[row] ||_2, then the mean over rows in a
+// fixed order (deterministic), intensity = min(1, mean / tau_0).
+__global__ void event_intensity_kernel(const float* __restrict__ crf, const float* __restrict__ prev, int64_t rows, int d,
+                                       float tau_0, float* __restrict__ out) {
+  __shared__ float part[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int64_t r = warp; r < rows; r += 32) {
+    float ss = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      const float dl = fabsf(crf[r * d + c] - prev[r * d + c]);
+      ss = fmaf(dl, dl, ss);
+    }
+    ss = warp_sum(ss);
+    acc += sqrtf(ss);
+  }
+  if (lane == 0) part[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float v = part[lane];
+    v = warp_sum(v);
+    if (lane == 0) {
+      const float avg = v / (float)rows;
+      out[0] = avg;
+      out[1] = fminf(1.f, avg / tau_0);
+    }
+  }
+}
+
+int launch_event_intensity(const float* crf, const float* prev, int64_t rows, int d, float tau_0, float* out,
+                           cudaStream_t s) {
+  event_intensity_kernel<<<1, 1024, 0, s>>>(crf, prev, rows, d, tau_0, out);
+  FFD_CHECK_LAUNCH("event_intensity_kernel");
+  return FFD_OK;
+}
+
 }  // namespace ffd

@@ -104,6 +104,13 @@ int64_t ffd_fresca_scratch_floats(int64_t B, int L, int C);
 int ffd_fresca(const float* U, const float* V, const float* score, float* out, float* scratch, int64_t B, int L, int C,
                float low_scale, float high_scale, float cutoff_ratio, int strategy, ffd_stream_t stream);
 
+/* ---- E2-CRF event intensity (caching.py:524-559, E2CRFCache.compute_event_intensity) ------------------
+ * out[0] = mean over the `rows` = num_layers * max_len rows of || crf[row, :] - prev_crf[row, :] ||_2,
+ * out[1] = min(1, out[0] / tau_0).  out is DEVICE memory: the value can feed a device-side decision without a host
+ * sync (the reference calls .item()).  Deterministic (fixed reduction order). */
+int ffd_event_intensity(const float* crf, const float* prev_crf, int64_t rows, int d, float tau_0, float* out,
+                        ffd_stream_t stream);
+
 /* ---- embeddings (transformer.py) ---------------------------------------- */
 int ffd_posemb_renorm(float* table, int L, int d, float max_norm, ffd_stream_t stream);
 /* out[i, :] = dense_w @ [sin(2*pi*t_i*W), cos(...)][:d] + dense_b   for i < n */

@@ -629,3 +629,14 @@ def philox_normal(seed: int, stream: int, n: int) -> np.ndarray:
     out = np.stack([rad0 * np.cos(2 * np.pi * u[:, 1]), rad0 * np.sin(2 * np.pi * u[:, 1]),
                     rad1 * np.cos(2 * np.pi * u[:, 3]), rad1 * np.sin(2 * np.pi * u[:, 3])], axis=1)
     return out.reshape(-1)[:n].astype(np.float32)
+
+
+def event_intensity(crf, prev_crf, tau_0, step=1, dtype=np.float32):
+    """E2CRFCache.compute_event_intensity (caching.py:524-559): prev None -> 1.0 at step 0 else 0.1; otherwise
+    min(1, mean_{layer, token} ||crf - prev||_2 / tau_0)."""
+    if prev_crf is None:
+        return 0.1 if step > 0 else 1.0
+    delta = np.abs(np.asarray(crf, dtype) - np.asarray(prev_crf, dtype))   # :541
+    energy = np.sqrt((delta * delta).sum(-1, dtype=dtype))                # :544 torch.norm(dim=-1)
+    avg = float(energy.mean(dtype=dtype))                                 # :547
+    return min(1.0, avg / tau_0)                                          # :550

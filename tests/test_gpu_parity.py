@@ -510,3 +510,27 @@ def test_tiny_sampler_trace_with_fresca(prec):
     m.cache.reset()
     out = s.run_steps_unfused(X0, 0, noise=torch.from_numpy(g["step_z"]).cuda())
     assert rel(out.cpu().numpy(), g["final"]) < TOL[prec]["traj"]
+
+
+@pytest.mark.parametrize("tag", ["tiny", "ecg", "sat", "nasa"])
+def test_event_intensity_against_reference_vectors(tag):
+    """E2CRFCache.compute_event_intensity (caching.py:524-559) through ffd_event_intensity; the device variant
+    returns the value without a host sync."""
+    import fastfourierdiffusion_b200 as F
+
+    g = load_golden("event_intensity.npz")
+    prev, cur, tau = g[f"{tag}_prev"], g[f"{tag}_cur"], float(g[f"{tag}_tau"])
+    NL, L, d = prev.shape
+    c = F.E2CRFCache(num_layers=NL, max_len=L, device=torch.device("cuda"), tau_0=tau)
+    c.attach_stores(1, d, d)
+    assert c.compute_event_intensity(torch.from_numpy(cur).cuda(), 0) == 1.0
+    assert c.compute_event_intensity(torch.from_numpy(cur).cuda(), 5) == 0.1
+    c.current_step = 0
+    c.update_crf(torch.from_numpy(prev).cuda())
+    want = float(g[f"{tag}_val"])
+    got = c.compute_event_intensity(torch.from_numpy(cur).cuda(), 3)
+    assert abs(got - want) <= 2e-6 * max(1.0, abs(want))
+    dev = c.event_intensity_device(torch.from_numpy(cur).cuda())
+    assert dev.is_cuda and dev.shape == (2,)
+    assert abs(float(dev[1]) - want) <= 2e-6 * max(1.0, abs(want))
+    assert abs(float(dev[0]) - O.event_intensity(cur, prev, 1e30) * 1e30) <= 1e-5 * float(dev[0])

@@ -165,3 +165,13 @@ def test_fresca_oracle_matches_reference(L, strat):
     for tag, kw in FRESCA_KW.items():
         got = O.apply_fresca_to_score(g[f"x_{L}"], cutoff_strategy=strat, **kw)
         assert rel(got, g[f"y_{L}_{strat}_{tag}"]) < 2e-6, (L, strat, tag)
+
+
+@pytest.mark.parametrize("tag", ["tiny", "ecg", "sat", "nasa"])
+def test_event_intensity_oracle_matches_reference(tag):
+    """compute_event_intensity (caching.py:524-559): the restatement against values produced by the reference."""
+    g = load_golden("event_intensity.npz")
+    assert O.event_intensity(None, None, 0.1, step=0) == float(g[f"{tag}_none0"]) == 1.0
+    assert O.event_intensity(None, None, 0.1, step=5) == float(g[f"{tag}_none5"]) == 0.1
+    got = O.event_intensity(g[f"{tag}_cur"], g[f"{tag}_prev"], float(g[f"{tag}_tau"]), step=3)
+    assert abs(got - float(g[f"{tag}_val"])) <= 2e-6 * max(1.0, abs(float(g[f"{tag}_val"])))
