@@ -2,9 +2,8 @@
 //   y = LN2(x + W2 relu(W1 x + b1) + b2)          cached_transformer.py:130-132,325-327
 // which carries 86 % of the sampling path's FLOPs.
 //
-// One persistent CTA per SM walks over pairs of 128-token tiles (A, B).  The fp32 token tiles move between
-// HBM and shared memory as single bulk async copies (a tile of 128 rows is contiguous), so no thread touches
-// global memory.  Per 128-wide slice j of the F hidden units:
+// One persistent CTA per SM walks over pairs of 128-token tiles (A, B).  Per 128-wide slice j of the F hidden
+// units:
 //   GEMM1  H_s = X_s[128 x DP] . W1_j^T          tcgen05.mma kind::f16, A operand (bf16 X_s) read from TMEM,
 //                                                 B operand from shared memory, fp32 accumulate in TMEM
 //   epilogue warps: tcgen05.ld H_s -> relu -> bf16 -> tcgen05.st, in place over H_s
@@ -14,15 +13,19 @@
 // b1 rides in two spare K columns of W1 (hi + lo bf16 parts against constant-1 columns of X), so the slice
 // epilogue is relu + convert only.
 //
-// v5: the slice loop (measured 1350 cycles per slice for both tiles, against 1280 of tensor-pipe time) never
-// stops at a pair boundary.  Four "tile warps" stage the NEXT pair's activations into TMEM as soon as this
-// pair's last GEMM1 has read X_s, and turn Y_s + b2 + residual into the LayerNorm output (in place in the fp32
-// tile buffer, one bulk copy stores it) while the next pair's slices already run; the 16 epilogue warps do
-// nothing but slices.
+// v6: the slice loop (measured 1350 cycles per slice for both tiles, against 1280 of tensor-pipe time) never
+// stops at a pair boundary, and shared memory belongs to the tensor core.  "Tile warps" (one group of four per
+// tile) read the NEXT pair's token rows straight from global memory into the bf16 TMEM operand as soon as this
+// pair's last GEMM1 has read X_s, and turn Y_s + b2 + residual into the LayerNorm output
+// while the next pair's slices already run: the fp32 rows wait in shared memory as the residual, are replaced by
+// the pre-LN values in one sweep (so that Y_s is released early) and leave as coalesced 16-byte global stores.  The tensor core streams its B
+// operands from shared memory at 64 B/clk, half the SM's shared-memory bandwidth: staging the fp32 tiles through
+// shared memory with bulk copies, as v5 did, cost 14 % (tile copies) + 6 % (LayerNorm passes) of the kernel
+// (same-box ablations, tools/ab.sh).  The 16 epilogue warps do nothing but slices.
 //
 // Warp roles (28 warps): 0 = weight-slice producer, 1 / 2 = MMA issuers of tile 0 / tile 1 (two independent issue
-// streams), 3 = token tiles in / finished tiles out, 4..7 / 8..11 = tile warps of tile 0 / 1, 12..27 = four
-// epilogue groups of four warps: group g serves tile g & 1 and the (g >> 1)-th half of every 128-column slice.
+// streams), 3 = idle, 4..7 / 8..11 = tile warps of tile 0 / 1, 12..27 = four epilogue groups of four warps: group g
+// serves tile g & 1 and the (g >> 1)-th half of every 128-column slice.
 #include "ffd_tc_ptx.cuh"
 
 namespace ffd {
@@ -30,12 +33,12 @@ namespace ffd {
 namespace tc {
 
 constexpr int CHUNK = 128;    // hidden units per slice (UMMA N of GEMM1, K extent of GEMM2)
-constexpr int STAGES = 2;     // weight ring depth (shared memory holds two tile pairs + the rings)
+constexpr int STAGES = 2;     // weight ring depth (shared memory: two pairs of fp32 row buffers + the rings)
 constexpr int NUM_THREADS = 896;
 
 // ---- shared-memory plan ------------------------------------------------------------------------
 struct FfnSmem {
-  int x32, w1, w2, consts, bars, tmem, total;
+  int vbuf, w1, w2, consts, bars, tmem, total;
   int tile_bytes, tile_stride, w1_bytes, w2_bytes;
 };
 
@@ -51,7 +54,7 @@ __host__ __device__ inline FfnSmem ffn_smem(int DP, int d) {
   s.tile_stride = (s.tile_bytes + 127) / 128 * 128;
   s.w1_bytes = CHUNK * DP * 2;    // bf16 [128 n x DP k]
   s.w2_bytes = DP * CHUNK * 2;    // bf16 [DP n x 128 k]
-  s.x32 = take(4 * s.tile_stride);  // two tile pairs: one in flight, one being stored / prefetched
+  s.vbuf = take(4 * s.tile_stride);   // fp32 rows (residual, then pre-LayerNorm values) of tile s of pair parity p: 2 p + s
   s.w1 = take(STAGES * s.w1_bytes);
   s.w2 = take(STAGES * s.w2_bytes);
   s.consts = take(3 * DP * 4);    // b2, ln weight, ln bias
@@ -64,7 +67,7 @@ __host__ __device__ inline FfnSmem ffn_smem(int DP, int d) {
 // ---- the kernel ------------------------------------------------------------------------------------
 template <int DP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t* __restrict__ w1img,
+ffn_ln_tc_kernel(const float* x, float* y /* may alias x */, const uint8_t* __restrict__ w1img,
                  const uint8_t* __restrict__ w2img, const float* __restrict__ b2, const float* __restrict__ lnw,
                  const float* __restrict__ lnb, int64_t M, int d, int n_chunks, int64_t n_pairs, float eps,
                  long long* __restrict__ dbg) {
@@ -81,7 +84,7 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
   uint64_t* w2_full = bars + 2 * STAGES;    // [STAGES] tx
   uint64_t* w2_empty = bars + 3 * STAGES;   // [STAGES] 2 commits
   uint64_t* t_full = bars + 4 * STAGES;     // [4] tx: fp32 tile landed in buffer (pair parity, tile)
-  uint64_t* y_ready = t_full + 4;           // [4] 128 arrivals: LayerNorm output sits in the tile buffer
+  uint64_t* y_ready = t_full + 4;           // [4] 128 arrivals: the tile has left the buffer (LayerNorm output stored)
   uint64_t* x_full = y_ready + 4;           // [2] 128 arrivals: bf16 X_s written to TMEM
   uint64_t* x_free = x_full + 2;            // [2] commit: the pair's last GEMM1 has read X_s
   uint64_t* h_full = x_free + 2;            // [2] commit
@@ -160,45 +163,24 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
         }
       }
     } else if (warp == 3) {
-      // ================= token-tile load / store =================
+      // ================= token tiles in (one bulk copy per tile; a tile of 128 rows is contiguous) =================
       if (lane == 0) {
-        auto pair_of = [&](uint32_t np) { return (int64_t)blockIdx.x + (int64_t)np * gridDim.x; };
-        auto rows_of = [&](int64_t pair, int s) -> int64_t {
-          const int64_t row0 = (pair * 2 + s) * TILE_M;
-          return M - row0 < TILE_M ? (M - row0 > 0 ? M - row0 : 0) : TILE_M;
-        };
         auto load_pair = [&](uint32_t np) {
-          const int64_t pair = pair_of(np);
+          const int64_t pair = (int64_t)blockIdx.x + (int64_t)np * gridDim.x;
           for (int s = 0; s < 2; ++s) {
             const int buf = (np & 1) * 2 + s;
-            const int64_t rows = rows_of(pair, s);
+            const int64_t row0 = (pair * 2 + s) * TILE_M;
+            const int64_t rows = M - row0 < TILE_M ? (M - row0 > 0 ? M - row0 : 0) : TILE_M;
+            if (np >= 2) mbar_wait_relaxed(&y_ready[buf], ((np - 2) >> 1) & 1, 100);  // its previous tile has left
             if (rows > 0) {
               mbar_expect_tx(&t_full[buf], (uint32_t)(rows * d * 4));
-              bulk_load(smem + sm.x32 + buf * sm.tile_stride, x + (pair * 2 + s) * TILE_M * d,
-                        (uint32_t)(rows * d * 4), &t_full[buf]);
+              bulk_load(smem + sm.vbuf + buf * sm.tile_stride, x + row0 * d, (uint32_t)(rows * d * 4), &t_full[buf]);
             } else {
               mbar_arrive(&t_full[buf]);
             }
           }
         };
-        load_pair(0);
-        if (my_pairs > 1) load_pair(1);
-        for (uint32_t np = 0; np < my_pairs; ++np) {
-          const int64_t pair = pair_of(np);
-          for (int s = 0; s < 2; ++s) {
-            const int buf = (np & 1) * 2 + s;
-            const int64_t rows = rows_of(pair, s);
-            mbar_wait_relaxed(&y_ready[buf], (np >> 1) & 1, 100);
-            if (rows > 0) {
-              bulk_store(y + (pair * 2 + s) * TILE_M * d, smem + sm.x32 + buf * sm.tile_stride,
-                         (uint32_t)(rows * d * 4));
-              bulk_commit();
-            }
-          }
-          bulk_wait_read();
-          if (np + 2 < my_pairs) load_pair(np + 2);  // the pair's buffers are free again
-        }
-        bulk_wait_all();
+        for (uint32_t np = 0; np < my_pairs; ++np) load_pair(np);
       }
     } else if (warp == 1 || warp == 2) {
       // ================= MMA issuers: warp 1 drives tile 0 of every pair, warp 2 tile 1 (whole warp converged,
@@ -278,13 +260,15 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;      // row inside the 128-token tile
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    // bf16 X_s -> TMEM (A operand of GEMM1) from the fp32 tile buffer; columns d, d+1 are the constant-1 bias
-    // columns
+    const int n4 = d / 4;                              // float4 per row
+    // bf16 X_s -> TMEM (A operand of GEMM1), rows read straight from global memory; columns d, d+1 are the
+    // constant-1 bias columns
     auto stage_x = [&](uint32_t np) {
       const int64_t pair = (int64_t)blockIdx.x + (int64_t)np * gridDim.x;
+      const int64_t grow = (pair * 2 + s) * TILE_M + row;
+      const bool valid = grow < M;
       const int buf = (np & 1) * 2 + s;
-      const float4* src = reinterpret_cast<const float4*>(smem + sm.x32 + buf * sm.tile_stride) + (size_t)row * (d / 4);
-      const bool valid = (pair * 2 + s) * TILE_M + row < M;
+      const float4* src = reinterpret_cast<const float4*>(smem + sm.vbuf + buf * sm.tile_stride) + (size_t)row * n4;
       mbar_wait_relaxed(&t_full[buf], (np >> 1) & 1, 100);
       // convert first (registers), so that only the TMEM stores remain once X_s is free
       uint32_t xp[XC];
@@ -310,15 +294,19 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
       tc_fence_before();
       mbar_arrive(&x_full[s]);
     };
-    // Y_s + b2 + residual -> LayerNorm, in place in the fp32 tile buffer (one thread owns a row).  Y_s is released
-    // after one sweep, so the next pair's first GEMM2 is not held up.
+    // Y_s + b2 + residual -> LayerNorm -> global.  Sweep 1 (one thread owns a row): pre-LN values into the
+    // shared-memory buffer, row statistics; Y_s is released.  Sweep 2: the tile leaves as consecutive 16-byte
+    // chunks (thread t takes chunks t, t + 128, ...: coalesced stores).
     auto finish = [&](uint32_t np) {
-      const int buf = (np & 1) * 2 + s;
-      float4* myrow = reinterpret_cast<float4*>(smem + sm.x32 + buf * sm.tile_stride) + (size_t)row * (d / 4);
+      float4* vb = reinterpret_cast<float4*>(smem + sm.vbuf + ((np & 1) * 2 + s) * sm.tile_stride);
+      const int64_t pair = (int64_t)blockIdx.x + (int64_t)np * gridDim.x;
+      const int64_t row0 = (pair * 2 + s) * TILE_M;
+      const int rows = (int)(M - row0 < TILE_M ? (M - row0 > 0 ? M - row0 : 0) : TILE_M);
+      float4* myrow = vb + (size_t)row * n4;
       mbar_wait_relaxed(&y_full[s], np & 1, 40);
       tc_fence_after();
       float s1 = 0.f, s2 = 0.f;
-      // 16 accumulator columns + b2 + residual -> the tile buffer, row statistics
+      // 16 accumulator columns + b2 + residual -> the buffer, row statistics
       auto unit = [&](const uint32_t (&r)[16], const float4 (&res)[4], int c0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -335,6 +323,13 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
           }
         }
       };
+      auto residual = [&](float4 (&e)[4], int c0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = c0 + 4 * i;
+          e[i] = c < d ? myrow[c >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
       // two 16-column units per TMEM round trip; the residual loads are issued before the round trip completes
 #pragma unroll
       for (int c0 = 0; c0 < DP; c0 += 32) {
@@ -344,11 +339,7 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
         const bool two = kTwoAlways || c0 + 16 < DP;
         FFD_TMEM_LD16(tmem_base + lane_base + COL_Y + s * 128 + c0, ra);
         if (two) FFD_TMEM_LD16(tmem_base + lane_base + COL_Y + s * 128 + c0 + 16, rb);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = c0 + 4 * i;
-          e[i] = c < d ? myrow[c >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        residual(e, c0);
         tmem_ld_wait();
         if (c0 + 32 >= DP) {
           tc_fence_before();
@@ -356,28 +347,42 @@ ffn_ln_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8
         }
         unit(ra, e, c0);
         if (two) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c = c0 + 16 + 4 * i;
-            e[i] = c < d ? myrow[c >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          residual(e, c0 + 16);
           unit(rb, e, c0 + 16);
         }
       }
       const float mean = s1 / (float)d;
       const float rstd = rsqrtf(fmaxf(s2 / (float)d - mean * mean, 0.f) + eps);
-#pragma unroll 6
-      for (int c = 0; c < d; c += 4) {
-        const float4 v = myrow[c >> 2];
-        float4 o;
-        o.x = (v.x - mean) * rstd * consts[DP + c] + consts[2 * DP + c];
-        o.y = (v.y - mean) * rstd * consts[DP + c + 1] + consts[2 * DP + c + 1];
-        o.z = (v.z - mean) * rstd * consts[DP + c + 2] + consts[2 * DP + c + 2];
-        o.w = (v.w - mean) * rstd * consts[DP + c + 3] + consts[2 * DP + c + 3];
-        myrow[c >> 2] = o;
+      __syncwarp();  // this warp's 32 rows are in the buffer
+      {
+        // sweep 2: the warp's 32 rows are one contiguous block of the tile; lane l takes its 16-byte chunks l,
+        // l + 32, ... (coalesced global stores); the row statistics come from the lane that owns the row
+        const int wrow0 = quad * 32;
+        const float4* wv = vb + (size_t)wrow0 * n4;
+        float4* dst = reinterpret_cast<float4*>(y + (row0 + wrow0) * d);
+        const int wrows = rows - wrow0 < 32 ? rows - wrow0 : 32;  // may be <= 0 in the ragged last tile
+        const int step_r = 32 / n4, step_c = 32 % n4;
+        int r = lane / n4, c4 = lane % n4;
+        for (int q = lane; q < 32 * n4; q += 32) {
+          const float m_r = __shfl_sync(0xffffffffu, mean, r & 31);
+          const float s_r = __shfl_sync(0xffffffffu, rstd, r & 31);
+          if (r < wrows) {
+            const float4 v = wv[q];
+            const float4 w4 = *reinterpret_cast<const float4*>(consts + DP + 4 * c4);
+            const float4 b4 = *reinterpret_cast<const float4*>(consts + 2 * DP + 4 * c4);
+            float4 o;
+            o.x = (v.x - m_r) * s_r * w4.x + b4.x;
+            o.y = (v.y - m_r) * s_r * w4.y + b4.y;
+            o.z = (v.z - m_r) * s_r * w4.z + b4.z;
+            o.w = (v.w - m_r) * s_r * w4.w + b4.w;
+            dst[q] = o;
+          }
+          r += step_r, c4 += step_c;
+          if (c4 >= n4) c4 -= n4, ++r;
+        }
       }
-      fence_proxy_async();
-      mbar_arrive(&y_ready[buf]);
+      fence_proxy_async();  // the next bulk copy into this buffer is ordered after these reads
+      mbar_arrive(&y_ready[(np & 1) * 2 + s]);
     };
     stage_x(0);
     for (uint32_t np = 0; np < my_pairs; ++np) {
