@@ -45,12 +45,14 @@ constexpr int V_STAGES = 2;    // V image ring
 constexpr int HP = 16;         // slots per Q tile (UMMA K of the score MMA, N of the PV MMA)
 constexpr int SCR_COLS = 64;   // TMEM scratch columns (Q projection / out-proj passes)
 // Share of the softmax exponentials evaluated on the FMA pipe instead of MUFU: bit mask over the 8 fp16 pairs of
-// a 16-column chunk (tools/polytest.sh sweeps it).
-#ifndef FFD_STAGGER_NS
-#define FFD_STAGGER_NS 250
-#endif
+// a 16-column chunk.  Same-box sweep (tools/ab.sh, ECG shapes): 0x00 2.031 ms, 0x01 (1/8) 1.980, 0x81 / 0x03 (2/8)
+// 2.013, 0x11 2.021, 0x49 (3/8) 2.075, 0x55 (4/8) 2.176 -- the loop is bound by issue slots as much as by MUFU, so
+// only a small share pays.
 #ifndef FFD_POLY_PAIRS
-#define FFD_POLY_PAIRS 0x00u
+#define FFD_POLY_PAIRS 0x01u
+#endif
+#ifndef FFD_STAGGER_NS
+#define FFD_STAGGER_NS 250   // start-up offset between the four softmax warps of a sub-partition
 #endif
 constexpr uint32_t POLY_PAIRS = FFD_POLY_PAIRS;
 
