@@ -656,10 +656,10 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
       pk_[e >> 1] = ((POLY_PAIRS >> (e >> 1)) & 1)                                                   \
                         ? ex2_pack_f16_shift_poly(__uint_as_float(r[16 * (G_) + e]), __uint_as_float(r[16 * (G_) + e + 1]), (mc_)) \
                         : ex2_pack_f16_shift(__uint_as_float(r[16 * (G_) + e]), __uint_as_float(r[16 * (G_) + e + 1]), (mc_))
-#define FFD_SOFTMAX_HEAD(LAST, SPARE, n_)                                                          \
+#define FFD_SOFTMAX_HEAD(LAST, SPARE, n_, B_)                                                      \
   {                                                                                               \
     const uint32_t n = (n_);                                                                      \
-    const uint32_t b = n & 1;                                                                     \
+    constexpr uint32_t b = (B_); /* = n & 1: the loop is unrolled by two, so buffers and parities are constants */ \
     const uint32_t pcol = pcol0 + b * (COL_P1 - COL_P0);                                          \
     const bool has_next = n + 1 < n_heads;                                                        \
     const float mc = -mb;                                                                         \
@@ -676,7 +676,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     }                                                                                             \
     if (has_next) {                                                                               \
       FFD_STAMP(warp == 12 && n - 2u * NV < (uint32_t)NV, 128 + (n - 2u * NV) * 4 + 1);                               \
-      mbar_wait_relaxed(s_full, (n + 1) & 1, 32);                                                 \
+      mbar_wait_relaxed(s_full, b ^ 1, 32); /* parity (n + 1) & 1 */                              \
       tc_fence_after();                                                                           \
       FFD_STAMP(warp == 12 && n - 2u * NV < (uint32_t)NV, 128 + (n - 2u * NV) * 4 + 2);                               \
       _Pragma("unroll") for (int j = 0; j < KQ - 1; ++j) FFD_TMEM_LD16(scol + 16 * j, (r + 16 * j)); \
@@ -711,8 +711,8 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     FFD_STAMP(warp == 12 && n - 2u * NV < (uint32_t)NV, 128 + (n - 2u * NV) * 4 + 3);                                 \
   }
     for (uint32_t n2 = 0; n2 < n_heads; n2 += 2) {
-      FFD_SOFTMAX_HEAD(KQ - 1, KQ, n2);
-      if (n2 + 1 < n_heads) FFD_SOFTMAX_HEAD(KQ, KQ - 1, n2 + 1);
+      FFD_SOFTMAX_HEAD(KQ - 1, KQ, n2, 0);
+      if (n2 + 1 < n_heads) FFD_SOFTMAX_HEAD(KQ, KQ - 1, n2 + 1, 1);
     }
 #undef FFD_SOFTMAX_HEAD
 #undef FFD_EXP16
