@@ -421,6 +421,23 @@ def test_entry_points_run(tmp_path):
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert (out / "benchmark_results.csv").exists()
+    # cmd/ablation_cache.py on the time-domain model (BASELINE.json config 5: no DFT, G = 1)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "cmd", "ablation_cache.py"), "num_samples=4",
+                        "num_diffusion_steps=6", "fourier_transform=false", "sampler.sample_batch_size=2",
+                        "score_model.num_layers=1", f"output_dir={out}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+
+    res = json.load(open(out / "ablation_results.json"))
+    assert list(res) == ["Baseline", "E2-CRF (full)", "No event trigger", "No error feedback", "No energy weighting",
+                         "Naive caching"]
+    assert all(v["finite"] for v in res.values())
+    # first cache of the model (K=5, R=10: refresh every 500 steps): step 0 recomputes, the 11 later global steps
+    # (two sampler batches share the cache) are cache hits for all L tokens of the layer.  Later configurations
+    # report zero counters, like the reference: the cached layers keep the FIRST cache object.
+    st = res["E2-CRF (full)"]["cache_stats"]
+    assert st["recompute_count"] == 187 and st["cache_hit_count"] == 187 * (2 * 6 - 1)
+    assert res["No error feedback"]["cache_stats"]["recompute_count"] == 0
 
 
 @pytest.mark.parametrize("prec", PRECS)
