@@ -808,7 +808,7 @@ __global__ void pack_kvproj_kernel(const float* __restrict__ in_w, const float* 
 // its tile mates' are zeroed), the V units after an 8 x 8 transpose through shared memory (a V unit holds 8
 // consecutive keys of one dim).
 template <int DP>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, 4)
 kv_own_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wkimg, uint8_t* __restrict__ img, int d,
                  int H, int hd, int G, int QN, int L, int NCH, int CK, int tps) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -836,10 +836,47 @@ kv_own_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wkimg,
     mbar_expect_tx(w_full, wk_bytes + wv_bytes);
     bulk_load(wk, wkimg, wk_bytes + wv_bytes, w_full);
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp == 0) tmem_alloc(tmem_slot, 128);  // K slots, then V dims: four CTAs per SM
   // stage this tile's rows as the bf16 A operand; rows beyond the sample are all zero (their constant columns too,
   // so that their V row-sum slot stays 0)
-  {
+  if ((d & 7) == 0) {
+    // A warp's 32 rows are one contiguous block of global memory: lane l reads its 16-byte chunks l, l + 32, ...
+    // (coalesced); two neighbouring chunks of a row make one 16-byte bf16 unit of the operand (even lanes pack).
+    const int n4 = d >> 2;
+    const int wrows = rows - warp * 32 < 32 ? rows - warp * 32 : 32;  // valid rows of this warp (may be <= 0)
+    const float4* src = reinterpret_cast<const float4*>(x + (sample * L + (int64_t)part * TILE_M + warp * 32) * d);
+    const int step_r = 32 / n4, step_c = 32 % n4;
+    int r = lane / n4, c4 = lane % n4;
+#pragma unroll 6
+    for (int q = lane; q < 32 * n4; q += 32) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < wrows) a = src[q];
+      float4 b4;
+      b4.x = __shfl_down_sync(0xffffffffu, a.x, 1);
+      b4.y = __shfl_down_sync(0xffffffffu, a.y, 1);
+      b4.z = __shfl_down_sync(0xffffffffu, a.z, 1);
+      b4.w = __shfl_down_sync(0xffffffffu, a.w, 1);
+      if ((lane & 1) == 0) {
+        const int trow = warp * 32 + r;
+        uint4 pk;
+        pk.x = pack_bf16(a.x, a.y);
+        pk.y = pack_bf16(a.z, a.w);
+        pk.z = pack_bf16(b4.x, b4.y);
+        pk.w = pack_bf16(b4.z, b4.w);
+        *reinterpret_cast<uint4*>(xo + (uint32_t)(trow >> 3) * 128 + (uint32_t)(trow & 7) * 16 +
+                                  (c4 >> 1) * (TILE_M * 16)) = pk;
+      }
+      r += step_r, c4 += step_c;
+      if (c4 >= n4) c4 -= n4, ++r;
+    }
+    // constant columns (d, d + 1 = 1 for valid rows) and the zero padding up to DP
+    const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
+    for (int kg = d >> 3; kg < DP / 8; ++kg) {
+      uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+      if (kg == (d >> 3) && valid) pk.x = pack_bf16(1.f, 1.f);
+      *reinterpret_cast<uint4*>(xo + row_off + kg * (TILE_M * 16)) = pk;
+    }
+  } else {
     const float4* src = reinterpret_cast<const float4*>(x + (sample * L + (int64_t)part * TILE_M + row) * d);
     const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
     constexpr int NG = DP / 8;
@@ -873,10 +910,6 @@ kv_own_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wkimg,
     umma_ss_chain<DP / 16>(tmem_base, make_desc(smem_u32(xo), LBO128, 128), (2 * LBO128) >> 4,
                            make_desc(smem_u32(wk), NK * 16, 128), (2 * NK * 16) >> 4, make_idesc(TILE_M, NK), 0);
     umma_commit(k_done);
-    umma_ss_chain<DP / 16>(tmem_base + 128, make_desc(smem_u32(xo), LBO128, 128), (2 * LBO128) >> 4,
-                           make_desc(smem_u32(wk + wk_bytes), NVR * 16, 128), (2 * NVR * 16) >> 4,
-                           make_idesc(TILE_M, NVR), 0);
-    umma_commit(v_done);
   }
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
   const size_t k_bytes = (size_t)CK * HP * 2, img_stride = 2 * k_bytes;
@@ -931,6 +964,15 @@ kv_own_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wkimg,
     }
   }
   // ---- V images: 8 x 8 transpose of (key, dim) through shared memory, per group of 8 keys ----
+  tc_fence_before();
+  __syncthreads();  // every thread has read its K accumulators: the columns are reused for V
+  if (warp == 0) {
+    tc_fence_after();
+    umma_ss_chain<DP / 16>(tmem_base, make_desc(smem_u32(xo), LBO128, 128), (2 * LBO128) >> 4,
+                           make_desc(smem_u32(wk + wk_bytes), NVR * 16, 128), (2 * NVR * 16) >> 4,
+                           make_idesc(TILE_M, NVR), 0);
+    umma_commit(v_done);
+  }
   mbar_wait(v_done, 0);
   tc_fence_after();
   uint4* my_stage = reinterpret_cast<uint4*>(stage + warp * 512);
@@ -938,7 +980,7 @@ kv_own_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wkimg,
   for (int h0 = 0; h0 < H; h0 += 2) {
     // two heads per TMEM load: columns 8 h0 .. 8 h0 + 15
     uint32_t r[16];
-    FFD_TMEM_LD16(tmem_base + lane_base + 128 + 8 * h0, r);
+    FFD_TMEM_LD16(tmem_base + lane_base + 8 * h0, r);
     tmem_ld_wait();
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
@@ -970,7 +1012,7 @@ kv_own_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wkimg,
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
 // Images per (layer, head h, key chunk c), keys [c CK, (c+1) CK):
