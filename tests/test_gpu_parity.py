@@ -450,7 +450,9 @@ def test_entry_points_run(tmp_path):
                                    # head_dim 12: one head per Q tile, row sum in slot 15, K/V images of the stock
                                    # branch from the fp32 projection + pack kernel; odd head count
                                    dict(max_len=50, n_channels=2, d_model=48, num_layers=2, n_head=4),
-                                   dict(max_len=70, n_channels=1, d_model=36, num_layers=2, n_head=3)])
+                                   dict(max_len=70, n_channels=1, d_model=36, num_layers=2, n_head=3),
+                                   # three key chunks of 192: the padded keys 512..575 lie beyond the four row tiles
+                                   dict(max_len=385, n_channels=2, d_model=24, num_layers=1, n_head=4)])
 def test_other_shapes_against_oracle(prec, shape):
     """Other geometries of the tensor-core attention kernel -- several key chunks per head (L > 192: 2 x 128 or
     2 x 192 keys), three heads per Q tile (d=60, hd=5), one 64-key chunk, multi-channel -- every branch against the
