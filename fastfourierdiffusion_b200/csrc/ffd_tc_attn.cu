@@ -28,10 +28,14 @@
 //    softmax warp holds its share in registers; P goes to its own double buffer.  The score MMA of head n+2 and
 //    the P.V MMA of head n are issued by two different warps, so neither waits behind the other's barrier.
 //
-// Warp roles (28 warps): 0 = K/V image + weight producer, 1 = TMEM allocator, score MMAs and the scratch passes
-// (Q projection / out-projection), 2 = token-tile load/store, 3 = P.V MMAs, 4..7 = O read-out (combine
-// quarters/chunks, normalise, write the out-proj operand), 8..11 = tile warps, 12..27 = four softmax groups of
-// four warps.
+// Warp roles (28 warps, register budgets per warpgroup via setmaxnreg): 0 = K/V image + weight producer,
+// 1 = TMEM allocator + score MMAs, 2 = token-tile load/store, 3 = P.V MMAs, 4..7 = O read-out (combine
+// quarters/chunks, normalise, write the out-proj operand), 8..11 = tile warps (warp 8 also issues their scratch
+// MMAs: Q projection / out-projection), 12..27 = four softmax groups of four warps (88 registers: they hold two
+// heads' scores).  One eighth of the exponentials runs on the FMA pipe (FFD_POLY_PAIRS).
+//
+// Lown > 0 runs STOCK attention with the same code: tiles are aligned to samples and every sample brings its own
+// K/V images (kv_own_tc_kernel below builds them with the K/V projection fused in).
 #include <cuda_fp16.h>
 
 #include "ffd_tc_ptx.cuh"
