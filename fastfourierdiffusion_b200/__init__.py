@@ -9,9 +9,10 @@ from .batch import DiffusableBatch
 from .caching import E2CRFCache
 from .fourier import dft, idft
 from .fresca import apply_fresca_to_score, frequency_scale
+from .metrics import MarginalWasserstein, SlicedWasserstein, WassersteinDistances
 from .sampler import DiffusionSampler
 from .score_model import ScoreModule
 from .sde import SDE, SamplingOutput, VEScheduler, VPScheduler
 
 __all__ = ["DiffusableBatch", "E2CRFCache", "dft", "idft", "apply_fresca_to_score", "frequency_scale", "DiffusionSampler", "ScoreModule", "SDE",
-           "SamplingOutput", "VEScheduler", "VPScheduler"]
+           "SamplingOutput", "VEScheduler", "VPScheduler", "SlicedWasserstein", "MarginalWasserstein", "WassersteinDistances"]

@@ -234,6 +234,32 @@ int ffd_event_intensity(const float* crf, const float* prev_crf, int64_t rows, i
   return launch_event_intensity(crf, prev_crf, rows, d, tau_0, out, (cudaStream_t)stream);
 }
 
+int ffd_metric_project(const float* data, int64_t N, int D, const float* dirs, int R, float* out,
+                       ffd_stream_t stream) {
+  FFD_CHECK_ARG(data && dirs && out && N > 0 && D > 0 && R > 0, "bad ffd_metric_project arguments");
+  return launch_metric_project(data, N, D, dirs, R, out, (cudaStream_t)stream);
+}
+
+int ffd_metric_sort_rows(float* x, int R, int64_t N, ffd_stream_t stream) {
+  FFD_CHECK_ARG(x && R > 0 && N > 0, "bad ffd_metric_sort_rows arguments");
+  if (N > 32768) {
+    set_error("ffd_metric_sort_rows: rows of more than 32768 values are not supported (got %lld)", (long long)N);
+    return FFD_ERR_UNSUPPORTED;
+  }
+  return launch_metric_sort_rows(x, R, N, (cudaStream_t)stream);
+}
+
+int ffd_metric_w2_sorted(const float* a, int64_t N, const float* b, int64_t M, int R, float* out,
+                         ffd_stream_t stream) {
+  FFD_CHECK_ARG(a && b && out && N > 0 && M > 0 && R > 0, "bad ffd_metric_w2_sorted arguments");
+  return launch_metric_w2_sorted(a, N, b, M, R, out, (cudaStream_t)stream);
+}
+
+int ffd_metric_row_std(const float* x, int R, int64_t N, float* out, ffd_stream_t stream) {
+  FFD_CHECK_ARG(x && out && N > 0 && R > 0, "bad ffd_metric_row_std arguments");
+  return launch_metric_row_std(x, R, N, out, (cudaStream_t)stream);
+}
+
 int ffd_posemb_renorm(float* table, int L, int d, float max_norm, ffd_stream_t stream) {
   FFD_CHECK_ARG(table && L > 0 && d > 0, "bad ffd_posemb_renorm arguments");
   return launch_posemb_renorm(table, L, d, max_norm, (cudaStream_t)stream);

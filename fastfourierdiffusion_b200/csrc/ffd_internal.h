@@ -38,6 +38,12 @@ int launch_fresca(const float* U, const float* V, const float* score, float* out
 int launch_event_intensity(const float* crf, const float* prev, int64_t rows, int d, float tau_0, float* out,
                            cudaStream_t s);
 
+// ffd_metrics.cu
+int launch_metric_project(const float* data, int64_t N, int D, const float* dirs, int R, float* out, cudaStream_t s);
+int launch_metric_sort_rows(float* x, int R, int64_t N, cudaStream_t s);
+int launch_metric_w2_sorted(const float* a, int64_t N, const float* b, int64_t M, int R, float* out, cudaStream_t s);
+int launch_metric_row_std(const float* x, int R, int64_t N, float* out, cudaStream_t s);
+
 // ffd_tc.cu (tcgen05 path)
 int64_t tc_packed_bytes(const ffd_dims& m);
 int tc_pack_weights(const ffd_dims& m, const float* weights, void* packed, cudaStream_t s);

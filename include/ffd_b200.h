@@ -111,6 +111,18 @@ int ffd_fresca(const float* U, const float* V, const float* score, float* out, f
 int ffd_event_intensity(const float* crf, const float* prev_crf, int64_t rows, int d, float tau_0, float* out,
                         ffd_stream_t stream);
 
+/* ---- sample-quality metrics (sampling/metrics.py:101-216 over utils/wasserstein.py:96-199) ---------------
+ * Sliced / marginal Wasserstein-2 distances without leaving the device.  The reference projects with numpy and calls
+ * POT's ot.emd2_1d (uniform weights, squared-Euclidean cost) per direction on the host.
+ *   ffd_metric_project:   out[r, n] = <data[n, :], dirs[r, :]>            (wasserstein.py:146-149, all directions)
+ *   ffd_metric_sort_rows: every row of x[R, N] ascending, in place         (N <= 32768)
+ *   ffd_metric_w2_sorted: out[r] = sqrt(emd2_1d(a[r, :N], b[r, :M])) for ascending rows (wasserstein.py:117-143)
+ *   ffd_metric_row_std:   out[r] = np.std(x[r, :])                         (wasserstein.py:157-159 "standardise") */
+int ffd_metric_project(const float* data, int64_t N, int D, const float* dirs, int R, float* out, ffd_stream_t stream);
+int ffd_metric_sort_rows(float* x, int R, int64_t N, ffd_stream_t stream);
+int ffd_metric_w2_sorted(const float* a, int64_t N, const float* b, int64_t M, int R, float* out, ffd_stream_t stream);
+int ffd_metric_row_std(const float* x, int R, int64_t N, float* out, ffd_stream_t stream);
+
 /* ---- embeddings (transformer.py) ---------------------------------------- */
 int ffd_posemb_renorm(float* table, int L, int d, float max_norm, ffd_stream_t stream);
 /* out[i, :] = dense_w @ [sin(2*pi*t_i*W), cos(...)][:d] + dense_b   for i < n */

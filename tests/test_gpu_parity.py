@@ -557,3 +557,40 @@ def test_event_intensity_against_reference_vectors(tag):
     assert dev.is_cuda and dev.shape == (2,)
     assert abs(float(dev[1]) - want) <= 2e-6 * max(1.0, abs(want))
     assert abs(float(dev[0]) - O.event_intensity(cur, prev, 1e30) * 1e30) <= 1e-5 * float(dev[0])
+
+
+@pytest.mark.parametrize("n,m,shape", [(1000, 777, (187, 1)), (4096, 4096, (24, 3)), (300, 1, (16, 2)),
+                                       (16384, 5000, (187, 1))])
+def test_wasserstein_metrics_against_oracle(n, m, shape):
+    """SlicedWasserstein / MarginalWasserstein (metrics.py:101-216) on the device against the numpy restatement:
+    same directions (host RNG), distances within 1e-4 relative (fp32 projections vs float64)."""
+    import fastfourierdiffusion_b200 as F
+    from oracle import metrics_oracle as MO
+
+    rng = np.random.default_rng(5)
+    L, C = shape
+    orig = rng.normal(size=(n, L, C)).astype(np.float32)
+    other = (rng.normal(size=(m, L, C)) * 1.3 + 0.4 * np.sin(np.arange(L))[None, :, None]).astype(np.float32)
+    ndir = 16 if n > 5000 else 40
+    got = F.SlicedWasserstein(orig, random_seed=42, num_directions=ndir, save_all_distances=True)(torch.from_numpy(other))
+    want, wd = MO.sliced_wasserstein(orig, other, 42, ndir)
+    assert np.allclose(got["sliced_wasserstein_all"], wd, rtol=1e-4, atol=1e-5)
+    assert abs(got["sliced_wasserstein_mean"] - want["sliced_wasserstein_mean"]) < 1e-4 * want["sliced_wasserstein_mean"]
+    assert abs(got["sliced_wasserstein_max"] - want["sliced_wasserstein_max"]) < 1e-4 * want["sliced_wasserstein_max"]
+    if n <= 5000:
+        gm = F.MarginalWasserstein(orig, random_seed=42, save_all_distances=True)(other)
+        wm, wdm = MO.marginal_wasserstein(orig, other, 42)
+        assert np.allclose(gm["marginal_wasserstein_all"], wdm, rtol=1e-4, atol=1e-5)
+        assert abs(gm["marginal_wasserstein_mean"] - wm["marginal_wasserstein_mean"]) < 1e-4 * wm["marginal_wasserstein_mean"]
+        # standardise + single direction helpers
+        w = F.WassersteinDistances(orig, other, normalisation="standardise", seed=7)
+        wo = MO.WassersteinDistances(orig.reshape(n, -1), other.reshape(m, -1), normalisation="standardise", seed=7)
+        assert np.allclose(w.sliced_distances(6), wo.sliced_distances(6), rtol=1e-4, atol=1e-5)
+        assert abs(w.feature_distance(3) - wo.feature_distance(3)) < 1e-4
+    if n == 1000:
+        base = F.SlicedWasserstein(orig, random_seed=1, num_directions=8).baseline_metrics
+        assert set(base) == {"sliced_wasserstein_mean_self", "sliced_wasserstein_max_self",
+                             "sliced_wasserstein_mean_dummy", "sliced_wasserstein_max_dummy"}
+        assert 0 < base["sliced_wasserstein_mean_self"] < base["sliced_wasserstein_mean_dummy"]
+    with pytest.raises(Exception):
+        F.WassersteinDistances(np.zeros((40000, 4), np.float32), np.zeros((10, 4), np.float32))

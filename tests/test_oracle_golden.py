@@ -175,3 +175,36 @@ def test_event_intensity_oracle_matches_reference(tag):
     assert O.event_intensity(None, None, 0.1, step=5) == float(g[f"{tag}_none5"]) == 0.1
     got = O.event_intensity(g[f"{tag}_cur"], g[f"{tag}_prev"], float(g[f"{tag}_tau"]), step=3)
     assert abs(got - float(g[f"{tag}_val"])) <= 2e-6 * max(1.0, abs(float(g[f"{tag}_val"])))
+
+
+def test_emd2_1d_oracle_against_the_transport_lp():
+    """The 1-D transport cost behind the Wasserstein metrics (POT's emd2_1d, absent here): the quantile-coupling
+    restatement and the literal two-pointer walk against the optimum of the transport linear programme, and
+    against closed forms."""
+    from scipy.optimize import linprog
+
+    from oracle import metrics_oracle as MO
+
+    rng = np.random.default_rng(3)
+    for n, m in [(1, 1), (4, 4), (5, 3), (7, 12), (9, 1), (16, 11)]:
+        a, b = rng.normal(size=n), rng.normal(size=m) * 1.7 + 0.3
+        C = (a[:, None] - b[None, :]) ** 2
+        A_eq = np.zeros((n + m, n * m))
+        for i in range(n):
+            A_eq[i, i * m:(i + 1) * m] = 1.0
+        for j in range(m):
+            A_eq[n + j, j::m] = 1.0
+        b_eq = np.concatenate([np.full(n, 1.0 / n), np.full(m, 1.0 / m)])
+        lp = linprog(C.ravel(), A_eq=A_eq, b_eq=b_eq, bounds=(0, None), method="highs")
+        assert lp.status == 0
+        assert abs(MO.emd2_1d(a, b) - lp.fun) < 1e-9 * max(1.0, lp.fun)
+        assert abs(MO.emd2_1d_walk(a, b) - lp.fun) < 1e-9 * max(1.0, lp.fun)
+    x = rng.normal(size=1000)
+    assert abs(np.sqrt(MO.emd2_1d(x, x + 2.5)) - 2.5) < 1e-12        # translation
+    assert abs(np.sqrt(MO.emd2_1d(x, 3.0 * x)) - 2.0 * np.sqrt(np.mean(x ** 2))) < 1e-12  # scaling: comonotone
+    # class level: standardise divides both by std(original)
+    X, Y = rng.normal(size=(50, 6)), rng.normal(size=(70, 6)) + 0.5
+    d0 = MO.WassersteinDistances(X, Y, seed=1).sliced_distances(5)
+    d1 = MO.WassersteinDistances(X, Y, normalisation="standardise", seed=1).sliced_distances(5)
+    dirs = MO.WassersteinDistances(X, Y, seed=1).get_random_directions(5)
+    assert np.allclose(d1, d0 / np.array([np.std(X @ u) for u in dirs]))
