@@ -234,6 +234,12 @@ int ffd_event_intensity(const float* crf, const float* prev_crf, int64_t rows, i
   return launch_event_intensity(crf, prev_crf, rows, d, tau_0, out, (cudaStream_t)stream);
 }
 
+int ffd_spectral_density(const float* x_tilde, float* out, int64_t B, int L, int C, ffd_stream_t stream) {
+  FFD_CHECK_ARG(x_tilde && out && B >= 0 && L > 0 && C > 0, "bad ffd_spectral_density arguments");
+  if (B == 0) return FFD_OK;
+  return launch_spectral_density(x_tilde, out, B, L, C, (cudaStream_t)stream);
+}
+
 int ffd_metric_project(const float* data, int64_t N, int D, const float* dirs, int R, float* out,
                        ffd_stream_t stream) {
   FFD_CHECK_ARG(data && dirs && out && N > 0 && D > 0 && R > 0, "bad ffd_metric_project arguments");

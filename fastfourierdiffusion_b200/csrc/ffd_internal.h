@@ -42,6 +42,7 @@ int launch_event_intensity(const float* crf, const float* prev, int64_t rows, in
 int launch_metric_project(const float* data, int64_t N, int D, const float* dirs, int R, float* out, cudaStream_t s);
 int launch_metric_sort_rows(float* x, int R, int64_t N, cudaStream_t s);
 int launch_metric_w2_sorted(const float* a, int64_t N, const float* b, int64_t M, int R, float* out, cudaStream_t s);
+int launch_spectral_density(const float* xt, float* out, int64_t B, int L, int C, cudaStream_t s);
 int launch_metric_row_std(const float* x, int R, int64_t N, float* out, cudaStream_t s);
 
 // ffd_tc.cu (tcgen05 path)

@@ -123,6 +123,30 @@ __global__ void metric_row_std_kernel(const float* __restrict__ x, int64_t N, fl
   if (threadIdx.x == 0) out[blockIdx.x] = (float)sqrt(var);
 }
 
+// out[b, k, c] = Re(X_k)^2 + Im(X_k)^2 from the real-packed spectrum xt[b, :, c] (fourier.py:108-131): real parts in
+// rows 0..n_r-1, imaginary parts of bins 1.. in rows n_r.. (bin 0, and the Nyquist bin of an even L, have none).
+__global__ void spectral_density_kernel(const float* __restrict__ xt, float* __restrict__ out, int64_t B, int L, int C) {
+  const int nr = L / 2 + 1;
+  const int64_t total = B * nr * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int k = (int)((i / C) % nr);
+    const int64_t b = i / ((int64_t)C * nr);
+    const float re = xt[(b * L + k) * C + c];
+    const bool has_im = k > 0 && !(L % 2 == 0 && k == nr - 1);
+    const float im = has_im ? xt[(b * L + nr + k - 1) * C + c] : 0.f;
+    out[i] = re * re + im * im;
+  }
+}
+
+int launch_spectral_density(const float* xt, float* out, int64_t B, int L, int C, cudaStream_t s) {
+  const int64_t total = B * (L / 2 + 1) * C;
+  const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  spectral_density_kernel<<<grid ? grid : 1, 256, 0, s>>>(xt, out, B, L, C);
+  FFD_CHECK_LAUNCH("spectral_density_kernel");
+  return FFD_OK;
+}
+
 int launch_metric_project(const float* data, int64_t N, int D, const float* dirs, int R, float* out, cudaStream_t s) {
   dim3 grid((unsigned)((N + 63) / 64), (unsigned)((R + 63) / 64));
   metric_project_kernel<<<grid, 256, 0, s>>>(data, N, D, dirs, R, out);

@@ -55,3 +55,16 @@ def idft(x: torch.Tensor, feature_std: Optional[torch.Tensor] = None,
     """Inverse of :func:`dft`.  ``feature_std`` / ``feature_mean`` ([L, C]) fuse the
     de-standardisation of cmd/sample.py:107-109 in front of the transform."""
     return _apply(x, inverse=True, scale=feature_std, shift=feature_mean)
+
+
+def spectral_density(x: torch.Tensor, apply_dft: bool = True) -> torch.Tensor:
+    """fourier.py:97-131: (B, L, C) time series (or, with ``apply_dft=False``, its real-packed DFT) ->
+    |X_k|^2 of shape (B, L // 2 + 1, C)."""
+    dev = _lib.require_cuda()
+    assert x.dim() == 3, "expected (batch_size, max_len, n_channels)"
+    src = x.device
+    xt = (dft(x) if apply_dft else x).detach().to(device=dev, dtype=torch.float32).contiguous()
+    B, L, Cc = xt.shape
+    out = torch.empty(B, L // 2 + 1, Cc, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().ffd_spectral_density(_lib.ptr(xt), _lib.ptr(out), B, L, Cc, _lib.stream_handle(dev)))
+    return out if src.type == "cuda" else out.to(src)

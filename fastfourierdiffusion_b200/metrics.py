@@ -178,3 +178,55 @@ class MarginalWasserstein(_Metric):
     @property
     def name(self) -> str:
         return "marginal_wasserstein"
+
+
+class MetricCollection:
+    """metrics.py:28-98: every (partially instantiated) metric is evaluated on the time-domain samples and on their
+    DFT; optionally the marginal Wasserstein distance between spectral densities; baselines merged in."""
+
+    def __init__(self, metrics: list, original_samples: Optional[ArrayLike] = None, include_baselines: bool = True,
+                 include_spectral_density: bool = False) -> None:
+        from functools import partial
+
+        from .fourier import dft, spectral_density
+
+        self._dft, self._spectral = dft, spectral_density
+        metrics_time, metrics_freq = [], []
+        orig = None if original_samples is None else self._as_tensor(original_samples)
+        orig_freq = dft(orig) if orig is not None else None
+        for metric in metrics:
+            if isinstance(metric, partial):  # metrics.py:45-51
+                assert orig is not None, "Original samples must be provided for the metrics to be instantiated."
+                metrics_time.append(metric(original_samples=orig))
+                metrics_freq.append(metric(original_samples=orig_freq))
+        self.metrics_time, self.metrics_freq = metrics_time, metrics_freq
+        self.include_baselines = include_baselines
+        self.metric_spectral = (MarginalWasserstein(original_samples=spectral_density(orig), random_seed=42,
+                                                    save_all_distances=True)
+                                if include_spectral_density else None)
+
+    @staticmethod
+    def _as_tensor(x: ArrayLike) -> torch.Tensor:
+        t = torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x.detach()
+        return t.to(device=_lib.require_cuda(), dtype=torch.float32)
+
+    def __call__(self, other_samples: ArrayLike) -> dict:
+        other = self._as_tensor(other_samples)
+        other_freq = self._dft(other)
+        out: dict = {}
+        for mt, mf in zip(self.metrics_time, self.metrics_freq):
+            out.update({f"time_{k}": v for k, v in mt(other).items()})
+            out.update({f"freq_{k}": v for k, v in mf(other_freq).items()})
+        if self.include_baselines:
+            out.update(self.baseline_metrics)
+        if self.metric_spectral is not None:
+            out.update({f"spectral_{k}": v for k, v in self.metric_spectral(self._spectral(other)).items()})
+        return dict(sorted(out.items(), key=lambda item: item[0]))
+
+    @property
+    def baseline_metrics(self) -> dict:
+        out: dict = {}
+        for mt, mf in zip(self.metrics_time, self.metrics_freq):
+            out.update({f"time_{k}": v for k, v in mt.baseline_metrics.items()})
+            out.update({f"freq_{k}": v for k, v in mf.baseline_metrics.items()})
+        return out

@@ -117,7 +117,10 @@ int ffd_event_intensity(const float* crf, const float* prev_crf, int64_t rows, i
  *   ffd_metric_project:   out[r, n] = <data[n, :], dirs[r, :]>            (wasserstein.py:146-149, all directions)
  *   ffd_metric_sort_rows: every row of x[R, N] ascending, in place         (N <= 32768)
  *   ffd_metric_w2_sorted: out[r] = sqrt(emd2_1d(a[r, :N], b[r, :M])) for ascending rows (wasserstein.py:117-143)
- *   ffd_metric_row_std:   out[r] = np.std(x[r, :])                         (wasserstein.py:157-159 "standardise") */
+ *   ffd_metric_row_std:   out[r] = np.std(x[r, :])                         (wasserstein.py:157-159 "standardise")
+ *   ffd_spectral_density: out[b, k, c] = |X_k|^2 of the real-packed spectrum x_tilde[B, L, C] -> [B, L/2+1, C]
+ *                         (fourier.py:97-131 with apply_dft=False; MetricCollection's spectral metric) */
+int ffd_spectral_density(const float* x_tilde, float* out, int64_t B, int L, int C, ffd_stream_t stream);
 int ffd_metric_project(const float* data, int64_t N, int D, const float* dirs, int R, float* out, ffd_stream_t stream);
 int ffd_metric_sort_rows(float* x, int R, int64_t N, ffd_stream_t stream);
 int ffd_metric_w2_sorted(const float* a, int64_t N, const float* b, int64_t M, int R, float* out, ffd_stream_t stream);

@@ -640,3 +640,16 @@ def event_intensity(crf, prev_crf, tau_0, step=1, dtype=np.float32):
     energy = np.sqrt((delta * delta).sum(-1, dtype=dtype))                # :544 torch.norm(dim=-1)
     avg = float(energy.mean(dtype=dtype))                                 # :547
     return min(1.0, avg / tau_0)                                          # :550
+
+
+def spectral_density(x, apply_dft=True):
+    """fourier.py:97-131 on ``x[B, L, C]``: |X_k|^2 per frequency bin from the real-packed DFT."""
+    L = x.shape[1]
+    xt = dft(x) if apply_dft else x                       # :109
+    nr = n_real(L)                                        # :112
+    re, im = xt[:, :nr, :], xt[:, nr:, :]                 # :113-114
+    zero = np.zeros((x.shape[0], 1, x.shape[2]), xt.dtype)
+    im = np.concatenate([zero, im], axis=1)               # :117-118
+    if L % 2 == 0:
+        im = np.concatenate([im, zero], axis=1)           # :121-122
+    return re ** 2 + im ** 2                              # :129

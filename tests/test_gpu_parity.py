@@ -594,3 +594,46 @@ def test_wasserstein_metrics_against_oracle(n, m, shape):
         assert 0 < base["sliced_wasserstein_mean_self"] < base["sliced_wasserstein_mean_dummy"]
     with pytest.raises(Exception):
         F.WassersteinDistances(np.zeros((40000, 4), np.float32), np.zeros((10, 4), np.float32))
+
+
+@pytest.mark.parametrize("L", [24, 187, 101, 252])
+def test_spectral_density_against_reference_vectors(L):
+    """spectral_density (fourier.py:97-131) through ffd_dft_apply + ffd_spectral_density."""
+    import fastfourierdiffusion_b200 as F
+
+    g = load_golden("spectral.npz")
+    x = torch.from_numpy(g[f"x_{L}"]).cuda()
+    got = F.spectral_density(x)
+    assert got.shape == g[f"sd_{L}"].shape
+    assert np.allclose(got.cpu().numpy(), g[f"sd_{L}"], rtol=2e-4, atol=2e-5)
+    got2 = F.spectral_density(F.dft(x), apply_dft=False)
+    assert np.allclose(got2.cpu().numpy(), g[f"sdf_{L}"], rtol=2e-4, atol=2e-5)
+    assert F.spectral_density(x.cpu()).device.type == "cpu"  # returned on the caller's device, like dft
+
+
+def test_metric_collection_against_oracle():
+    """MetricCollection (metrics.py:28-98): time / freq / spectral keys, values against the numpy restatement."""
+    from functools import partial
+
+    import fastfourierdiffusion_b200 as F
+    from oracle import metrics_oracle as MO
+
+    rng = np.random.default_rng(9)
+    orig = rng.normal(size=(600, 24, 2)).astype(np.float32)
+    other = (rng.normal(size=(500, 24, 2)) * 1.2 + 0.2).astype(np.float32)
+    mc = F.MetricCollection([partial(F.SlicedWasserstein, random_seed=42, num_directions=12),
+                             partial(F.MarginalWasserstein, random_seed=42)], original_samples=orig,
+                            include_baselines=True, include_spectral_density=True)
+    res = mc(other)
+    assert list(res) == sorted(res)
+    for k in ("time_sliced_wasserstein_mean", "freq_sliced_wasserstein_max", "time_marginal_wasserstein_mean",
+              "freq_marginal_wasserstein_mean_self", "time_sliced_wasserstein_mean_dummy",
+              "spectral_marginal_wasserstein_mean", "spectral_marginal_wasserstein_all"):
+        assert k in res, k
+    o64, x64 = orig.astype(np.float64), other.astype(np.float64)
+    want_t, _ = MO.sliced_wasserstein(o64, x64, 42, 12)
+    want_f, _ = MO.sliced_wasserstein(O.dft(o64), O.dft(x64), 42, 12)
+    want_s, _ = MO.marginal_wasserstein(O.spectral_density(o64), O.spectral_density(x64), 42)
+    assert abs(res["time_sliced_wasserstein_mean"] - want_t["sliced_wasserstein_mean"]) < 1e-4
+    assert abs(res["freq_sliced_wasserstein_mean"] - want_f["sliced_wasserstein_mean"]) < 1e-4
+    assert abs(res["spectral_marginal_wasserstein_mean"] - want_s["marginal_wasserstein_mean"]) < 2e-4

@@ -208,3 +208,12 @@ def test_emd2_1d_oracle_against_the_transport_lp():
     d1 = MO.WassersteinDistances(X, Y, normalisation="standardise", seed=1).sliced_distances(5)
     dirs = MO.WassersteinDistances(X, Y, seed=1).get_random_directions(5)
     assert np.allclose(d1, d0 / np.array([np.std(X @ u) for u in dirs]))
+
+
+@pytest.mark.parametrize("L", [24, 187, 101, 252])
+def test_spectral_density_oracle_matches_reference(L):
+    """spectral_density (fourier.py:97-131), odd and even lengths, with and without the inner dft."""
+    g = load_golden("spectral.npz")
+    x = g[f"x_{L}"].astype(np.float64)
+    assert np.allclose(O.spectral_density(x), g[f"sd_{L}"], rtol=1e-4, atol=1e-5)
+    assert np.allclose(O.spectral_density(O.dft(x), apply_dft=False), g[f"sdf_{L}"], rtol=1e-4, atol=1e-5)
