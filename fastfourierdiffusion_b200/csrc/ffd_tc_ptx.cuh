@@ -213,6 +213,85 @@ __device__ __forceinline__ void umma_ts_4x3(uint32_t d, uint32_t a, uint32_t a_q
 #undef FFD_Q3
 }
 
+
+// ---- CTA pairs (cta_group::2): two SMs of a cluster run one M = 256 MMA; each supplies half of the B operand --------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA 0 of the cluster (the MMA-issuing CTA).  Default
+// semantics (as CUTLASS's ClusterBarrier::arrive): what is handed over lives in TMEM / is ordered by the tcgen05
+// fences, and a cluster-scope release would cost a memory fence per arriving thread (measured: 4x slower epilogue).
+__device__ __forceinline__ void mbar_arrive_cta0(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "memory");
+  return ok != 0;
+}
+// wait on a barrier that threads of the PEER CTA arrive on (cluster-scope acquire)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++polls > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t.reg .b16 m;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}" ::"r"(
+          smem_u32(bar))
+      : "memory");
+}
+#define FFD_TS2_HEAD                                                                  \
+  "{\n\t.reg .pred q, p;\n\t.reg .b32 ra;\n\t.reg .b64 bd, bs;\n\t"                     \
+  "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"                          \
+  "mov.b32 ra, %1;\n\tmov.b64 bd, %2;\n\tcvt.u64.u32 bs, %6;\n\t"                      \
+  "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [ra], bd, %3, p;\n\t"
+#define FFD_TS2_NEXT \
+  "add.u32 ra, ra, %5;\n\tadd.u64 bd, bd, bs;\n\t@q tcgen05.mma.cta_group::2.kind::f16 [%0], [ra], bd, %3, 1;\n\t"
+// D[tmem d] (+)= A[tmem a + i*a_step columns] . B[desc bd + i*b_step], i < NK, over the CTA pair (M = 256)
+template <int NK>
+__device__ __forceinline__ void umma2_ts_chain(uint32_t d, uint32_t a, uint32_t a_step, uint64_t bd, uint32_t b_step,
+                                               uint32_t idesc, uint32_t acc) {
+  if constexpr (NK >= 4) {
+    asm volatile(FFD_TS2_HEAD FFD_TS2_NEXT FFD_TS2_NEXT FFD_TS2_NEXT "}" FFD_TS_ARGS);
+    umma2_ts_chain<NK - 4>(d, a + 4 * a_step, a_step, bd + 4 * (uint64_t)b_step, b_step, idesc, 1);
+  } else if constexpr (NK >= 2) {
+    asm volatile(FFD_TS2_HEAD FFD_TS2_NEXT "}" FFD_TS_ARGS);
+    umma2_ts_chain<NK - 2>(d, a + 2 * a_step, a_step, bd + 2 * (uint64_t)b_step, b_step, idesc, 1);
+  } else if constexpr (NK == 1) {
+    asm volatile(FFD_TS2_HEAD "}" FFD_TS_ARGS);
+  }
+}
+
 #define FFD_SS_HEAD                                                                   \
   "{\n\t.reg .pred q, p;\n\t.reg .b64 ad, bd, as, bs;\n\t"                             \
   "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"                          \
