@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libffd_b200.so")
-SOURCES = ["ffd_api.cu", "ffd_simt.cu", "ffd_metrics.cu", "ffd_tc.cu", "ffd_tc_attn.cu"]
+SOURCES = ["ffd_api.cu", "ffd_simt.cu", "ffd_metrics.cu", "ffd_event.cu", "ffd_tc.cu", "ffd_tc_attn.cu"]
 
 
 def _nvcc() -> str:

@@ -25,6 +25,7 @@ EXPORTS = [
     "ffd_packed_bytes", "ffd_pack_weights", "ffd_workspace_bytes", "ffd_has_tensor_path",
     "ffd_dft_matrix", "ffd_dft_apply", "ffd_posemb_renorm", "ffd_time_embedding", "ffd_score_forward",
     "ffd_sde_step", "ffd_prior", "ffd_philox_normal", "ffd_sample_steps", "ffd_ffn_ln", "ffd_launch_count", "ffd_attn_cached_ln", "ffd_fresca", "ffd_fresca_scratch_floats", "ffd_event_intensity",
+    "ffd_event_decide", "ffd_event_refresh_kv",
     "ffd_metric_project", "ffd_metric_sort_rows", "ffd_metric_w2_sorted", "ffd_metric_row_std", "ffd_spectral_density",
 ]
 
@@ -51,12 +52,23 @@ class StepCoef(C.Structure):
                 ("sqrt_dt", C.c_float)]
 
 
+EVENT_STATS = 8
+
+
+class EventArgs(C.Structure):
+    """ffd_event_args: the device-decided E2-CRF schedule (device buffers + thresholds)."""
+    _fields_ = [("z_prev", C.c_void_p), ("accum", C.c_void_p), ("weight", C.c_void_p), ("stats", C.c_void_p),
+                ("K", C.c_int32), ("R", C.c_int32), ("accumulate", C.c_int32), ("tau_0", C.c_float),
+                ("tau_warn", C.c_float), ("eps", C.c_float), ("eta", C.c_float), ("probe_ratio", C.c_float),
+                ("seed", C.c_uint64)]
+
+
 class SampleArgs(C.Structure):
     _fields_ = [("fwd", ForwardArgs), ("G", C.c_void_p), ("time_emb_table", C.c_void_p),
                 ("coef_host", C.POINTER(StepCoef)), ("n_own_host", C.POINTER(C.c_int32)),
                 ("store_crf_host", C.POINTER(C.c_int32)), ("noise", C.c_void_p), ("noise_step0", C.c_int32), ("seed", C.c_uint64),
                 ("stream_base", C.c_uint64), ("x", C.c_void_p), ("x_tmp", C.c_void_p),
-                ("step_begin", C.c_int32), ("step_end", C.c_int32)]
+                ("step_begin", C.c_int32), ("step_end", C.c_int32), ("event", C.POINTER(EventArgs))]
 
 
 _lib: Optional[C.CDLL] = None
@@ -98,6 +110,8 @@ def load() -> C.CDLL:
     lib.ffd_fresca_scratch_floats.argtypes = [i64, i32, i32]
     lib.ffd_fresca.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, f32, f32, f32, i32, vp]
     lib.ffd_event_intensity.argtypes = [vp, vp, i64, i32, f32, vp, vp]
+    lib.ffd_event_decide.argtypes = [C.POINTER(EventArgs), vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.ffd_event_refresh_kv.argtypes = [pd, vp, i32, vp, vp, vp, vp, vp]
     lib.ffd_metric_project.argtypes = [vp, i64, i32, vp, i32, vp, vp]
     lib.ffd_metric_sort_rows.argtypes = [vp, i32, i64, vp]
     lib.ffd_metric_w2_sorted.argtypes = [vp, i64, vp, i64, i32, vp, vp]

@@ -15,6 +15,14 @@ accepted and stored so that ``cache_kwargs`` keep working.  The event
 intensity (caching.py:524-559; not called by the reference's sampler either)
 is provided as a device kernel: ``compute_event_intensity`` mirrors the
 reference call, ``event_intensity_device`` keeps the value on the device.
+
+``event_driven=True`` (not a reference argument; default off) switches the
+schedule to the one the reference's PAPER describes (section 3.3, Eq. 14-18,
+Algorithm 1) and decides it on the device: per-token change of the final-layer
+CRF against energy-weighted thresholds, an error-feedback accumulator, random
+probes and the periodic gamma-correction -- ``ffd_event_decide`` /
+``ffd_event_refresh_kv`` (include/ffd_b200.h).  The host never reads a
+decision; ``get_event_stats`` is the one optional read-back, after sampling.
 """
 
 from __future__ import annotations
@@ -29,7 +37,9 @@ class E2CRFCache:
                  tau_0: float = 0.1, tau_warn: float = 0.5, use_freqca: bool = False, freq_decomp: str = "dct",
                  low_freq_ratio: float = 0.3, max_history: int = 10, hermite_order: int = 3,
                  freq_decomp_interval: int = 10, use_fresca_in_cache: bool = False,
-                 fresca_adaptive_threshold: bool = False):
+                 fresca_adaptive_threshold: bool = False, event_driven: bool = False,
+                 event_probe_ratio: float = 0.0, event_accumulate: bool = True, event_eps: float = 1e-6,
+                 event_eta: float = 1e-6, event_seed: int = 0):
         if use_freqca:
             raise NotImplementedError("FreqCa is off the sampling path of the reference and is not built")
         self.num_layers = num_layers
@@ -47,6 +57,15 @@ class E2CRFCache:
         self.freq_decomp_interval = freq_decomp_interval
         self.use_fresca_in_cache = use_fresca_in_cache
         self.fresca_adaptive_threshold = fresca_adaptive_threshold
+        if event_driven and R <= 0:
+            raise ValueError("event_driven needs a positive error-feedback period R")
+        self.event_driven = bool(event_driven)
+        self.event_probe_ratio = float(event_probe_ratio)
+        self.event_accumulate = bool(event_accumulate)
+        self.event_eps = float(event_eps)
+        self.event_eta = float(event_eta)
+        self.event_seed = int(event_seed)
+        self._event_state: Optional[dict] = None  # device buffers of ffd_event_args
         # device stores, attached by ScoreModule.enable_caching (shape needs nhead/head_dim)
         self._k_store: Optional[torch.Tensor] = None  # [NL, H, L, hd], zero = never stored
         self._v_store: Optional[torch.Tensor] = None
@@ -63,6 +82,35 @@ class E2CRFCache:
         self._k_store = torch.zeros(self.num_layers, n_head, self.max_len, head_dim, device=dev)
         self._v_store = torch.zeros_like(self._k_store)
         self._crf_store = torch.zeros(self.num_layers, self.max_len, d_model, device=dev)
+
+    def event_args(self, d_model: int):
+        """ffd_event_args over this cache's device buffers (allocated on first use)."""
+        from . import _lib
+
+        dev = self.device
+        st = self._event_state
+        if st is None or st["z_prev"].device != dev or st["z_prev"].shape[1] != d_model:
+            st = {"z_prev": torch.zeros(self.max_len, d_model, device=dev),
+                  "accum": torch.zeros(self.max_len, device=dev),
+                  "weight": torch.zeros(self.max_len, device=dev),
+                  "stats": torch.zeros(_lib.EVENT_STATS, device=dev)}
+            self._event_state = st
+        e = _lib.EventArgs()
+        e.z_prev, e.accum, e.weight, e.stats = (_lib.ptr(st[k]) for k in ("z_prev", "accum", "weight", "stats"))
+        e.K, e.R, e.accumulate = int(self.K), int(self.R), int(self.event_accumulate)
+        e.tau_0, e.tau_warn, e.eps, e.eta = float(self.tau_0), float(self.tau_warn), self.event_eps, self.event_eta
+        e.probe_ratio, e.seed = self.event_probe_ratio, self.event_seed
+        return e
+
+    def get_event_stats(self) -> dict:
+        """Counters the decision kernel keeps on the device (one read-back; never needed by the step loop)."""
+        if self._event_state is None:
+            return {}
+        s = self._event_state["stats"].tolist()
+        n = max(s[0], 1.0)
+        return {"steps_decided": int(s[0]), "tokens_recomputed": int(s[1]), "tokens_corrected": int(s[2]),
+                "feedback_steps": int(s[3]), "last_event_intensity": s[4], "mean_event_intensity": s[5] / n,
+                "recompute_fraction": s[1] / (n * self.max_len)}
 
     @property
     def k_cache_tensor(self) -> Optional[torch.Tensor]:
@@ -99,6 +147,8 @@ class E2CRFCache:
         ``event_intensity`` are ignored, as in the reference."""
         if step == 0:
             return set(range(self.max_len))
+        if self.event_driven:
+            return set()  # which tokens are refreshed is decided on the device (ffd_event_decide)
         interval = 500 if self.R < 100 else self.R
         if step % interval == 0:
             return set(range(min(2 * min(self.K, self.max_len), self.max_len)))

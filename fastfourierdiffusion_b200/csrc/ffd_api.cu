@@ -97,7 +97,11 @@ static int pick_branch(const ffd_forward_args& a, int* populate) {
   return a.n_own == 0 ? 1 : 2;
 }
 
-static int forward_hidden(const ffd_forward_args& a, const Arena& ar, const Workspace& ws, cudaStream_t s) {
+// ev != nullptr: the device-decided schedule (ffd_event_args) -- pure-cache steps refresh each layer's sample-0 K/V
+// rows under the weights the previous step's decision left on the device, and every cached step ends with the
+// next decision; the full-recompute step (re)initialises the event state.
+static int forward_hidden(const ffd_forward_args& a, const Arena& ar, const Workspace& ws, cudaStream_t s,
+                          const ffd_event_args* ev = nullptr, int step = 0) {
   const ffd_dims& m = a.dims;
   const int L = m.max_len, C = m.n_channels, d = m.d_model, H = m.n_head, hd = d / H;
   const int64_t M = a.B * L;
@@ -107,12 +111,23 @@ static int forward_hidden(const ffd_forward_args& a, const Arena& ar, const Work
     return rc;
   int populate = 0;
   const int branch = pick_branch(a, &populate);
-  if (branch == 1 && a.precision == FFD_PREC_BF16 && tc_attn_supported(m)) {
+  const bool tc_images = branch == 1 && a.precision == FFD_PREC_BF16 && tc_attn_supported(m);
+  const bool event_refresh = ev && branch == 1;
+  if (tc_images && !event_refresh) {
     // the fp32 cache is the source of truth (it may have been reset or refreshed since the last
     // call); its bf16 operand images are 1.5 MB, so they are simply rebuilt every pure-cache step
     if ((rc = tc_pack_kv(m, a.k_cache, a.v_cache, ws.kvimg, s))) return rc;
   }
   for (int l = 0; l < m.n_layers; ++l) {
+    if (event_refresh) {
+      // sample 0's rows of this layer's input are the first L rows of ws.h
+      const float* w = a.weights + ar.layer0 + (int64_t)l * ar.layer_stride;
+      if ((rc = launch_event_refresh_kv(w + ar.in_w + (int64_t)d * d, w + ar.in_b + d, ws.h, ev->weight,
+                                        a.k_cache + (int64_t)l * H * L * hd, a.v_cache + (int64_t)l * H * L * hd, L, d,
+                                        H, s)))
+        return rc;
+      if (tc_images && (rc = tc_pack_kv_layer(m, l, a.k_cache, a.v_cache, ws.kvimg, s))) return rc;
+    }
     if ((rc = run_layer(a, ar, ws, l, branch, s))) return rc;
     if (populate) {
       // K/V of the layer OUTPUT of sample 0, all rows (cached_transformer.py:142-168)
@@ -129,6 +144,10 @@ static int forward_hidden(const ffd_forward_args& a, const Arena& ar, const Work
       FFD_CHECK_CUDA(cudaMemcpyAsync(a.crf_out + (int64_t)l * L * d, ws.h, sizeof(float) * L * d,
                                      cudaMemcpyDeviceToDevice, s));
     }
+  }
+  if (ev && a.mode == FFD_MODE_CACHED && (event_refresh || populate)) {
+    // z = final-layer CRF of sample 0, x = sample 0's state: the decision for the next step stays on the device
+    if ((rc = launch_event_decide(*ev, ws.h, a.X, L, d, C, step, populate ? 1 : 0, s))) return rc;
   }
   return FFD_OK;
 }
@@ -375,12 +394,41 @@ int ffd_philox_normal(uint64_t seed, uint64_t stream_id, float* out, int64_t n, 
   return launch_philox_normal(seed, stream_id, out, n, (cudaStream_t)stream);
 }
 
+int ffd_event_decide(const ffd_event_args* ev, const float* z, const float* x0, int L, int d, int C, int step,
+                     int first, ffd_stream_t stream) {
+  FFD_CHECK_ARG(ev && z && x0 && L > 0 && d > 0 && C > 0 && step >= 0, "bad ffd_event_decide arguments");
+  FFD_CHECK_ARG(ev->z_prev && ev->accum && ev->weight && ev->stats, "null pointer in ffd_event_args");
+  FFD_CHECK_ARG(ev->R > 0 && ev->K >= 0, "ffd_event_args: R must be positive, K non-negative");
+  return launch_event_decide(*ev, z, x0, L, d, C, step, first, (cudaStream_t)stream);
+}
+
+int ffd_event_refresh_kv(const ffd_dims* dims, const float* weights, int layer, const float* h0, const float* weight,
+                         float* k_cache, float* v_cache, ffd_stream_t stream) {
+  FFD_CHECK_ARG(dims && weights && h0 && weight && k_cache && v_cache, "bad ffd_event_refresh_kv arguments");
+  int rc = check_dims(*dims);
+  if (rc) return rc;
+  const ffd_dims& m = *dims;
+  FFD_CHECK_ARG(layer >= 0 && layer < m.n_layers, "layer %d out of range", layer);
+  const Arena ar = arena_of(m);
+  const int L = m.max_len, d = m.d_model, H = m.n_head, hd = d / H;
+  const float* w = weights + ar.layer0 + (int64_t)layer * ar.layer_stride;
+  return launch_event_refresh_kv(w + ar.in_w + (int64_t)d * d, w + ar.in_b + d, h0, weight,
+                                 k_cache + (int64_t)layer * H * L * hd, v_cache + (int64_t)layer * H * L * hd, L, d, H,
+                                 (cudaStream_t)stream);
+}
+
 int ffd_sample_steps(const ffd_sample_args* a, ffd_stream_t stream) {
   FFD_CHECK_ARG(a != nullptr, "null args");
   FFD_CHECK_ARG(a->G && a->time_emb_table && a->coef_host && a->n_own_host && a->x && a->x_tmp,
                 "null pointer in ffd_sample_args");
   FFD_CHECK_ARG(a->step_begin >= 0 && a->step_end >= a->step_begin, "bad step range");
   FFD_CHECK_ARG(!a->noise || a->noise_step0 <= a->step_begin, "noise_step0 beyond step_begin");
+  if (a->event) {
+    const ffd_event_args& e = *a->event;
+    FFD_CHECK_ARG(e.z_prev && e.accum && e.weight && e.stats, "null pointer in ffd_event_args");
+    FFD_CHECK_ARG(e.R > 0 && e.K >= 0, "ffd_event_args: R must be positive, K non-negative");
+    FFD_CHECK_ARG(a->fwd.k_cache && a->fwd.v_cache, "the event-driven schedule needs the K/V cache");
+  }
   ffd_forward_args f = a->fwd;
   f.X = a->x;
   f.time_emb = a->time_emb_table;  // placeholder for the null check
@@ -411,7 +459,7 @@ int ffd_sample_steps(const ffd_sample_args* a, ffd_stream_t stream) {
       FFD_CHECK_ARG(n_own <= m.max_len && fi.k_cache && fi.v_cache, "bad cached step %d", i);
     }
     if (!(a->store_crf_host && a->store_crf_host[i])) fi.crf_out = nullptr;
-    if ((rc = forward_hidden(fi, ar, ws, s))) return rc;
+    if ((rc = forward_hidden(fi, ar, ws, s, a->event, i))) return rc;
     const float* z = a->noise ? a->noise + (int64_t)(i - a->noise_step0) * n_elem : nullptr;
     if ((rc = launch_unembed_step(ws.h, f.weights + ar.unemb_w, f.weights + ar.unemb_b, f.score, 1, &c, a->G, cur, z,
                                   a->seed, a->stream_base + (uint64_t)i, nxt, f.B * m.max_len, m.max_len,

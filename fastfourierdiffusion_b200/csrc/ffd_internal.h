@@ -38,6 +38,12 @@ int launch_fresca(const float* U, const float* V, const float* score, float* out
 int launch_event_intensity(const float* crf, const float* prev, int64_t rows, int d, float tau_0, float* out,
                            cudaStream_t s);
 
+// ffd_event.cu (device-decided E2-CRF schedule)
+int launch_event_decide(const ffd_event_args& ev, const float* z, const float* x0, int L, int d, int C, int step,
+                        int first, cudaStream_t s);
+int launch_event_refresh_kv(const float* Wkv, const float* bkv, const float* h0, const float* weight, float* kc,
+                            float* vc, int L, int d, int H, cudaStream_t s);
+
 // ffd_metrics.cu
 int launch_metric_project(const float* data, int64_t N, int D, const float* dirs, int R, float* out, cudaStream_t s);
 int launch_metric_sort_rows(float* x, int R, int64_t N, cudaStream_t s);
@@ -63,6 +69,8 @@ int tc_pack_attn(const ffd_dims& m, const float* weights, void* img_base, int64_
                  int64_t attn_off_bytes, cudaStream_t s);
 // bf16 K/V operand images of all layers/heads from the fp32 sample-0 cache [NL, H, L, hd]
 int tc_pack_kv(const ffd_dims& m, const float* kc, const float* vc, void* kvimg, cudaStream_t s);
+// the same for one layer (kc / vc / kvimg are the bases of all layers)
+int tc_pack_kv_layer(const ffd_dims& m, int layer, const float* kc, const float* vc, void* kvimg, cudaStream_t s);
 // y = LN1(x + out_proj(softmax(q K_c^T / sqrt(hd)) V_c)) for layer `layer`, rows [0, M); y may alias x
 int tc_attn_cached(const ffd_dims& m, const void* attn_img, const void* kvimg, const float* weights, int layer,
                    const float* x, float* y, int64_t M, cudaStream_t s);

@@ -1171,6 +1171,16 @@ int tc_pack_kv(const ffd_dims& m, const float* kc, const float* vc, void* kvimg,
   return FFD_OK;
 }
 
+int tc_pack_kv_layer(const ffd_dims& m, int layer, const float* kc, const float* vc, void* kvimg, cudaStream_t s) {
+  const AttnGeom g = attn_geom(m);
+  const int64_t cache_off = (int64_t)layer * m.n_head * m.max_len * g.hd;
+  const int64_t img_off = (int64_t)layer * m.n_head * g.NCH * 2 * g.CK * tc::HP;  // 16-bit elements
+  tc::pack_kv_kernel<<<16, 256, 0, s>>>(kc + cache_off, vc + cache_off, (uint16_t*)kvimg + img_off, m.n_head,
+                                        m.max_len, g.hd, m.n_head, g.G, g.NCH, g.CK);
+  FFD_CHECK_LAUNCH("pack_kv_kernel");
+  return FFD_OK;
+}
+
 long long* g_attn_dbg = nullptr;  // optional device buffer of clock64 stamps (profiling aid)
 
 template <int DP, int KQ>

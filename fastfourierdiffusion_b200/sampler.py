@@ -186,6 +186,11 @@ class DiffusionSampler:
         a.store_crf_host = crf_flags
         a.seed = self.seed
         a.stream_base = self._stream_base(batch_idx) + 1
+        event = None
+        if cache is not None and cache.event_driven:
+            # the device-decided schedule: K/V rows live with the first cache of the model
+            event = cache.event_args(model.dims.d_model)
+            a.event = C.pointer(event)
         x_tmp = torch.empty_like(X)
         a.x = _lib.ptr(X)
         a.x_tmp = _lib.ptr(x_tmp)

@@ -18,6 +18,7 @@
  *   ffd_prior                        src/fdiff/schedulers/sde.py:79-87, :125-127
  *   ffd_philox_normal                torch.randn / randn_like call sites sde.py:85,157,238
  *   ffd_sample_steps                 src/fdiff/sampling/sampler.py:157-210 (the step loop)
+ *   ffd_event_decide / _refresh_kv   the paper's Algorithm 1 (no counterpart in the reference's code)
  *
  * Conventions: plain pointers and sizes only; all pointers are DEVICE pointers
  * unless the name ends in _host; the library never allocates, never frees and
@@ -185,6 +186,46 @@ int ffd_prior(const float* G, const float* z, uint64_t seed, uint64_t stream_id,
               int64_t B, int L, int C, ffd_stream_t stream);
 int ffd_philox_normal(uint64_t seed, uint64_t stream_id, float* out, int64_t n, ffd_stream_t stream);
 
+/* ---- E2-CRF event-driven schedule, decided on the device (opt-in) ---------------------------------------
+ * The reference's shipped schedule is a pure function of the step index (caching.py:131-181); its event code
+ * (caching.py:524-559) is never called.  This is the schedule the reference's paper describes
+ * (submission/TSD_Cache_Paper_Final.pdf, section 3.3, Eq. 14-18, Algorithm 1), run without a host sync:
+ *
+ *   after the score model of step i (ffd_event_decide; z = final-layer CRF of sample 0, [L, d]):
+ *     r_i      = ||z_i - z_{i-1}||_F^2 / (||z_{i-1}||_F^2 + eta)                                    (Eq. 14)
+ *     delta_k  = ||z_i[k] - z_{i-1}[k]||_2 ;  a_k <- a_k + delta_k   (error-feedback accumulator; a_k <- delta_k
+ *                when accumulate == 0, which is Eq. 15 verbatim)
+ *     tau_k    = tau_0 / (eps + ||x_i[k]||_2^2)            (energy-weighted threshold, x = sample 0's state)
+ *     S_{i+1}  = {k <= K}  U  {k : a_k > tau_k}  U  RandomProbe(k > K, probability probe_ratio)      (Eq. 15)
+ *     weight_k = 1 for k in S_{i+1} (recompute; a_k <- 0), else gamma_i = min(0.1, r_i / 2) when
+ *                (i + 1) % R == 0 or r_i > tau_warn (error-feedback correction, Eq. 17-18), else 0 (reuse)
+ *   before every layer's attention of step i+1 (ffd_event_refresh_kv):
+ *     K_l[k], V_l[k] <- (1 - weight_k) * cache + weight_k * Project(layer input of sample 0, token k)
+ *   and every sample attends to the refreshed sample-0 cache (pure-cache branch, cached_transformer.py:228-258).
+ * With batch size 1 (the reference's benchmark batch, cmd/benchmark_cache.py:73) this is Algorithm 1 itself; for
+ * larger batches the cache keeps sample 0 only, as the reference's store does (caching.py:326-328).
+ * All buffers are DEVICE memory; the decision never leaves the device. */
+#define FFD_EVENT_STATS 8 /* floats: [0] steps decided, [1] tokens recomputed (weight 1), [2] tokens corrected
+                             (0 < weight < 1), [3] feedback steps, [4] last r_i, [5] sum of r_i, [6..7] reserved */
+typedef struct ffd_event_args {
+  float* z_prev;   /* [L, d]  final-layer CRF of the previous step */
+  float* accum;    /* [L]     error-feedback accumulators a_k */
+  float* weight;   /* [L]     blend weights applied by the NEXT step's refresh */
+  float* stats;    /* [FFD_EVENT_STATS] running counters */
+  int32_t K;       /* tokens 0..K are always recomputed */
+  int32_t R;       /* error-feedback period (> 0) */
+  int32_t accumulate; /* 1: a_k accumulates while a token is reused; 0: a_k = delta_k */
+  float tau_0, tau_warn, eps, eta, probe_ratio;
+  uint64_t seed;   /* RandomProbe: Philox keyed (seed, step), counter = token */
+} ffd_event_args;
+
+/* first != 0: (re)initialise -- z_prev <- z, a_k = 0, weight = 0, stats = 0 (after the full-recompute step 0). */
+int ffd_event_decide(const ffd_event_args* ev, const float* z, const float* x0, int L, int d, int C, int step,
+                     int first, ffd_stream_t stream);
+/* layer `layer` of the sample-0 cache [NL, H, L, hd] from h0 = sample 0's rows [L, d] of that layer's input */
+int ffd_event_refresh_kv(const ffd_dims* dims, const float* weights, int layer, const float* h0, const float* weight,
+                         float* k_cache, float* v_cache, ffd_stream_t stream);
+
 /* ---- the step loop -------------------------------------------------------- */
 typedef struct ffd_sample_args {
   ffd_forward_args fwd;        /* X is updated in place; score may be NULL */
@@ -200,6 +241,7 @@ typedef struct ffd_sample_args {
   float* x;                    /* [B, L, C] state, in/out */
   float* x_tmp;                /* [B, L, C] scratch */
   int32_t step_begin, step_end;
+  const ffd_event_args* event; /* HOST struct or NULL: device-decided schedule for cached steps with n_own_host == 0 */
 } ffd_sample_args;
 
 int ffd_sample_steps(const ffd_sample_args* a, ffd_stream_t stream);

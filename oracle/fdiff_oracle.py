@@ -436,6 +436,103 @@ def cache_stats(store: KVStore, current_step: int) -> Dict[str, float]:
 # --------------------------------------------------------------------------- #
 
 
+# --------------------------------------------------------------------------- #
+# Event-driven schedule of the reference's PAPER (submission/TSD_Cache_Paper_Final.pdf
+# section 3.3: Eq. 14 intensity, Eq. 15 recompute set, Eq. 17-18 error feedback,
+# Algorithm 1).  The reference's code never runs it (caching.py:131-181 decides by
+# step index; caching.py:524-559 is dead), so this part of the oracle restates the
+# paper's equations, not reference code: parity for it is UNPINNED by reference runs
+# and is anchored on the closed forms in tests/test_event_cpu.py instead.
+# --------------------------------------------------------------------------- #
+
+
+@dataclass
+class EventConfig:
+    K: int = 5
+    R: int = 10
+    tau_0: float = 0.1
+    tau_warn: float = 0.5
+    eps: float = 1e-6
+    eta: float = 1e-6
+    probe_ratio: float = 0.0
+    accumulate: bool = True
+    seed: int = 0
+
+
+class EventState:
+    def __init__(self, max_len: int, d_model: int, dtype=np.float32):
+        self.z_prev = np.zeros((max_len, d_model), dtype=dtype)
+        self.accum = np.zeros(max_len, dtype=dtype)
+        self.weight = np.zeros(max_len, dtype=dtype)
+        self.stats = np.zeros(8, dtype=np.float64)
+        self.last: Dict[str, np.ndarray] = {}
+
+
+def event_uniform(seed: int, step: int, max_len: int) -> np.ndarray:
+    """RandomProbe draw per token: Philox(counter=(k, 0, step, 0), key=seed), first word -> (0, 1) in fp32."""
+    k = np.arange(max_len, dtype=np.uint32)
+    ctr = np.stack([k, np.zeros_like(k), np.full_like(k, step), np.zeros_like(k)], axis=1)
+    key = np.stack([np.full(max_len, seed & 0xFFFFFFFF, dtype=np.uint32),
+                    np.full(max_len, (seed >> 32) & 0xFFFFFFFF, dtype=np.uint32)], axis=1)
+    r = philox4x32_10(ctr, key)[:, 0]
+    return (r.astype(np.float32) + np.float32(0.5)) * np.float32(2.3283064365386963e-10)
+
+
+def event_decide(cfg: EventConfig, st: EventState, z: np.ndarray, x0: np.ndarray, step: int, first: bool) -> None:
+    """Decision after the score model of step `step`: z = final-layer CRF of sample 0 [L, d], x0 = sample 0's
+    state [L, C].  Leaves the next step's blend weights in st.weight."""
+    dt = st.z_prev.dtype
+    z = z.astype(dt)
+    L = z.shape[0]
+    if first:
+        st.z_prev = z.copy()
+        st.accum[:] = 0
+        st.weight[:] = 0
+        st.stats[:] = 0
+        st.last = {}
+        return
+    diff = z - st.z_prev
+    delta = np.sqrt((diff * diff).sum(axis=1))                       # ||z_i[k] - z_{i-1}[k]||_2
+    r = (diff * diff).sum() / ((st.z_prev * st.z_prev).sum() + dt.type(cfg.eta))   # Eq. 14
+    feedback = ((step + 1) % cfg.R == 0) or (r > cfg.tau_warn)       # Algorithm 1, line 16
+    gamma = min(0.1, 0.5 * float(r))
+    energy = (x0.astype(dt) ** 2).sum(axis=1)
+    tau = dt.type(cfg.tau_0) / (dt.type(cfg.eps) + energy)           # Eq. 15 thresholds
+    a = (st.accum if cfg.accumulate else 0) + delta
+    k = np.arange(L)
+    probe = np.zeros(L, dtype=bool)
+    if cfg.probe_ratio > 0:
+        probe = (k > cfg.K) & (event_uniform(cfg.seed, step, L) < np.float32(cfg.probe_ratio))
+    rec = (k <= cfg.K) | (a > tau) | probe                           # Eq. 15
+    st.weight = np.where(rec, 1.0, gamma if feedback else 0.0).astype(dt)
+    st.accum = np.where(rec, 0.0, a).astype(dt)
+    st.z_prev = z.copy()
+    st.stats[0] += 1
+    st.stats[1] += int(rec.sum())
+    st.stats[2] += int(((~rec) & (st.weight > 0)).sum())
+    st.stats[3] += 1 if feedback else 0
+    st.stats[4] = float(r)
+    st.stats[5] += float(r)
+    st.last = {"r": np.asarray(r), "a": a, "tau": tau, "rec": rec, "probe": probe, "feedback": np.asarray(feedback),
+               "gamma": np.asarray(gamma), "delta": delta}
+
+
+def event_refresh_kv(lw: LayerWeights, h0: np.ndarray, weight: np.ndarray, store: KVStore, layer: int, H: int) -> None:
+    """K/V rows of sample 0 for layer `layer` from that layer's input h0 [L, d] (the mixed branch's projection,
+    cached_transformer.py:282-296), blended into the store: cache += weight * (new - cache)  (Eq. 18; weight 1 =
+    recompute, 0 = reuse)."""
+    L, d = h0.shape
+    wk, wv = lw.in_proj_w[d:2 * d], lw.in_proj_w[2 * d:3 * d]
+    bk, bv = lw.in_proj_b[d:2 * d], lw.in_proj_b[2 * d:3 * d]
+    kn = _split_heads((h0 @ wk.T + bk)[None], H)[0]  # [H, L, hd]
+    vn = _split_heads((h0 @ wv.T + bv)[None], H)[0]
+    w = weight.astype(h0.dtype)[None, :, None]
+    on = (weight > 0)[None, :, None]
+    full = (weight >= 1)[None, :, None]
+    store.k[layer] = np.where(full, kn, np.where(on, store.k[layer] + w * (kn - store.k[layer]), store.k[layer]))
+    store.v[layer] = np.where(full, vn, np.where(on, store.v[layer] + w * (vn - store.v[layer]), store.v[layer]))
+
+
 class OracleScoreModel:
     def __init__(self, w: ModelWeights, max_len: int, n_channels: int, dtype=np.float32,
                  renorm_iters: int = 3):
@@ -475,6 +572,17 @@ class OracleScoreModel:
         return self.unembed(h), np.stack(crf)
 
 
+    def forward_event(self, X: np.ndarray, t: float, store: KVStore, weight: np.ndarray):
+        """A pure-cache step of the event-driven schedule: every layer first refreshes the sample-0 K/V rows
+        from its own input under `weight`, then runs the pure-cache branch.  Returns (score, z_L)."""
+        h = self.embed(X, t)
+        for i, lw in enumerate(self.w.layers):
+            lw = _cast_layer(lw, self.dtype)
+            event_refresh_kv(lw, h[0], weight, store, i, self.H)
+            h = cached_layer(lw, h, self.H, [], store, i)
+        return self.unembed(h), h[0].copy()
+
+
 def _cast_layer(lw: LayerWeights, dtype) -> LayerWeights:
     if lw.w1.dtype == dtype:
         return lw
@@ -492,7 +600,10 @@ class OracleSampler:
     """DiffusionSampler.sample (sampler.py:105-215) with injected noise."""
 
     def __init__(self, model: OracleScoreModel, sde: SDEConfig, use_cache: bool = False,
-                 K: int = 5, R: int = 10):
+                 K: int = 5, R: int = 10, event: Optional[EventConfig] = None):
+        self.event = event
+        self.event_state = (EventState(model.L, model.w.d_model, np.dtype(model.dtype)) if event is not None
+                            else None)
         self.model = model
         self.sde = sde
         self.use_cache = use_cache
@@ -507,7 +618,13 @@ class OracleSampler:
         """reverse_diffusion_step (sampler.py:48-103)."""
         if self.use_cache and S is not None:
             self.current_step = global_step  # sampler.py:182
+            if self.event is not None and len(S) == 0:
+                score, zL = self.model.forward_event(X, t, self.store, self.event_state.weight)
+                event_decide(self.event, self.event_state, zL, X[0], global_step, False)
+                return sde_step(self.sde, self.G, score, t, X, z, step_size, self.model.dtype), score
             score, crf = self.model.forward_cached(X, t, S, self.store)
+            if self.event is not None and len(S) == self.model.L:
+                event_decide(self.event, self.event_state, crf[-1], X[0], global_step, True)
             if self.current_step % self.R == 0:  # update_crf, caching.py:474 (R=0 raises there too)
                 self.crf = crf
         else:

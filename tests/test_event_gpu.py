@@ -1,0 +1,211 @@
+"""The device-decided E2-CRF schedule (ffd_event_decide / ffd_event_refresh_kv / ffd_sample_steps with
+ffd_event_args) against the restatement of the paper's Algorithm 1 in oracle/fdiff_oracle.py.  Decisions (the
+per-token blend weights left on the device) must match exactly except where a token sits within 1e-3 of its
+threshold; values within fp32 tolerances stated per check."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from ffd_testutil import ECG, build_seeded_model, build_tiny_model, load_golden, rel, tiny_state_dict
+from oracle import fdiff_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _event_args(L, d, cfg):
+    from fastfourierdiffusion_b200 import _lib
+
+    bufs = {"z_prev": torch.zeros(L, d, device="cuda"), "accum": torch.zeros(L, device="cuda"),
+            "weight": torch.zeros(L, device="cuda"), "stats": torch.zeros(_lib.EVENT_STATS, device="cuda")}
+    e = _lib.EventArgs()
+    e.z_prev, e.accum, e.weight, e.stats = (_lib.ptr(bufs[k]) for k in ("z_prev", "accum", "weight", "stats"))
+    e.K, e.R, e.accumulate = cfg.K, cfg.R, int(cfg.accumulate)
+    e.tau_0, e.tau_warn, e.eps, e.eta, e.probe_ratio, e.seed = (cfg.tau_0, cfg.tau_warn, cfg.eps, cfg.eta,
+                                                                cfg.probe_ratio, cfg.seed)
+    return e, bufs
+
+
+def _check_decision(bufs, st, tag):
+    last = st.last
+    margin = np.abs(last["a"] / last["tau"] - 1.0)
+    safe = (margin > 1e-3) | (np.arange(len(margin)) <= 0)
+    w_dev = bufs["weight"].cpu().numpy()
+    rec_dev = w_dev >= 1.0
+    assert np.array_equal(rec_dev[safe], last["rec"][safe]), tag
+    same = rec_dev == last["rec"]
+    assert np.allclose(w_dev[same], st.weight[same], rtol=1e-4, atol=1e-7), tag
+    assert np.allclose(bufs["accum"].cpu().numpy()[same], st.accum[same], rtol=1e-4, atol=1e-6), tag
+    return bool(same.all())
+
+
+@pytest.mark.parametrize("L,d,Cc", [(187, 72, 1), (365, 72, 13), (16, 12, 2), (1500, 128, 3)])
+@pytest.mark.parametrize("accumulate", [True, False])
+def test_event_decide_kernel_against_oracle(L, d, Cc, accumulate):
+    from fastfourierdiffusion_b200 import _lib
+
+    lib = _lib.load()
+    st_h = _lib.stream_handle()
+    rng = np.random.default_rng(L + d)
+    cfg = O.EventConfig(K=min(5, L - 1), R=4, tau_0=0.6, tau_warn=0.02, eps=1e-6, eta=1e-6, probe_ratio=0.05,
+                        accumulate=accumulate, seed=1234567891011)
+    e, bufs = _event_args(L, d, cfg)
+    st = O.EventState(L, d, np.dtype(np.float32))
+    z = rng.normal(size=(L, d)).astype(np.float32)
+    all_same = True
+    for step in range(12):
+        x0 = (rng.normal(size=(L, Cc)) * rng.uniform(0.2, 3.0, size=(L, 1))).astype(np.float32)
+        first = step == 0
+        _lib.check(lib.ffd_event_decide(C.byref(e), _lib.ptr(torch.from_numpy(z).cuda()),
+                                        _lib.ptr(torch.from_numpy(x0).cuda()), L, d, Cc, step, int(first), st_h))
+        O.event_decide(cfg, st, z, x0, step, first)
+        torch.cuda.synchronize()
+        assert np.array_equal(bufs["z_prev"].cpu().numpy(), z)
+        if not first:
+            all_same &= _check_decision(bufs, st, f"step {step}")
+            s = bufs["stats"].cpu().numpy()
+            assert s[4] == pytest.approx(float(st.last["r"]), rel=1e-4)
+            assert s[3] == st.stats[3] and s[0] == st.stats[0]
+            rec = st.last["rec"]
+            assert 0.02 * L < rec.sum() < 0.98 * L or L <= 16  # thresholds chosen so that both outcomes occur
+        # token-dependent drift: some tokens move a lot, most a little
+        scale = np.where(rng.uniform(size=(L, 1)) < 0.15, 0.3, 0.01 * (1 + step % 3))
+        z = (z + scale * rng.normal(size=(L, d))).astype(np.float32)
+    if all_same:
+        assert np.array_equal(bufs["stats"].cpu().numpy()[:4], st.stats[:4].astype(np.float32))
+
+
+@pytest.mark.parametrize("dims", [dict(max_len=16, n_channels=2, d_model=12, n_head=2, d_ff=64, n_layers=2),
+                                  dict(max_len=187, n_channels=1, d_model=72, n_head=12, d_ff=2048, n_layers=3)])
+def test_event_refresh_kv_kernel_against_oracle(dims):
+    from fastfourierdiffusion_b200 import _lib
+
+    lib = _lib.load()
+    L, d, H, NL = dims["max_len"], dims["d_model"], dims["n_head"], dims["n_layers"]
+    hd = d // H
+    dm = _lib.Dims(L, dims["n_channels"], d, H, dims["d_ff"], NL)
+    rng = np.random.default_rng(3)
+    arena = (rng.normal(size=lib.ffd_weights_count(dm)) * 0.2).astype(np.float32)
+    l0, stride = lib.ffd_layer0_offset(dm), lib.ffd_layer_stride(dm)
+    layer = NL - 1
+    in_w = arena[l0 + layer * stride:][:3 * d * d].reshape(3 * d, d)
+    in_b = arena[l0 + layer * stride + 3 * d * d:][:3 * d]
+    lw = O.LayerWeights(in_proj_w=in_w.astype(np.float64), in_proj_b=in_b.astype(np.float64),
+                        **{f: np.zeros(1) for f in O.LayerWeights.__dataclass_fields__ if not f.startswith("in_proj")})
+    store = O.KVStore(NL, L)
+    k0 = rng.normal(size=(NL, H, L, hd)).astype(np.float32)
+    v0 = rng.normal(size=(NL, H, L, hd)).astype(np.float32)
+    store.k, store.v = k0.astype(np.float64), v0.astype(np.float64)
+    h0 = rng.normal(size=(L, d)).astype(np.float32)
+    w = np.zeros(L, dtype=np.float32)
+    w[rng.uniform(size=L) < 0.3] = 1.0
+    w[(rng.uniform(size=L) < 0.3) & (w == 0)] = 0.07
+    kc, vc = torch.from_numpy(k0).cuda(), torch.from_numpy(v0).cuda()
+    _lib.check(lib.ffd_event_refresh_kv(dm, _lib.ptr(torch.from_numpy(arena).cuda()), layer,
+                                        _lib.ptr(torch.from_numpy(h0).cuda()), _lib.ptr(torch.from_numpy(w).cuda()),
+                                        _lib.ptr(kc), _lib.ptr(vc), _lib.stream_handle()))
+    O.event_refresh_kv(lw, h0.astype(np.float64), w.astype(np.float64), store, layer, H)
+    assert rel(kc.cpu().numpy(), store.k) < 2e-6 and rel(vc.cpu().numpy(), store.v) < 2e-6
+    # reused tokens and the other layers are untouched, bit for bit
+    keep = w == 0
+    assert np.array_equal(kc.cpu().numpy()[layer][:, keep], k0[layer][:, keep])
+    assert np.array_equal(kc.cpu().numpy()[:layer], k0[:layer]) and np.array_equal(vc.cpu().numpy()[:layer], v0[:layer])
+
+
+def _oracle_event_run(g, cfg, n, B):
+    w = O.ModelWeights.from_state_dict(tiny_state_dict(), 2)
+    osamp = O.OracleSampler(O.OracleScoreModel(w, 16, 2), O.SDEConfig("vp", fourier_noise_scaling=True),
+                            use_cache=True, K=cfg.K, R=cfg.R, event=cfg)
+    X = O.prior_sample(osamp.sde, osamp.G, g["prior_z"][0][:B])
+    ts = g["timesteps"]
+    decisions = []
+    for i in range(n):
+        S = list(range(16)) if i == 0 else []
+        X, _ = osamp.step(X, float(ts[i]), g["step_z"][0][i][:B], np.float32(ts[0] - ts[1]), S, i)
+        decisions.append(osamp.event_state.weight.copy())
+    return X, osamp, decisions
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("B", [1, 3])
+def test_event_driven_sampler_against_oracle(prec, B):
+    """Whole event-driven runs of the tiny model through DiffusionSampler.run_steps (ffd_sample_steps with
+    ffd_event_args), the reference's noise injected.  fp32: per-step decisions equal the oracle's, states within
+    the trajectory tolerance.  bf16: states within the bf16 trajectory tolerance, recompute fraction within 3 %."""
+    import fastfourierdiffusion_b200 as F
+    from fastfourierdiffusion_b200 import _lib
+
+    if prec == "bf16" and not _lib.load().ffd_has_tensor_path():
+        pytest.skip("tensor path not available")
+    m = build_tiny_model(precision=prec)
+    if prec == "bf16" and not m._tc_ok():
+        pytest.skip("model shape not supported by the tcgen05 kernels")
+    g = load_golden("tiny_vp_freq_cache.npz")
+    n = 40
+    cfg = O.EventConfig(K=1, R=4, tau_0=1000.0, tau_warn=0.05, probe_ratio=0.1, seed=3)
+    kw = dict(K=cfg.K, R=cfg.R, tau_0=cfg.tau_0, tau_warn=cfg.tau_warn, event_driven=True,
+              event_probe_ratio=cfg.probe_ratio, event_seed=cfg.seed)
+    sampler = F.DiffusionSampler(m, B, use_cache=True, cache_kwargs=kw)
+    m.noise_scheduler.set_timesteps(int(g["n_steps"]))
+    m.cache.reset()
+    Xo, osamp, decisions = _oracle_event_run(g, cfg, n, B)
+    z = torch.from_numpy(g["step_z"][0][:, :B].copy())
+    X = m.noise_scheduler.prior_from_noise(torch.from_numpy(g["prior_z"][0][:B].copy()))
+    if prec == "fp32":
+        for i in range(n):
+            X = sampler.run_steps(X, 0, noise=z, step_begin=i, step_end=i + 1)
+            w_dev = m.cache._event_state["weight"].cpu().numpy()
+            assert np.array_equal(w_dev >= 1, decisions[i] >= 1), i
+            assert np.allclose(w_dev, decisions[i], rtol=1e-3, atol=1e-6), i
+    else:
+        X = sampler.run_steps(X, 0, noise=z, step_begin=0, step_end=n)
+    tol = 5e-4 if prec == "fp32" else 5e-2
+    assert rel(X.cpu().numpy(), Xo) < tol
+    st = m.cache.get_event_stats()
+    os_ = osamp.event_state.stats
+    assert st["steps_decided"] == int(os_[0]) == n - 1
+    if prec == "fp32":
+        assert st["tokens_recomputed"] == int(os_[1]) and st["feedback_steps"] == int(os_[3])
+        own = m._kv_owner
+        assert rel(own._k_store.cpu().numpy(), osamp.store.k) < 2e-3
+        assert rel(own._v_store.cpu().numpy(), osamp.store.v) < 2e-3
+    else:
+        assert abs(st["tokens_recomputed"] - os_[1]) <= 0.03 * (n - 1) * 16
+    assert 0.1 < st["recompute_fraction"] < 0.95  # both outcomes occur in this run
+
+
+def test_event_driven_is_one_launch_loop_without_host_sync():
+    """ECG-sized event-driven run on the tensor-core path: one ffd_sample_steps call covers all steps (the decision
+    never visits the host), extreme thresholds reduce to the two limiting schedules, and the result stays finite."""
+    import fastfourierdiffusion_b200 as F
+    from fastfourierdiffusion_b200 import _lib
+
+    if not _lib.load().ffd_has_tensor_path():
+        pytest.skip("tensor path not available")
+    m = build_seeded_model(ECG, 42, precision="bf16").to("cuda").eval()
+    B, n = 64, 12
+    outs = {}
+    for tag, tau0 in (("never", 1e30), ("always", 0.0), ("mixed", 2e3)):
+        s = F.DiffusionSampler(m, B, use_cache=True, noise="philox",
+                               cache_kwargs=dict(K=5, R=1000, tau_0=tau0, tau_warn=1e30, event_driven=True))
+        m.noise_scheduler.set_timesteps(1000)
+        m.cache.reset()
+        X = s.sample_prior(B)
+        n0 = _lib.load().ffd_launch_count()
+        X = s.run_steps(X, 0, step_begin=0, step_end=n)
+        torch.cuda.synchronize()
+        assert torch.isfinite(X).all()
+        outs[tag] = (X.cpu().numpy(), m.cache.get_event_stats(), _lib.load().ffd_launch_count() - n0)
+    L = ECG["max_len"]
+    assert outs["never"][1]["tokens_recomputed"] == (n - 1) * 6          # tokens 0..K only
+    assert outs["always"][1]["tokens_recomputed"] == (n - 1) * L
+    assert (n - 1) * 6 < outs["mixed"][1]["tokens_recomputed"] < (n - 1) * L
+    # the reference's index schedule with the same K never refreshes in 12 steps: "never" differs from it only in
+    # tokens 0..K being re-projected from sample 0's current rows
+    s = F.DiffusionSampler(m, B, use_cache=True, noise="philox", cache_kwargs=dict(K=5, R=10))
+    m.noise_scheduler.set_timesteps(1000)
+    m.cache.reset()
+    Xr = s.run_steps(s.sample_prior(B), 0, step_begin=0, step_end=n).cpu().numpy()
+    assert rel(outs["never"][0], Xr) < 0.2 and not np.array_equal(outs["never"][0], Xr)

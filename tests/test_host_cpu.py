@@ -37,14 +37,14 @@ def test_struct_layouts_match_header_sizes():
     import tempfile
 
     _lib = _built_lib()
-    src = '#include "ffd_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu\\n",sizeof(ffd_dims),' \
-          'sizeof(ffd_forward_args),sizeof(ffd_step_coef),sizeof(ffd_sample_args));return 0;}'
+    src = '#include "ffd_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",sizeof(ffd_dims),' \
+          'sizeof(ffd_forward_args),sizeof(ffd_step_coef),sizeof(ffd_sample_args),sizeof(ffd_event_args));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o",
                                os.path.join(d, "s")])
         out = subprocess.check_output([os.path.join(d, "s")]).decode().split()
-    got = [ctypes.sizeof(c) for c in (_lib.Dims, _lib.ForwardArgs, _lib.StepCoef, _lib.SampleArgs)]
+    got = [ctypes.sizeof(c) for c in (_lib.Dims, _lib.ForwardArgs, _lib.StepCoef, _lib.SampleArgs, _lib.EventArgs)]
     assert got == [int(v) for v in out]
 
 
