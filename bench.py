@@ -35,6 +35,11 @@ D_FF = 2048
 METRIC = "samples/sec (ECG freq-domain, 1000 steps, E2-CRF)"
 
 
+# the FFN + LayerNorm kernel the library launches for the default model: CTA pairs unless FFD_FFN_CTA2=0
+FFN_KERNEL_NAME = ("ffn_ln_tc2_kernel<80, 72> (cta_group::2 pairs)" if os.environ.get("FFD_FFN_CTA2", "1")[:1] == "1"
+                   else "ffn_ln_tc_kernel<80>")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -354,7 +359,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": bytes_io / Ke, "steps": Ke,
                 "api": "DiffusionSampler.sample(): host prior noise -> H2D -> steps (torch device noise) -> D2H"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "ffn_ln_tc_kernel<80>" if args.precision == "bf16" else "ffn_kernel+add_ln_kernel",
+        "roofline": {"kernel": FFN_KERNEL_NAME if args.precision == "bf16" else "ffn_kernel+add_ln_kernel",
                      "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": pk["src"] + " (burst)",
                      "flops_per_launch": ffn_flops, "ms_per_launch": ffn_ms,

@@ -31,7 +31,7 @@
 #include "ffd_tc_ptx.cuh"
 
 #ifndef FFD_FFN_CTA2_DEFAULT
-#define FFD_FFN_CTA2_DEFAULT 0
+#define FFD_FFN_CTA2_DEFAULT 1
 #endif
 
 namespace ffd {
@@ -982,6 +982,12 @@ int tc_pack_weights(const ffd_dims& m, const float* weights, void* packed, cudaS
 
 extern long long* g_attn_dbg;  // optional clock64 stamp buffer (ffd_debug_set_attn_stamps)
 
+// LayerNorm eps; FFD_FFN_RAW=1 (debug) makes both kernels store the pre-LayerNorm values instead
+static float ffn_eps() {
+  static const float eps = getenv("FFD_FFN_RAW") ? -1.f : 1e-5f;
+  return eps;
+}
+
 template <int DP>
 static int launch_ffn_tc(const ffd_dims& m, const uint8_t* img, const float* w, const Arena& ar, const float* x,
                          float* y, int64_t M, cudaStream_t s) {
@@ -1001,7 +1007,7 @@ static int launch_ffn_tc(const ffd_dims& m, const uint8_t* img, const float* w, 
   const uint8_t* w2img = img + (size_t)n_chunks * sm.w1_bytes;
   tc::ffn_ln_tc_kernel<DP><<<grid, tc::NUM_THREADS, sm.total, s>>>(x, y, w1img, w2img, w + ar.b2, w + ar.n2w,
                                                                     w + ar.n2b, M, m.d_model, n_chunks, n_pairs,
-                                                                    getenv("FFD_FFN_RAW") ? -1.f : 1e-5f, g_attn_dbg);
+                                                                    ffn_eps(), g_attn_dbg);
   FFD_CHECK_LAUNCH("ffn_ln_tc_kernel");
   return FFD_OK;
 }
@@ -1041,7 +1047,7 @@ static int launch_ffn_tc2(const ffd_dims& m, const uint8_t* himg, const float* w
   const uint8_t* w1h = himg;
   const uint8_t* w2h = himg + (size_t)n_chunks * 2 * sm.w1_bytes;
   tc::ffn_ln_tc2_kernel<DP, D><<<grid, tc::NUM_THREADS, sm.total, s>>>(x, y, w1h, w2h, w + ar.b2, w + ar.n2w, w + ar.n2b,
-                                                                     M, m.d_model, n_chunks, n_pairs, getenv("FFD_FFN_RAW") ? -1.f : 1e-5f,
+                                                                     M, m.d_model, n_chunks, n_pairs, ffn_eps(),
                                                                      g_attn_dbg);
   FFD_CHECK_LAUNCH("ffn_ln_tc2_kernel");
   return FFD_OK;

@@ -58,8 +58,8 @@ def test_event_decide_kernel_against_oracle(L, d, Cc, accumulate):
     for step in range(12):
         x0 = (rng.normal(size=(L, Cc)) * rng.uniform(0.2, 3.0, size=(L, 1))).astype(np.float32)
         first = step == 0
-        _lib.check(lib.ffd_event_decide(C.byref(e), _lib.ptr(torch.from_numpy(z).cuda()),
-                                        _lib.ptr(torch.from_numpy(x0).cuda()), L, d, Cc, step, int(first), st_h))
+        zd, xd = torch.from_numpy(z).cuda(), torch.from_numpy(x0).cuda()  # kept alive across the async launch
+        _lib.check(lib.ffd_event_decide(C.byref(e), _lib.ptr(zd), _lib.ptr(xd), L, d, Cc, step, int(first), st_h))
         O.event_decide(cfg, st, z, x0, step, first)
         torch.cuda.synchronize()
         assert np.array_equal(bufs["z_prev"].cpu().numpy(), z)
@@ -103,9 +103,10 @@ def test_event_refresh_kv_kernel_against_oracle(dims):
     w[rng.uniform(size=L) < 0.3] = 1.0
     w[(rng.uniform(size=L) < 0.3) & (w == 0)] = 0.07
     kc, vc = torch.from_numpy(k0).cuda(), torch.from_numpy(v0).cuda()
-    _lib.check(lib.ffd_event_refresh_kv(dm, _lib.ptr(torch.from_numpy(arena).cuda()), layer,
-                                        _lib.ptr(torch.from_numpy(h0).cuda()), _lib.ptr(torch.from_numpy(w).cuda()),
-                                        _lib.ptr(kc), _lib.ptr(vc), _lib.stream_handle()))
+    ad, hd_, wd = torch.from_numpy(arena).cuda(), torch.from_numpy(h0).cuda(), torch.from_numpy(w).cuda()
+    _lib.check(lib.ffd_event_refresh_kv(dm, _lib.ptr(ad), layer, _lib.ptr(hd_), _lib.ptr(wd), _lib.ptr(kc),
+                                        _lib.ptr(vc), _lib.stream_handle()))
+    torch.cuda.synchronize()
     O.event_refresh_kv(lw, h0.astype(np.float64), w.astype(np.float64), store, layer, H)
     assert rel(kc.cpu().numpy(), store.k) < 2e-6 and rel(vc.cpu().numpy(), store.v) < 2e-6
     # reused tokens and the other layers are untouched, bit for bit
@@ -187,7 +188,7 @@ def test_event_driven_is_one_launch_loop_without_host_sync():
     m = build_seeded_model(ECG, 42, precision="bf16").to("cuda").eval()
     B, n = 64, 12
     outs = {}
-    for tag, tau0 in (("never", 1e30), ("always", 0.0), ("mixed", 2e3)):
+    for tag, tau0 in (("never", 1e30), ("always", 0.0), ("mixed", 1.0)):
         s = F.DiffusionSampler(m, B, use_cache=True, noise="philox",
                                cache_kwargs=dict(K=5, R=1000, tau_0=tau0, tau_warn=1e30, event_driven=True))
         m.noise_scheduler.set_timesteps(1000)
