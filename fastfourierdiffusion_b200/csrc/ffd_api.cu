@@ -45,10 +45,15 @@ static int run_layer(const ffd_forward_args& a, const Arena& ar, const Workspace
       return rc;
     return tc_ffn_ln(m, a.packed, a.weights, layer, ws.h, ws.h, M, s);
   }
-  if (branch == 0 && a.precision == FFD_PREC_BF16 && tc_attn_supported(m)) {
+  if ((branch == 0 || branch == 2) && a.precision == FFD_PREC_BF16 && tc_attn_supported(m)) {
     // stock attention (all K/V own) on the same tensor-core kernel: K/V projection + per-sample operand images
     // (one tcgen05 kernel; fp32 projection + pack kernel for head dims > 7), attention block, FFN block.  Q is
-    // projected inside the attention kernel.
+    // projected inside the attention kernel.  Mixed branch (2): the same, with the key rows outside the recompute
+    // set patched in from the shared sample-0 images, and sample 0's recomputed rows (projected in fp32 from the
+    // layer INPUT, cached_transformer.py:282-304) stored afterwards.
+    if (branch == 2 && (rc = launch_linear(ws.h, d, w + ar.in_w + (int64_t)d * d, d, w + ar.in_b + d, ws.kvtmp, 2 * d,
+                                           L, 2 * d, d, 0, s)))
+      return rc;
     const float* kv_src = nullptr;
     if (!tc_attn_own_fused(m)) {
       if ((rc = launch_linear(ws.h, d, w + ar.in_w + (int64_t)d * d, d, w + ar.in_b + d, ws.qkv + d, 3 * d, M, 2 * d,
@@ -57,7 +62,9 @@ static int run_layer(const ffd_forward_args& a, const Arena& ar, const Workspace
       kv_src = ws.qkv;
     }
     if ((rc = tc_attn_own(m, tc_attn_image(m, a.packed, layer), ws.kvimg_own, kv_src, 3 * d, d, 2 * d, a.weights,
-                          layer, ws.h, ws.h, M, s)))
+                          layer, ws.h, ws.h, M, s, branch == 2 ? ws.kvimg : nullptr, a.n_own, a.own_mask)))
+      return rc;
+    if (branch == 2 && (rc = launch_scatter_kv(ws.kvtmp, 2 * d, 0, d, a.own_mask, a.n_own, kc, vc, L, H, hd, s)))
       return rc;
     return tc_ffn_ln(m, a.packed, a.weights, layer, ws.h, ws.h, M, s);
   }
@@ -111,7 +118,7 @@ static int forward_hidden(const ffd_forward_args& a, const Arena& ar, const Work
     return rc;
   int populate = 0;
   const int branch = pick_branch(a, &populate);
-  const bool tc_images = branch == 1 && a.precision == FFD_PREC_BF16 && tc_attn_supported(m);
+  const bool tc_images = (branch == 1 || branch == 2) && a.precision == FFD_PREC_BF16 && tc_attn_supported(m);
   const bool event_refresh = ev && branch == 1;
   if (tc_images && !event_refresh) {
     // the fp32 cache is the source of truth (it may have been reset or refreshed since the last

@@ -81,7 +81,10 @@ int tc_attn_cached(const ffd_dims& m, const void* attn_img, const void* kvimg, c
 // tc_attn_own_fused(m)) the K/V projection runs on the tensor cores inside the image build, straight from x.
 int64_t tc_kv_own_image_bytes(const ffd_dims& m, int64_t B);
 bool tc_attn_own_fused(const ffd_dims& m);
+// kvimg_shared != nullptr (mixed branch): only the tokens of the recompute set (prefix [0, n_prefix) or own_mask)
+// keep their own K/V rows, every other key row is taken from the shared sample-0 images (tc_pack_kv) of `layer`.
 int tc_attn_own(const ffd_dims& m, const void* attn_img, void* kvimg_own, const float* kv_src, int ld, int k_off,
-                int v_off, const float* weights, int layer, const float* x, float* y, int64_t M, cudaStream_t s);
+                int v_off, const float* weights, int layer, const float* x, float* y, int64_t M, cudaStream_t s,
+                const void* kvimg_shared = nullptr, int n_prefix = 0, const int32_t* own_mask = nullptr);
 
 }  // namespace ffd

@@ -1052,6 +1052,40 @@ __global__ void pack_kv_kernel(const float* __restrict__ kc, const float* __rest
   }
 }
 
+// Mixed branch (cached_transformer.py:259-305): a sample's own K/V rows only for the tokens of the recompute set S
+// (prefix [0, n_prefix) or mask); every other key row of the per-sample images is replaced by the row of the shared
+// sample-0 images of this layer.  One thread per 16-byte core-matrix row: a K-image row belongs to one key, a
+// V-image row holds 8 consecutive keys of one dim.
+__global__ void patch_kv_own_kernel(uint4* __restrict__ own, const uint4* __restrict__ shared_layer, int64_t B, int NV,
+                                    int NCH, int CK, int L, int n_prefix, const int32_t* __restrict__ mask) {
+  const int units = 4 * CK;
+  const int64_t total = B * NV * units;
+  auto in_set = [&](int key) { return key < L && (mask ? mask[key] != 0 : key < n_prefix); };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int u = (int)(i % units);
+    const int hc = (int)((i / units) % NV);
+    const int ch = hc % NCH;
+    const uint4 sh = shared_layer[(int64_t)hc * units + u];
+    if (u < 2 * CK) {
+      if (!in_set(ch * CK + u % CK)) own[i] = sh;
+    } else {
+      const int key0 = ch * CK + ((u - 2 * CK) / 16) * 8;
+      uint4 o = own[i];
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+      const uint32_t* sw = reinterpret_cast<const uint32_t*>(&sh);
+      bool changed = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool k0 = in_set(key0 + 2 * j), k1 = in_set(key0 + 2 * j + 1);
+        const uint32_t v = (k0 ? ow[j] : sw[j]) & 0xFFFFu, w = (k1 ? ow[j] : sw[j]) & 0xFFFF0000u;
+        changed |= !k0 || !k1;
+        ow[j] = v | w;
+      }
+      if (changed) own[i] = o;
+    }
+  }
+}
+
 // The same images for every sample's OWN keys (stock attention): K/V rows come from the projected tokens
 // src[(b L + key) * ld + k_off / v_off + h hd + dim].  One thread writes one 16-byte core-matrix row.
 __global__ void pack_kv_own_kernel(const float* __restrict__ src, int ld, int k_off, int v_off,
@@ -1262,7 +1296,8 @@ static int launch_kv_own(const ffd_dims& m, const AttnGeom& g, const uint8_t* wk
 bool tc_attn_own_fused(const ffd_dims& m) { return kvproj_fused(m); }
 
 int tc_attn_own(const ffd_dims& m, const void* attn_img, void* kvimg_own, const float* kv_src, int ld, int k_off,
-                int v_off, const float* weights, int layer, const float* x, float* y, int64_t M, cudaStream_t s) {
+                int v_off, const float* weights, int layer, const float* x, float* y, int64_t M, cudaStream_t s,
+                const void* kvimg_shared, int n_prefix, const int32_t* own_mask) {
   const Arena ar = arena_of(m);
   const AttnGeom g = attn_geom(m);
   const float* w = weights + ar.layer0 + (int64_t)layer * ar.layer_stride;
@@ -1284,6 +1319,12 @@ int tc_attn_own(const ffd_dims& m, const void* attn_img, void* kvimg_own, const 
     tc::pack_kv_own_kernel<<<148 * 16, 256, 0, s>>>(kv_src, ld, k_off, v_off, (uint4*)kvimg_own, B, m.max_len, g.hd,
                                                      m.n_head, g.G, g.NCH, g.CK);
     FFD_CHECK_LAUNCH("pack_kv_own_kernel");
+  }
+  if (kvimg_shared) {
+    const uint8_t* kvl = (const uint8_t*)kvimg_shared + (size_t)layer * g.NV * 2 * g.CK * tc::HP * 2;
+    tc::patch_kv_own_kernel<<<148 * 16, 256, 0, s>>>((uint4*)kvimg_own, (const uint4*)kvl, B, g.NV, g.NCH, g.CK,
+                                                      m.max_len, n_prefix, own_mask);
+    FFD_CHECK_LAUNCH("patch_kv_own_kernel");
   }
   return attn_dispatch(m, g, (const uint8_t*)attn_img, (const uint8_t*)kvimg_own, w, ar, x, y, M, 1, s);
 }

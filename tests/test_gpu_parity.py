@@ -280,11 +280,56 @@ def test_ecg_default_model_cached_trace(prec):
     tol = 1e-4 if prec == "fp32" else 5e-2
     assert rel(c.k_cache_tensor[[0, 9]].cpu().numpy(), g["k_cache"]) < tol
     assert rel(c.v_cache_tensor[[0, 9]].cpu().numpy(), g["v_cache"]) < tol
-    assert rel(c.crf_cache[[0, 9]].cpu().numpy(), g["crf"]) < tol
+    crf = c.crf_cache[[0, 9]].cpu().numpy()
+    if prec == "fp32":
+        assert rel(crf, g["crf"]) < tol
+    else:
+        # The CRF kept at the end is the one of the mixed step 100, where the random-init reverse SDE has driven
+        # |X| to ~470: un-normalised layer-0 scores are in the hundreds, the softmax is nearly
+        # one-hot, and bf16 operands flip the winning key for a few tokens (O(1) row errors at layer 0, damped by
+        # the later LayerNorms).  So: the bulk of the rows at bf16 accuracy, the outliers bounded.
+        err = np.abs(crf - g["crf"]).max(axis=-1) / np.abs(g["crf"]).max()
+        assert np.percentile(err, 90) < 1e-2 and err.max() < 0.5, (np.percentile(err, 90), err.max())
     st = c.get_cache_stats()
     ref = dict(zip(g["stats_keys"], g["stats_vals"]))
     for k in ref:
         assert st[k] == pytest.approx(ref[k], rel=1e-12), k
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_ecg_mixed_branch_well_conditioned(prec):
+    """The mixed branch (cached_transformer.py:259-305) of the default model at prior-sized inputs (|X| ~ 1, where
+    bf16 arithmetic is well conditioned): prefix and non-prefix recompute sets against the oracle, score / CRF /
+    stored K/V rows.  In bf16 mode this is the tensor-core path: per-sample K/V images with the rows outside the
+    set patched in from the shared sample-0 images."""
+    import fastfourierdiffusion_b200 as F
+
+    m = build_seeded_model(ECG, 42, precision=prec)
+    _skip_unless(prec, m)
+    sd = {k: v.detach().numpy().copy() for k, v in m.state_dict().items()}
+    m = m.to("cuda").eval()
+    L = ECG["max_len"]
+    rng = np.random.default_rng(11)
+    B = 3
+    m.enable_caching(K=5, R=10)
+    m.cache.reset()
+    om = O.OracleScoreModel(O.ModelWeights.from_state_dict(sd, ECG["n_head"]), L, ECG["n_channels"])
+    store = O.KVStore(ECG["num_layers"], L)
+    tol = TOL[prec]["score"]
+    sets = [set(range(L)), set(range(10)), {3, 50, 186}, set(), set(range(0, L, 2))]
+    for i, S in enumerate(sets):
+        X = rng.normal(size=(B, L, 1)).astype(np.float32)
+        t = 0.9 - 0.1 * i
+        ts = torch.full((B,), t, dtype=torch.float32, device="cuda")
+        m.cache.current_step = i
+        score, crf = m(F.DiffusableBatch(X=torch.from_numpy(X).cuda(), timesteps=ts), recompute_tokens=S, step=i,
+                       return_crf=True)
+        want_s, want_c = om.forward_cached(X, t, sorted(S), store)
+        assert rel(score.cpu().numpy(), want_s) < tol, (i, "score")
+        assert rel(crf.cpu().numpy(), want_c) < tol, (i, "crf")
+        own = m._kv_owner
+        assert rel(own._k_store.cpu().numpy(), store.k) < tol, (i, "k")
+        assert rel(own._v_store.cpu().numpy(), store.v) < tol, (i, "v")
 
 
 @pytest.mark.parametrize("prec", PRECS)
