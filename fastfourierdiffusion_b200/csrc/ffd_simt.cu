@@ -24,31 +24,43 @@ __global__ void embed_kernel(const float* __restrict__ X, const float* __restric
   h[idx] = ((acc + be[j]) + pos[(int64_t)l * d + j]) + te[j];
 }
 
-// float4 variant (d % 4 == 0): one 16-byte store per thread, fully coalesced -- the kernel is a pure HBM write
+// float4 variant (d % 4 == 0): a pure HBM write.  One block writes EMB_ROWS consecutive token rows (a contiguous span
+// of the output) as 16-byte stores, several per thread in flight, with 32-bit index arithmetic only.
+constexpr int EMB_ROWS = 128;
 __global__ void __launch_bounds__(256)
 embed4_kernel(const float* __restrict__ X, const float* __restrict__ We, const float* __restrict__ be,
               const float* __restrict__ pos, const float* __restrict__ te, float4* __restrict__ h, int64_t M, int L,
               int C, int d4) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * d4) return;
-  const int64_t m = idx / d4;
-  const int j = (int)(idx - m * d4) * 4;
-  const int l = (int)(m % L);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int c = 0; c < C; ++c) {
-    const float xv = __ldg(X + m * C + c);
+  const int64_t m0 = (int64_t)blockIdx.x * EMB_ROWS;
+  const int rows = M - m0 < EMB_ROWS ? (int)(M - m0) : EMB_ROWS;
+  const int l0 = (int)(m0 % L);
+  const int n = rows * d4;
+  float4* out = h + m0 * d4;
+  const float* x0 = X + m0 * C;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int r = i / d4;
+    const int j = (i - r * d4) * 4;
+    int l = l0 + r;
+    l -= l >= L ? L : 0;
+    l -= l >= L ? L : 0;  // EMB_ROWS may exceed L
+    while (l >= L) l -= L;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) {
+      const float xv = __ldg(x0 + r * C + c);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[e] = fmaf(xv, __ldg(We + (j + e) * C + c), acc[e]);
+      for (int e = 0; e < 4; ++e) acc[e] = fmaf(xv, __ldg(We + (j + e) * C + c), acc[e]);
+    }
+    const float4 b4 = *reinterpret_cast<const float4*>(be + j);
+    const float4 p4 = *reinterpret_cast<const float4*>(pos + l * (d4 * 4) + j);
+    const float4 t4 = *reinterpret_cast<const float4*>(te + j);
+    float4 o;
+    o.x = ((acc[0] + b4.x) + p4.x) + t4.x;
+    o.y = ((acc[1] + b4.y) + p4.y) + t4.y;
+    o.z = ((acc[2] + b4.z) + p4.z) + t4.z;
+    o.w = ((acc[3] + b4.w) + p4.w) + t4.w;
+    __stcs(out + i, o);  // streaming store: the first attention block reads it from HBM anyway (882 MB >> L2)
   }
-  const float4 b4 = *reinterpret_cast<const float4*>(be + j);
-  const float4 p4 = *reinterpret_cast<const float4*>(pos + (int64_t)l * (d4 * 4) + j);
-  const float4 t4 = *reinterpret_cast<const float4*>(te + j);
-  float4 o;
-  o.x = ((acc[0] + b4.x) + p4.x) + t4.x;
-  o.y = ((acc[1] + b4.y) + p4.y) + t4.y;
-  o.z = ((acc[2] + b4.z) + p4.z) + t4.z;
-  o.w = ((acc[3] + b4.w) + p4.w) + t4.w;
-  h[idx] = o;
 }
 
 int launch_embed(const float* X, const float* We, const float* be, const float* pos, const float* te, float* h,
@@ -56,8 +68,8 @@ int launch_embed(const float* X, const float* We, const float* be, const float* 
   const bool aligned = d % 4 == 0 && ((uintptr_t)be % 16 == 0) && ((uintptr_t)pos % 16 == 0) &&
                        ((uintptr_t)te % 16 == 0) && ((uintptr_t)h % 16 == 0);
   if (aligned) {
-    const int64_t n = M * (d / 4);
-    embed4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(X, We, be, pos, te, (float4*)h, M, L, C, d / 4);
+    embed4_kernel<<<(unsigned)((M + EMB_ROWS - 1) / EMB_ROWS), 256, 0, s>>>(X, We, be, pos, te, (float4*)h, M, L, C,
+                                                                              d / 4);
     FFD_CHECK_LAUNCH("embed4_kernel");
     return FFD_OK;
   }
@@ -476,11 +488,22 @@ unembed_step_tiled_kernel(const float* __restrict__ h, const float* __restrict__
   const int rows = (int)((M - row0 < UT) ? (M - row0) : UT);
   const int d4 = d / 4;
   const float4* src = reinterpret_cast<const float4*>(h + row0 * d);
-  for (int i = threadIdx.x; i < rows * d4; i += UT) {
-    const float4 v = __ldg(src + i);
-    const int r = i / d4, c = (i - r * d4) * 4;
-    float* dst = hs + r * (d + 1) + c;
-    dst[0] = v.x, dst[1] = v.y, dst[2] = v.z, dst[3] = v.w;
+  // six 16-byte loads per thread in flight before the first shared-memory store (the kernel is a pure HBM read)
+  const int n4 = rows * d4;
+  for (int i0 = threadIdx.x; i0 < n4; i0 += 6 * UT) {
+    float4 v[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u)
+      if (i0 + u * UT < n4) v[u] = __ldcs(src + i0 + u * UT);
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const int i = i0 + u * UT;
+      if (i < n4) {
+        const int r = i / d4, c = (i - r * d4) * 4;
+        float* dst = hs + r * (d + 1) + c;
+        dst[0] = v[u].x, dst[1] = v[u].y, dst[2] = v[u].z, dst[3] = v[u].w;
+      }
+    }
   }
   for (int i = threadIdx.x; i < C * d; i += UT) ws[i] = Wu[i];
   __syncthreads();
