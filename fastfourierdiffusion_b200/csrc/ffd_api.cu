@@ -189,12 +189,15 @@ static int check_forward(const ffd_forward_args& a) {
 
 namespace ffd {
 extern long long* g_attn_dbg;
+void tc_debug_set_ffn_pairs(int mode);
 }
 using namespace ffd;
 
 extern "C" {
 
 void ffd_debug_set_attn_stamps(long long* dev_buf) { ffd::g_attn_dbg = dev_buf; }
+// test / A-B hook (not part of the ABI header): 1 = FFN on CTA pairs, 0 = one-CTA kernel, -1 = FFD_FFN_CTA2 / default
+void ffd_debug_set_ffn_pairs(int mode) { ffd::tc_debug_set_ffn_pairs(mode); }
 int ffd_version(void) { return 1; }
 uint64_t ffd_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 const char* ffd_last_error(void) { return g_err; }

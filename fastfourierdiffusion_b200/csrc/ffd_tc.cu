@@ -1053,13 +1053,15 @@ static int launch_ffn_tc2(const ffd_dims& m, const uint8_t* himg, const float* w
   return FFD_OK;
 }
 
+static int g_ffn_pairs_mode = -1;  // -1 unknown (FFD_FFN_CTA2 or the default), 0 off, 1 on
+void tc_debug_set_ffn_pairs(int mode) { g_ffn_pairs_mode = mode; }
+
 static bool ffn_use_pairs(const ffd_dims& m) {
-  static int mode = -1;  // -1 unknown, 0 off, 1 on
-  if (mode < 0) {
+  if (g_ffn_pairs_mode < 0) {
     const char* e = getenv("FFD_FFN_CTA2");
-    mode = e ? (e[0] == '1') : FFD_FFN_CTA2_DEFAULT;
+    g_ffn_pairs_mode = e ? (e[0] == '1') : FFD_FFN_CTA2_DEFAULT;
   }
-  return mode == 1 && m.d_model == 72;  // the default model (the pair kernel is instantiated for it)
+  return g_ffn_pairs_mode == 1 && m.d_model == 72;  // the default model (the pair kernel is instantiated for it)
 }
 
 int tc_ffn_ln(const ffd_dims& m, const void* packed, const float* weights, int layer, const float* x, float* y,

@@ -125,3 +125,32 @@ def test_attn_cached_ln_fp32_and_tensor_path(which, B):
                                                1e-5).view(B * L, d)
     assert torch.isfinite(y2).all()
     assert float((y2.double() - want2).abs().mean() / want2.abs().mean()) < 3e-2
+
+
+@pytest.mark.parametrize("M", [1, 129, 511, 513, 148 * 256 - 5, 148 * 256 * 2 + 300, 148 * 256 * 5 + 77])
+def test_ffn_cta_pair_kernel_equals_one_cta_kernel(M):
+    """The cta_group::2 kernel (default for d_model 72) against the one-CTA kernel, same inputs: bit-identical for
+    every row count -- ragged last tiles, clusters with an empty second CTA, several tile-pair iterations per
+    cluster (a miscompiled X staging once dropped the bias-low column from the second iteration on)."""
+    from fastfourierdiffusion_b200 import _lib
+
+    lib = _lib.load()
+    if not lib.ffd_has_tensor_path():
+        pytest.skip("tensor path not available")
+    model = build_seeded_model(ECG, 42, precision="bf16").to("cuda").eval()
+    torch.manual_seed(M)
+    x = torch.randn(M, model.d_model, device="cuda") * 1.3
+    try:
+        lib.ffd_debug_set_ffn_pairs(0)
+        one = _run(model, 3, x, "bf16")
+        lib.ffd_debug_set_ffn_pairs(1)
+        pair = _run(model, 3, x, "bf16")
+        # identical tiles at different iterations of the persistent loop give identical rows
+        if M >= 148 * 256 * 2:
+            xx = torch.cat([x[:148 * 256], x[:148 * 256], x[:M - 2 * 148 * 256]]).contiguous()
+            yy = _run(model, 3, xx, "bf16")
+            assert torch.equal(yy[:148 * 256], yy[148 * 256:2 * 148 * 256])
+    finally:
+        lib.ffd_debug_set_ffn_pairs(-1)
+    assert torch.equal(one, pair)
+    assert rel(pair.cpu().numpy(), _ffn_ref(model, 3, x).cpu().numpy()) < 1e-2
