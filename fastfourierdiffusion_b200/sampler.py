@@ -79,6 +79,32 @@ class DiffusionSampler:
     # -- the loop ---------------------------------------------------------------------------
     def sample(self, num_samples: int, num_diffusion_steps: Optional[int] = None) -> torch.Tensor:
         """sampler.py:105-215: returns a CPU fp32 tensor [floor(N/bs)*bs, L, C] (one batch of N if N < bs)."""
+        return self._sample(num_samples, num_diffusion_steps, None)
+
+    def sample_time_domain(self, num_samples: int, num_diffusion_steps: Optional[int] = None,
+                           feature_std: Optional[torch.Tensor] = None,
+                           feature_mean: Optional[torch.Tensor] = None,
+                           fourier_transform: Optional[bool] = None) -> torch.Tensor:
+        """``sample`` followed by the tail of cmd/sample.py:107-113 (de-standardise ``X * std + mean``, then ``idft``
+        for a frequency-domain model) ON THE DEVICE, per batch, before the copy to the host: only time-domain
+        samples cross PCIe.  Same values as ``idft(sample(...), std, mean)``.
+        ``fourier_transform`` (cfg.fourier_transform of cmd/sample.py) defaults to the model's ``scale_noise``."""
+        from .fourier import idft
+
+        freq = bool(self.score_model.scale_noise) if fourier_transform is None else bool(fourier_transform)
+
+        def tail(X: torch.Tensor) -> torch.Tensor:
+            if freq:
+                return idft(X, feature_std, feature_mean)
+            if feature_std is not None:
+                X = X * feature_std.to(X.device)
+            if feature_mean is not None:
+                X = X + feature_mean.to(X.device)
+            return X
+
+        return self._sample(num_samples, num_diffusion_steps, tail)
+
+    def _sample(self, num_samples: int, num_diffusion_steps: Optional[int], tail) -> torch.Tensor:
         if num_diffusion_steps is not None:
             self._num_diffusion_steps = num_diffusion_steps
         model = self.score_model
@@ -100,6 +126,8 @@ class DiffusionSampler:
                 else:
                     X = self.run_steps(X, global_step, batch_idx=batch_idx)
                 global_step += n_steps
+                if tail is not None:
+                    X = tail(X)
                 all_samples.append(X.cpu())
         return torch.cat(all_samples, dim=0)
 

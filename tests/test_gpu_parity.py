@@ -682,3 +682,26 @@ def test_metric_collection_against_oracle():
     assert abs(res["time_sliced_wasserstein_mean"] - want_t["sliced_wasserstein_mean"]) < 1e-4
     assert abs(res["freq_sliced_wasserstein_mean"] - want_f["sliced_wasserstein_mean"]) < 1e-4
     assert abs(res["spectral_marginal_wasserstein_mean"] - want_s["marginal_wasserstein_mean"]) < 2e-4
+
+
+def test_sample_time_domain_equals_idft_of_sample():
+    """sample_time_domain = sample() + the de-standardise / idft tail of cmd/sample.py:107-113 on the device."""
+    import fastfourierdiffusion_b200 as F
+
+    m = build_tiny_model()
+    L, Cc = TINY["max_len"], TINY["n_channels"]
+    rng = np.random.default_rng(2)
+    std = torch.from_numpy(rng.uniform(0.5, 2.0, size=(L, Cc)).astype(np.float32))
+    mean = torch.from_numpy(rng.normal(size=(L, Cc)).astype(np.float32))
+    outs = []
+    for fn in ("sample", "sample_time_domain"):
+        s = F.DiffusionSampler(m, 4, use_cache=True, cache_kwargs=dict(K=2, R=100), noise="philox", seed=9)
+        if fn == "sample":
+            outs.append(F.idft(s.sample(8, 12), std, mean))
+        else:
+            outs.append(s.sample_time_domain(8, 12, std, mean))
+    assert outs[0].shape == outs[1].shape == (8, L, Cc) and outs[1].device.type == "cpu"
+    assert torch.equal(outs[0], outs[1])
+    want = O.idft(F.DiffusionSampler(m, 4, use_cache=True, cache_kwargs=dict(K=2, R=100), noise="philox",
+                                     seed=9).sample(8, 12).numpy().astype(np.float64) * std.numpy() + mean.numpy())
+    assert rel(outs[1].numpy(), want) < 2e-5
