@@ -40,6 +40,28 @@ FFN_KERNEL_NAME = ("ffn_ln_tc2_kernel<80, 72> (cta_group::2 pairs)" if os.enviro
                    else "ffn_ln_tc_kernel<80>")
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that lands on fd 1 (NCCL prints its version banner there,
+    torch.distributed.run its warnings) is sent to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -164,7 +186,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -390,7 +412,7 @@ def run_ours(args):
         "roofline_other": [attn_entry] if attn_entry else [],
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -407,6 +429,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
