@@ -87,20 +87,54 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.rows = []
+        self.source = "nvml"
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
 
+    def _nvml_handle(self):
+        """In-process NVML (no nvidia-smi process per sample: spawning one initialises every GPU of the box and was
+        measurably perturbing multi-GPU runs).  The device is matched by UUID, falling back to the index."""
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            return None, None
+
+    def _sample_nvml(self, nv, h):
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+        return [str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits]
+
     def _run(self):
+        nv, h = self._nvml_handle()
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) == 6:
-                    self.rows.append(parts)
+                if nv is not None:
+                    self.rows.append(self._sample_nvml(nv, h))
+                else:
+                    self.source = "nvidia-smi"
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                         timeout=5).stdout
+                    parts = [p.strip() for p in out.strip().split(",")]
+                    if len(parts) == 6:
+                        self.rows.append(parts)
             except Exception:
-                pass
-            self._stop.wait(0.2)
+                nv = None  # fall back to nvidia-smi
+                self.source = "nvidia-smi"
+            self._stop.wait(0.1 if nv is not None else 0.2)
 
     def __enter__(self):
         self._t.start()
@@ -117,7 +151,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": self.source}
 
 
 def build_model(precision: str):
