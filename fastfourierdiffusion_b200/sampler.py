@@ -154,6 +154,9 @@ class DiffusionSampler:
         dev = model.device
         X = X.to(device=dev, dtype=torch.float32).contiguous()
         cache = model.cache if (self.use_cache and model.cache is not None) else None
+        if cache is not None and getattr(cache, "event_driven", False):
+            raise NotImplementedError("the device-decided event schedule (event_driven=True) runs inside the fused "
+                                      "step loop (ffd_sample_steps); it is not available together with use_fresca")
         for step_idx, t in enumerate(self.noise_scheduler.timesteps.tolist()):
             timesteps = torch.full((X.shape[0],), t, dtype=torch.float32, device=dev)
             batch = DiffusableBatch(X=X, y=None, timesteps=timesteps)

@@ -155,3 +155,24 @@ def test_cli_overrides_and_checkpoint_lookup(tmp_path):
         (d / name).write_bytes(b"")
     assert find_checkpoint(str(tmp_path), "abc").endswith("epoch=9-val_loss=0.31.ckpt")
     assert find_checkpoint(str(tmp_path), None) is None
+
+
+def test_event_driven_cache_kwargs_and_schedule():
+    """event_driven is an extra, default-off constructor argument: the index schedule is untouched without it, only
+    the full step stays host-scheduled with it, and R must be positive."""
+    import pytest
+    import torch
+
+    from fastfourierdiffusion_b200.caching import E2CRFCache
+
+    c = E2CRFCache(num_layers=2, max_len=16, device=torch.device("cpu"), K=3, R=10)
+    assert not c.event_driven and c.determine_recompute_set(None, 0.1, 500) == set(range(6))
+    e = E2CRFCache(num_layers=2, max_len=16, device=torch.device("cpu"), K=3, R=10, event_driven=True,
+                   event_probe_ratio=0.1, event_seed=5)
+    assert e.determine_recompute_set(None, 0.1, 0) == set(range(16))
+    assert e.determine_recompute_set(None, 0.1, 500) == set() and e.determine_recompute_set(None, 0.1, 7) == set()
+    assert e.get_event_stats() == {}
+    with pytest.raises(ValueError):
+        E2CRFCache(num_layers=2, max_len=16, device=torch.device("cpu"), R=0, event_driven=True)
+    with pytest.raises(TypeError):
+        E2CRFCache(num_layers=2, max_len=16, device=torch.device("cpu"), not_an_argument=1)
