@@ -154,3 +154,25 @@ def test_ffn_cta_pair_kernel_equals_one_cta_kernel(M):
         lib.ffd_debug_set_ffn_pairs(-1)
     assert torch.equal(one, pair)
     assert rel(pair.cpu().numpy(), _ffn_ref(model, 3, x).cpu().numpy()) < 1e-2
+
+
+@pytest.mark.parametrize("dims", [TINY, dict(max_len=24, n_channels=2, d_model=60, num_layers=2, n_head=12),
+                                  dict(max_len=24, n_channels=2, d_model=40, num_layers=1, n_head=8), ECG])
+def test_ffn_rows_do_not_depend_on_the_loop_iteration(dims):
+    """The persistent FFN kernels (every d_model / DP instantiation) give bit-identical rows for identical tiles
+    whichever iteration of a CTA's tile-pair loop processes them."""
+    from fastfourierdiffusion_b200 import _lib
+
+    if not _lib.load().ffd_has_tensor_path():
+        pytest.skip("tensor path not available")
+    model = build_seeded_model(dims, 7, precision="bf16").to("cuda").eval()
+    if not model._tc_ok():
+        pytest.skip("model shape not supported by the tcgen05 kernels")
+    blk = 148 * 256  # rows one wave of CTAs (two tiles each) covers
+    torch.manual_seed(3)
+    x0 = torch.randn(blk, model.d_model, device="cuda")
+    x = torch.cat([x0, x0, x0, x0[:1000]]).contiguous()
+    y = _run(model, len(model.backbone.layers) - 1, x, "bf16")
+    assert torch.equal(y[:blk], y[blk:2 * blk]) and torch.equal(y[:blk], y[2 * blk:3 * blk])
+    assert torch.equal(y[:1000], y[3 * blk:])
+    assert rel(y[:blk].cpu().numpy(), _ffn_ref(model, len(model.backbone.layers) - 1, x0).cpu().numpy()) < 1e-2
