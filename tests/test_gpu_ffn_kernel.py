@@ -176,3 +176,32 @@ def test_ffn_rows_do_not_depend_on_the_loop_iteration(dims):
     assert torch.equal(y[:blk], y[blk:2 * blk]) and torch.equal(y[:blk], y[2 * blk:3 * blk])
     assert torch.equal(y[:1000], y[3 * blk:])
     assert rel(y[:blk].cpu().numpy(), _ffn_ref(model, len(model.backbone.layers) - 1, x0).cpu().numpy()) < 1e-2
+
+
+def test_attention_rows_do_not_depend_on_the_loop_iteration():
+    """Same property for the pure-cache attention block (rows are independent there: the K/V are the shared cache):
+    identical 128-row tiles handled by different iterations of a CTA's tile loop give bit-identical rows."""
+    from fastfourierdiffusion_b200 import _lib
+
+    lib = _lib.load()
+    if not lib.ffd_has_tensor_path():
+        pytest.skip("tensor path not available")
+    model = build_seeded_model(ECG, 42, precision="bf16").to("cuda").eval()
+    L, d, H = ECG["max_len"], ECG["d_model"], ECG["n_head"]
+    blk = 148 * 128
+    M = (3 * blk + L - 1) // L * L
+    torch.manual_seed(5)
+    x0 = torch.randn(blk, d, device="cuda")
+    x = torch.cat([x0, x0, x0, x0[:M - 3 * blk]]).contiguous()
+    y = torch.empty_like(x)
+    kc = torch.randn(ECG["num_layers"], H, L, d // H, device="cuda")
+    vc = torch.randn_like(kc)
+    arena, packed = model.device_weights()
+    ws = model.workspace(M // L)
+    _lib.check(lib.ffd_attn_cached_ln(model.dims, 1, _lib.ptr(arena), _lib.ptr(packed), 2, _lib.ptr(kc), _lib.ptr(vc),
+                                      _lib.ptr(x), _lib.ptr(y), _lib.ptr(ws), ws.numel() * ws.element_size(), M,
+                                      _lib.stream_handle()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    assert torch.equal(y[:blk], y[blk:2 * blk]) and torch.equal(y[:blk], y[2 * blk:3 * blk])
+    assert torch.equal(y[:M - 3 * blk], y[3 * blk:])
