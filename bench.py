@@ -40,6 +40,8 @@ FFN_KERNEL_NAME = ("ffn_ln_tc2_kernel<80, 72> (cta_group::2 pairs)" if os.enviro
                    else "ffn_ln_tc_kernel<80>")
 
 
+WORKLOAD = ("ECG L=187 C=1 freq-domain, d=72 H=12 NL=10 F=2048 random init (seed 42), VP-SDE 1000-step grid, "
+            "E2-CRF K=5 R=10")
 _REAL_STDOUT = None
 
 
@@ -214,7 +216,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ECG L=187 C=1, d=72 H=12 NL=10 F=2048, VP-SDE, E2-CRF K=5 R=10, CPU torch port",
+        "config": {"workload": WORKLOAD, "arm": "CPU torch port of the reference path (oracle/torch_port.py), fp32",
                    "torch_threads": torch.get_num_threads()},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -422,8 +424,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
-        "config": {"workload": "ECG L=187 C=1 freq-domain, d=72 H=12 NL=10 F=2048 random init (seed 42), VP-SDE "
-                               "1000-step grid, E2-CRF K=5 R=10, Philox noise in-kernel",
+        "config": {"workload": WORKLOAD, "noise": "Philox in-kernel",
                    "batch_per_gpu": B, "global_batch": world * B, "schedule_steps_timed": f"0..{K - 1}",
                    "value_definition": "global_batch / (1000 x mean step time over the timed steps)",
                    "l2": "per-step activations [B*L, 72] fp32 = %.0f MB >> 126 MB L2 (inputs larger than L2)" % (
