@@ -212,12 +212,34 @@ def run_reference(args):
     sd = {k: v for k, v in model.state_dict().items()}
     value, sample, ms = cpu_port_throughput(sd, budget_s=150.0, n_threads=cores, steps=list(range(args.steps)),
                                             warmup=args.warmup)
+    # informational: the same ATen op sequence (stock torch eager, TF32 matmuls) on one GPU of the box -- what the
+    # unmodified reference's operators would reach on this hardware.  Not the arm's value.
+    on_gpu = None
+    try:
+        if torch.cuda.is_available():
+            from oracle.torch_port import TorchPort, time_cached_steps
+
+            gb = 4096
+            torch.set_float32_matmul_precision("high")  # TF32 matmuls, as the reference sets them (cmd/sample.py:24)
+            gp = TorchPort(sd, ECG["max_len"], ECG["n_channels"], ECG["n_head"], device="cuda")
+            time_cached_steps(gp, gb, [0, 1], N_DIFFUSION_STEPS)  # warm-up (cuBLAS handles, allocator)
+            gp.k_cache = gp.v_cache = None
+            tt, _ = time_cached_steps(gp, gb, [0, 1, 2, 3, 4, 5], N_DIFFUSION_STEPS)
+            pure = sum(tt[i] for i in (1, 2, 3, 4, 5)) / 5
+            on_gpu = {"value": gb / (pure * N_DIFFUSION_STEPS), "unit": "samples/s", "batch": gb,
+                      "ms_per_pure_cache_step": pure * 1e3, "ms_full_step": tt[0] * 1e3,
+                      "what": "oracle/torch_port.py (the reference's ATen op sequence) in torch eager on cuda:0, TF32 "
+                              "matmuls as in cmd/sample.py:24"}
+            del gp
+            torch.cuda.empty_cache()
+    except Exception as exc:
+        on_gpu = {"error": str(exc)[:200]}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "arm": "CPU torch port of the reference path (oracle/torch_port.py), fp32",
-                   "torch_threads": torch.get_num_threads()},
+                   "torch_threads": torch.get_num_threads(), "reference_ops_on_gpu": on_gpu},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

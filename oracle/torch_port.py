@@ -22,8 +22,11 @@ import torch.nn.functional as F
 class TorchPort:
     def __init__(self, sd: Dict[str, torch.Tensor], max_len: int, n_channels: int, n_head: int, sde_kind: str = "vp",
                  fourier_noise_scaling: bool = True, beta_min: float = 0.1, beta_max: float = 20.0,
-                 sigma_min: float = 0.01, sigma_max: float = 50.0):
-        self.sd = {k: v.detach().float().cpu() for k, v in sd.items()}
+                 sigma_min: float = 0.01, sigma_max: float = 50.0, device: str = "cpu"):
+        # device="cuda" runs the same ATen op sequence as stock torch eager on the GPU (bench.py reports it next to
+        # the CPU figure as "what the unmodified reference's ops would do on this GPU"); never used by the product
+        self.dev = torch.device(device)
+        self.sd = {k: v.detach().float().to(self.dev) for k, v in sd.items()}
         self.L, self.C, self.H = max_len, n_channels, n_head
         self.d = self.sd["embedder.weight"].shape[0]
         self.NL = sum(1 for k in self.sd if k.endswith("linear1.weight"))
@@ -35,10 +38,10 @@ class TorchPort:
             G[0] *= math.sqrt(2)
             if max_len % 2 == 0:
                 G[max_len // 2] *= math.sqrt(2)
-        self.G = G
+        self.G = G.to(self.dev)
         pos = self.sd["pos_encoder.embedding.weight"].clone()
         for _ in range(3):  # transformer.py:13-15 max-norm renorm
-            torch.embedding_renorm_(pos, torch.arange(max_len), math.sqrt(self.d), 2.0)
+            torch.embedding_renorm_(pos, torch.arange(max_len, device=self.dev), math.sqrt(self.d), 2.0)
         self.pos = pos
         self.k_cache: Optional[torch.Tensor] = None
         self.v_cache: Optional[torch.Tensor] = None
@@ -78,14 +81,14 @@ class TorchPort:
         q = heads(F.linear(x, in_w[:d], in_b[:d]))
         if len(S) == 0:  # :237-258
             if self.k_cache is None:
-                k = v = torch.zeros(B, H, L, hd)
+                k = v = torch.zeros(B, H, L, hd, device=self.dev)
             else:
                 k = self.k_cache[i].unsqueeze(0).expand(B, -1, -1, -1)
                 v = self.v_cache[i].unsqueeze(0).expand(B, -1, -1, -1)
         else:  # :259-305
             S = sorted(S)
-            k = torch.zeros(B, H, L, hd)
-            v = torch.zeros(B, H, L, hd)
+            k = torch.zeros(B, H, L, hd, device=self.dev)
+            v = torch.zeros(B, H, L, hd, device=self.dev)
             rest = [j for j in range(L) if j not in set(S)]
             if rest and self.k_cache is not None:
                 k[:, :, rest] = self.k_cache[i][:, rest].unsqueeze(0)
@@ -99,7 +102,7 @@ class TorchPort:
 
     def _store(self, i: int, idx: List[int], k: torch.Tensor, v: torch.Tensor) -> None:
         if self.k_cache is None:  # caching.py:364-377
-            self.k_cache = torch.zeros(self.NL, self.H, self.L, self.d // self.H)
+            self.k_cache = torch.zeros(self.NL, self.H, self.L, self.d // self.H, device=self.dev)
             self.v_cache = torch.zeros_like(self.k_cache)
         self.k_cache[i][:, idx] = k[0]
         self.v_cache[i][:, idx] = v[0]
@@ -107,7 +110,7 @@ class TorchPort:
     def score(self, X: torch.Tensor, t: float, S: Optional[Sequence[int]]) -> torch.Tensor:
         sd = self.sd
         h = F.linear(X, sd["embedder.weight"], sd["embedder.bias"]) + self.pos
-        proj = torch.tensor(t, dtype=torch.float32) * sd["time_encoder.W"] * 2 * math.pi
+        proj = torch.tensor(t, dtype=torch.float32, device=self.dev) * sd["time_encoder.W"] * 2 * math.pi
         e = torch.cat([torch.sin(proj), torch.cos(proj)])[: self.d]
         h = h + F.linear(e, sd["time_encoder.dense.weight"], sd["time_encoder.dense.bias"])
         for i in range(self.NL):
@@ -146,13 +149,18 @@ def time_cached_steps(port: TorchPort, batch: int, steps: Sequence[int], n_total
 
     g = torch.Generator().manual_seed(seed)
     ts = torch.linspace(1.0, 1e-5, n_total)
-    dt = ts[0] - ts[1]
-    X = port.G[None, :, None] * torch.randn(batch, port.L, port.C, generator=g)
+    dt = (ts[0] - ts[1]).to(port.dev)
+    cuda = port.dev.type == "cuda"
+    X = port.G[None, :, None] * torch.randn(batch, port.L, port.C, generator=g).to(port.dev)
     out = {}
     with torch.no_grad():
         for i in steps:
-            z = torch.randn(batch, port.L, port.C, generator=g)
+            z = torch.randn(batch, port.L, port.C, generator=g).to(port.dev)
+            if cuda:
+                torch.cuda.synchronize()
             t0 = time.perf_counter()
             X = port.step(X, float(ts[i]), z, dt, recompute_set(i, K, R, port.L))
+            if cuda:
+                torch.cuda.synchronize()
             out[i] = time.perf_counter() - t0
     return out, X
