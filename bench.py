@@ -33,6 +33,20 @@ N_DIFFUSION_STEPS = 1000
 ECG = dict(max_len=187, n_channels=1, d_model=72, num_layers=10, n_head=12)
 D_FF = 2048
 METRIC = "samples/sec (ECG freq-domain, 1000 steps, E2-CRF)"
+# (max_len, n_channels) of the reference's datamodules (src/fdiff/dataloaders/datamodules.py:194-203 ECG,
+# :469-476 NASA-charge, :406-410 NASDAQ, :530-538 USDroughts); the score model is the Hydra default for all of them
+SHAPES = {"ecg": ("ECG", 187, 1), "nasa_charge": ("NASA-charge", 251, 4), "nasdaq": ("NASDAQ", 252, 5),
+          "droughts": ("USDroughts", 365, 13)}
+
+
+def set_workload(name: str) -> None:
+    """BASELINE.json configs[1] is ECG (the default and the driver's bench line); configs[2-3] name the other shapes."""
+    global METRIC, WORKLOAD
+    label, L, C = SHAPES[name]
+    ECG.update(max_len=L, n_channels=C)
+    METRIC = f"samples/sec ({label} freq-domain, 1000 steps, E2-CRF)"
+    WORKLOAD = (f"{label} L={L} C={C} freq-domain, d=72 H=12 NL=10 F=2048 random init (seed 42), VP-SDE 1000-step grid, "
+                "E2-CRF K=5 R=10")
 
 
 # the FFN + LayerNorm kernel the library launches for the default model: CTA pairs unless FFD_FFN_CTA2=0
@@ -72,9 +86,11 @@ def peaks():
     return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, src="fallback")
 
 
-def flops_per_sample_step(n_own: int, L=187, C=1, d=72, F=D_FF, NL=10) -> float:
+def flops_per_sample_step(n_own: int, L=None, C=None, d=72, F=D_FF, NL=10) -> float:
     """SURVEY 8d: NL*L*(8d^2 + 4Ld + 4dF) + 4LCd for a full step; the pure-cache step skips K/V (4d^2);
     a mixed step recomputes K/V for n_own rows."""
+    L = ECG["max_len"] if L is None else L
+    C = ECG["n_channels"] if C is None else C
     if n_own < 0 or n_own == L or n_own > 0.8 * L:
         return NL * L * (8 * d * d + 4 * L * d + 4 * d * F) + 4 * L * C * d
     return NL * (L * (4 * d * d + 4 * L * d + 4 * d * F) + 4 * n_own * d * d) + 4 * L * C * d
@@ -219,17 +235,25 @@ def run_reference(args):
         if torch.cuda.is_available():
             from oracle.torch_port import TorchPort, time_cached_steps
 
-            gb = 4096
             torch.set_float32_matmul_precision("high")  # TF32 matmuls, as the reference sets them (cmd/sample.py:24)
             gp = TorchPort(sd, ECG["max_len"], ECG["n_channels"], ECG["n_head"], device="cuda")
-            time_cached_steps(gp, gb, [0, 1], N_DIFFUSION_STEPS)  # warm-up (cuBLAS handles, allocator)
-            gp.k_cache = gp.v_cache = None
-            tt, _ = time_cached_steps(gp, gb, [0, 1, 2, 3, 4, 5], N_DIFFUSION_STEPS)
-            pure = sum(tt[i] for i in (1, 2, 3, 4, 5)) / 5
-            on_gpu = {"value": gb / (pure * N_DIFFUSION_STEPS), "unit": "samples/s", "batch": gb,
-                      "ms_per_pure_cache_step": pure * 1e3, "ms_full_step": tt[0] * 1e3,
+            on_gpu = {"unit": "samples/s",
                       "what": "oracle/torch_port.py (the reference's ATen op sequence) in torch eager on cuda:0, TF32 "
-                              "matmuls as in cmd/sample.py:24"}
+                              "matmuls as in cmd/sample.py:24", "batches": {}}
+            for gb in (4096, args.batch):  # the bench batch too, when the eager path fits it in memory
+                try:
+                    gp.k_cache = gp.v_cache = None
+                    time_cached_steps(gp, gb, [0, 1], N_DIFFUSION_STEPS)  # warm-up (cuBLAS handles, allocator)
+                    gp.k_cache = gp.v_cache = None
+                    tt, _ = time_cached_steps(gp, gb, [0, 1, 2, 3, 4, 5], N_DIFFUSION_STEPS)
+                    pure = sum(tt[i] for i in (1, 2, 3, 4, 5)) / 5
+                    on_gpu["batches"][str(gb)] = {"value": gb / (pure * N_DIFFUSION_STEPS),
+                                                  "ms_per_pure_cache_step": pure * 1e3, "ms_full_step": tt[0] * 1e3}
+                except Exception as exc:  # out of memory at the large batch: recorded, not fatal
+                    on_gpu["batches"][str(gb)] = {"error": str(exc)[:120]}
+                    torch.cuda.empty_cache()
+            best = [v["value"] for v in on_gpu["batches"].values() if "value" in v]
+            on_gpu["value"] = max(best) if best else None
             del gp
             torch.cuda.empty_cache()
     except Exception as exc:
@@ -268,11 +292,18 @@ def run_ours(args):
 
     lib = _lib.load()
     dev = torch.device("cuda", local)
-    B = args.batch
+    if world > 1:
+        from fastfourierdiffusion_b200.distributed import warm_communicator
+
+        warm_communicator(dev)  # NCCL connects lazily: keep the set-up out of every timed collective
+    strong = args.global_batch > 0
+    B = args.global_batch // world if strong else args.batch
+    SB = min(B, args.sampler_batch) if args.sampler_batch > 0 else B   # samples per sampler batch (one workspace)
+    n_chunks = (B + SB - 1) // SB
     K, W = args.steps, args.warmup
     model = build_model(args.precision).to(dev).eval()
     cpu_state = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
-    sampler = F.DiffusionSampler(model, B, use_cache=True, cache_kwargs={}, noise="philox", seed=42 + rank)
+    sampler = F.DiffusionSampler(model, SB, use_cache=True, cache_kwargs={}, noise="philox", seed=42 + rank)
     sched = model.noise_scheduler
     sched.set_timesteps(N_DIFFUSION_STEPS)
 
@@ -282,24 +313,31 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident run -------------------------------------------------------------------
-    X0 = sampler.sample_prior(B)
+    # B samples per GPU in n_chunks sampler batches of SB (the reference's sample_batch_size loop, sampler.py:157):
+    # every sampler batch runs schedule steps 0..K-1
+    sizes = [min(SB, B - c * SB) for c in range(n_chunks)]
+    X0s = [sampler.sample_prior(n, c) for c, n in enumerate(sizes)]
     model.cache.reset()
-    sampler.run_steps(X0, 0, step_begin=0, step_end=max(W, 1))  # warm-up: full step + pure steps
+    sampler.run_steps(X0s[0], 0, step_begin=0, step_end=max(W, 1))  # warm-up: full step + pure steps
     model.cache.reset()
     barrier()
     n0 = lib.ffd_launch_count()
-    ev0, evm, ev1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    ev0, ev1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+    evm = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_chunks)]
     with ClockSampler(local) as clocks:
         barrier()
         ev0.record()
-        X = sampler.run_steps(X0, 0, step_begin=0, step_end=1)   # schedule step 0: full recompute + cache fill
-        evm.record()
-        if K > 1:
-            X = sampler.run_steps(X, 0, step_begin=1, step_end=K)
+        for c in range(n_chunks):
+            model.cache.reset()
+            evm[c][0].record()
+            X = sampler.run_steps(X0s[c], 0, batch_idx=c, step_begin=0, step_end=1)  # step 0: full recompute + cache fill
+            evm[c][1].record()
+            if K > 1:
+                X = sampler.run_steps(X, 0, batch_idx=c, step_begin=1, step_end=K)
         ev1.record()
         barrier()
     launches = int(lib.ffd_launch_count() - n0)
-    ms = torch.tensor([ev0.elapsed_time(ev1), ev0.elapsed_time(evm)], device=dev)
+    ms = torch.tensor([ev0.elapsed_time(ev1), sum(a.elapsed_time(b) for a, b in evm)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total, ms_step0 = float(ms[0].item()), float(ms[1].item())
@@ -307,37 +345,44 @@ def run_ours(args):
     assert torch.isfinite(X).all()
     ms_per_step = ms_total / K
     value = world * B / (ms_per_step * 1e-3 * N_DIFFUSION_STEPS)
+    del X0s
 
     # ---- end to end through the public API with host buffers ------------------------------------
     # DiffusionSampler.sample(): prior noise drawn on the host, copied to the device, K steps with
     # per-step torch noise, final samples copied back to the host (sampler.py:105-215).
-    e2e_sampler = F.DiffusionSampler(model, B, use_cache=True, cache_kwargs={}, noise="torch")
+    # N > 1: every rank samples its shard (sample_on_device), ONE NCCL all-gather assembles [world * B, L, C] on every
+    # rank (the path's only collective) and rank 0 reads the result to the host -- all inside the timed region.
+    from fastfourierdiffusion_b200.distributed import gather_samples
+
+    e2e_sampler = F.DiffusionSampler(model, SB, use_cache=True, cache_kwargs={}, noise="torch")
     Ke = min(K, args.e2e_steps) if args.e2e_steps > 0 else K
+    gather_ms = None
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
-    out = e2e_sampler.sample(B, num_diffusion_steps=Ke)
+    if world == 1:
+        out = e2e_sampler.sample(B, num_diffusion_steps=Ke)
+        d2h = B
+    else:
+        Xd = e2e_sampler.sample_on_device(B, num_diffusion_steps=Ke)
+        g0.record()
+        allX = gather_samples(Xd, world * B)
+        g1.record()
+        out = allX.cpu() if rank == 0 else allX[:0].cpu()
+        d2h = world * B if rank == 0 else 0
     barrier()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    assert out.shape == (B, ECG["max_len"], ECG["n_channels"]) and out.device.type == "cpu"
+        gm = torch.tensor([g0.elapsed_time(g1)], device=dev)
+        dist.all_reduce(gm, op=dist.ReduceOp.MAX)
+        gather_ms = float(gm.item())
+        assert rank != 0 or out.shape[0] == world * B
+        del allX, Xd
+    assert tuple(out.shape[1:]) == (ECG["max_len"], ECG["n_channels"]) and out.device.type == "cpu"
     e2e_value = world * B / (float(t_e2e.item()) / Ke * N_DIFFUSION_STEPS)
     bytes_io = B * ECG["max_len"] * ECG["n_channels"] * 4
-
-    # ---- final gather of the samples over NCCL (the path's only collective) -------------
-    gather_ms = None
-    if world > 1:
-        from fastfourierdiffusion_b200.distributed import gather_samples
-
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        allX = gather_samples(X, world * B)
-        g1.record()
-        barrier()
-        assert allX.shape[0] == world * B
-        gather_ms = g0.elapsed_time(g1)
-        del allX
+    d2h_bytes = d2h * ECG["max_len"] * ECG["n_channels"] * 4
 
     if rank != 0:
         if world > 1:
@@ -346,7 +391,8 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (fused FFN + LN), timed alone with CUDA events -------------
     pk = peaks()
-    M = B * ECG["max_len"]
+    Bk = min(B, 16384)   # the kernel-level timings below use one bench-sized batch of rows
+    M = Bk * ECG["max_len"]
     arena, packed = model.device_weights()
     xbuf = torch.randn(M, ECG["d_model"], device=dev)
     ybuf = torch.empty_like(xbuf)
@@ -376,7 +422,7 @@ def run_ours(args):
     attn_entry = None
     if args.precision == "bf16":
         kc, vc = model.cache._k_store, model.cache._v_store
-        wsb = model.workspace(B)
+        wsb = model.workspace(Bk)
 
         def attn():
             _lib.check(lib.ffd_attn_cached_ln(model.dims, 1, _lib.ptr(arena), _lib.ptr(packed), 3, _lib.ptr(kc),
@@ -402,11 +448,14 @@ def run_ours(args):
                       "tensor_tflops_algorithmic": attn_flops / (attn_ms * 1e-3) / 1e12,
                       "peak_source": "148 SMs x 16 MUFU lanes x SM clock under load"}
     peak = pk["bf16"] if args.precision == "bf16" else 72.0  # fp32 FMA peak: 148 SMs x 128 lanes x 2 x 1.9 GHz
-    traffic = None
+    # DRAM traffic per launch comes from an ncu --set full capture (it cannot be measured inside a timed run): the
+    # committed summary of that capture, valid for the ECG M it was taken at; labelled as static
+    traffic, traffic_source = None, None
     tpath = os.path.join(ROOT, "profiles", "ffn_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and M == 16384 * 187:
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            traffic_source = "profiles/ffn_traffic.json (static: ncu --set full capture of this kernel at this M)"
         except Exception:
             traffic = None
     # whole-step figure: algorithmic FLOPs of the timed steps over the measured time
@@ -417,11 +466,11 @@ def run_ours(args):
     # ---- informational: the device-decided event schedule (paper Algorithm 1) on the same batch ---------------
     event_info = None
     try:
-        ev_sampler = F.DiffusionSampler(model, B, use_cache=True, noise="philox", seed=42 + rank,
+        ev_sampler = F.DiffusionSampler(model, SB, use_cache=True, noise="philox", seed=42 + rank,
                                         cache_kwargs=dict(K=5, R=50, tau_0=0.3, tau_warn=0.5, event_driven=True,
                                                           event_probe_ratio=0.02))
         model.cache.reset()
-        Xe = ev_sampler.run_steps(X0, 0, step_begin=0, step_end=3)
+        Xe = ev_sampler.run_steps(ev_sampler.sample_prior(SB), 0, step_begin=0, step_end=3)
         torch.cuda.synchronize()
         q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_ev = min(20, max(K - 3, 1))
@@ -444,10 +493,12 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+        "vs_baseline": None,
         "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "noise": "Philox in-kernel",
-                   "batch_per_gpu": B, "global_batch": world * B, "schedule_steps_timed": f"0..{K - 1}",
+                   "batch_per_gpu": B, "global_batch": world * B, "sampler_batch": SB,
+                   "sampler_batches_per_gpu": n_chunks, "schedule_steps_timed": f"0..{K - 1}",
                    "value_definition": "global_batch / (1000 x mean step time over the timed steps)",
                    "l2": "per-step activations [B*L, 72] fp32 = %.0f MB >> 126 MB L2 (inputs larger than L2)" % (
                        M * 72 * 4 / 1e6),
@@ -458,12 +509,15 @@ def run_ours(args):
                    "event_driven_schedule": event_info},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": bytes_io / Ke,
-                "d2h_bytes_per_step": bytes_io / Ke, "steps": Ke,
-                "api": "DiffusionSampler.sample(): host prior noise -> H2D -> steps (torch device noise) -> D2H"},
+                "d2h_bytes_per_step": d2h_bytes / Ke, "steps": Ke,
+                "api": ("DiffusionSampler.sample(): host prior noise -> H2D -> steps (torch device noise) -> D2H"
+                        if world == 1 else
+                        "per rank DiffusionSampler.sample_on_device() (host prior noise -> H2D -> steps) -> ONE NCCL "
+                        "all_gather_into_tensor of the samples -> D2H of [world*B, L, C] on rank 0, all timed")},
         "gpu_launches": launches,
         "roofline": {"kernel": FFN_KERNEL_NAME if args.precision == "bf16" else "ffn_kernel+add_ln_kernel",
                      "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": pk["src"] + " (burst)",
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source, "peak_source": pk["src"] + " (burst)",
                      "flops_per_launch": ffn_flops, "ms_per_launch": ffn_ms,
                      "how": f"{reps} back-to-back launches over M={M} rows between CUDA events on the launch stream"},
         "roofline_other": [attn_entry] if attn_entry else [],
@@ -480,12 +534,18 @@ def main():
     ap.add_argument("--steps", type=int, default=250)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16384, help="samples per GPU")
+    ap.add_argument("--batch", type=int, default=16384, help="samples per GPU (weak scaling)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="> 0: total samples over all GPUs (strong scaling: --batch is ignored)")
+    ap.add_argument("--sampler-batch", type=int, default=0,
+                    help="> 0: samples per sampler batch (sample_batch_size); a GPU's batch runs in chunks of this size")
+    ap.add_argument("--workload", default="ecg", choices=sorted(SHAPES))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="cap the steps of the e2e leg (0 = same as --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    set_workload(args.workload)
     claim_stdout()
     if args.impl == "reference":
         run_reference(args)

@@ -6,8 +6,10 @@
 
 Same keys as cmd/conf/sample.yaml.  The flow is the reference's (cmd/sample.py:99-125): sample in the model's
 domain, de-standardise, ``idft`` when the model works in the frequency domain, save ``samples.pt`` and
-``results.yaml``.  Without a trained checkpoint (no datasets/checkpoints ship with this repo) a random-init
-model of the named dataset's shape is used and the standardisation constants are the identity.  The quality
+``results.yaml``.  With ``model_id`` the run directory must hold ``train_config.yaml`` and a checkpoint
+(``FileNotFoundError`` otherwise, as in the reference): architecture, SDE, domain and standardisation come from
+them.  Without ``model_id`` (no datasets/checkpoints ship with this repo) a random-init model of the named
+dataset's shape is used and the standardisation constants are the identity.  The quality
 metrics of the reference (sliced Wasserstein, POT) are out of scope.
 """
 
@@ -23,23 +25,33 @@ import torch
 import yaml
 
 import fastfourierdiffusion_b200 as F
-from fastfourierdiffusion_b200.cli import SAMPLE_DEFAULTS, build_model, parse_overrides
+from fastfourierdiffusion_b200.cli import SAMPLE_DEFAULTS, build_model, instantiate, parse_overrides
 
 
 def main(argv) -> None:
     cfg = parse_overrides(argv, SAMPLE_DEFAULTS)
     torch.manual_seed(cfg["random_seed"])
     model, ckpt = build_model(cfg)
+    fourier_transform, feature_std, feature_mean = bool(cfg["fourier_transform"]), None, None
+    if ckpt is not None:
+        # cmd/sample.py:66-70,107-109: domain and standardisation belong to the TRAINING run, not to this call
+        datamodule = instantiate(cfg["_run"]["train_cfg"]["datamodule"])
+        datamodule.prepare_data()
+        datamodule.setup()
+        fourier_transform = bool(datamodule.fourier_transform)
+        if datamodule.standardize:
+            feature_mean, feature_std = datamodule.feature_mean_and_std
     kwargs = dict(sample_batch_size=cfg["sampler.sample_batch_size"], noise=cfg["noise"], seed=cfg["random_seed"])
     if cfg["use_cache"]:
         kwargs.update(use_cache=True, cache_kwargs=dict(cfg["cache_kwargs"] or {}))
     sampler = F.DiffusionSampler(score_model=model, **kwargs)
     t0 = time.time()
-    X = sampler.sample(num_samples=cfg["num_samples"], num_diffusion_steps=cfg["num_diffusion_steps"])
+    # de-standardise + idft on the device, per batch, before the copy to the host (cmd/sample.py:107-113)
+    X = sampler.sample_time_domain(num_samples=cfg["num_samples"], num_diffusion_steps=cfg["num_diffusion_steps"],
+                                   feature_std=feature_std, feature_mean=feature_mean,
+                                   fourier_transform=fourier_transform)
     torch.cuda.synchronize()
     dt = time.time() - t0
-    if cfg["fourier_transform"]:
-        X = F.idft(X)  # cmd/sample.py:111-113 (identity standardisation for random-init models)
     out_dir = cfg["output_dir"] or os.path.join(cfg["model_path"], str(cfg["model_id"] or "random_init"),
                                                 "samples_cache" if cfg["use_cache"] else "samples")
     os.makedirs(out_dir, exist_ok=True)

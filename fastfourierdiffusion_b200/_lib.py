@@ -14,7 +14,9 @@ from typing import Optional
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libffd_b200.so")
+# FFD_LIB selects another build of the same library (A/B timing of kernel variants, tools/ab.sh) without touching
+# the in-tree product file
+LIB_PATH = os.environ.get("FFD_LIB") or os.path.join(_PKG, "libffd_b200.so")
 
 PREC_FP32, PREC_BF16 = 0, 1
 SDE_VP, SDE_VE = 0, 1
@@ -63,12 +65,20 @@ class EventArgs(C.Structure):
                 ("seed", C.c_uint64)]
 
 
+class FrescaArgs(C.Structure):
+    """ffd_fresca_args: FreSca inside the fused step loop."""
+    _fields_ = [("U", C.c_void_p), ("V", C.c_void_p), ("scratch", C.c_void_p),
+                ("high_scale_host", C.POINTER(C.c_float)), ("low_scale", C.c_float), ("cutoff_ratio", C.c_float),
+                ("strategy", C.c_int32)]
+
+
 class SampleArgs(C.Structure):
     _fields_ = [("fwd", ForwardArgs), ("G", C.c_void_p), ("time_emb_table", C.c_void_p),
                 ("coef_host", C.POINTER(StepCoef)), ("n_own_host", C.POINTER(C.c_int32)),
                 ("store_crf_host", C.POINTER(C.c_int32)), ("noise", C.c_void_p), ("noise_step0", C.c_int32), ("seed", C.c_uint64),
                 ("stream_base", C.c_uint64), ("x", C.c_void_p), ("x_tmp", C.c_void_p),
-                ("step_begin", C.c_int32), ("step_end", C.c_int32), ("event", C.POINTER(EventArgs))]
+                ("step_begin", C.c_int32), ("step_end", C.c_int32), ("event", C.POINTER(EventArgs)),
+                ("fresca", C.POINTER(FrescaArgs))]
 
 
 _lib: Optional[C.CDLL] = None

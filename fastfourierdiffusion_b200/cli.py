@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ast
 import os
+import re
 from typing import Any, Dict, List, Optional
 
 import torch
@@ -52,31 +53,99 @@ def build_scheduler(name: str, fourier_noise_scaling: bool):
     raise SystemExit(f"unknown noise_scheduler {name!r} (vpsde | vesde)")
 
 
-def find_checkpoint(model_path: str, model_id: Optional[str]) -> Optional[str]:
-    """Best checkpoint of a reference training run: lowest val_loss in ``epoch=..-val_loss=..ckpt``
+def find_best_checkpoint(ckpt_dir: str) -> Optional[str]:
+    """Best checkpoint of a reference training run: lowest val_loss among ``*epoch=N-val_loss=X.ckpt``
     (utils/extraction.py:79-98)."""
-    if not model_id:
-        return None
-    d = os.path.join(model_path, str(model_id), "checkpoints")
-    if not os.path.isdir(d):
+    if not os.path.isdir(ckpt_dir):
         return None
     best, best_loss = None, float("inf")
-    for f in os.listdir(d):
-        if f.endswith(".ckpt") and "val_loss=" in f:
-            try:
-                loss = float(f.split("val_loss=")[1].rsplit(".ckpt", 1)[0])
-            except ValueError:
-                continue
-            if loss < best_loss:
-                best, best_loss = os.path.join(d, f), loss
+    for f in sorted(os.listdir(ckpt_dir)):
+        m = re.match(r"(.*?)epoch=(\d+)-val_loss=(\d+\.\d+)\.ckpt$", f)
+        if m is not None and float(m.group(3)) < best_loss:
+            best, best_loss = os.path.join(ckpt_dir, f), float(m.group(3))
     return best
 
 
+# ---- the run directory of a trained model (cmd/sample.py:31-75) ---------------------------------------------
+def resolve_config(cfg: Any, root: Optional[dict] = None) -> Any:
+    """``train_config.yaml`` is written by ``OmegaConf.save`` with its interpolations unresolved
+    (cmd/train.py:43): resolve ``${a.b}`` references against the root; resolver calls such as
+    ``${hydra:runtime.cwd}`` become the current directory."""
+    root = cfg if root is None else root
+
+    def lookup(path: str) -> Any:
+        node: Any = root
+        for part in path.split("."):
+            node = node[part]
+        return resolve_config(node, root)
+
+    if isinstance(cfg, dict):
+        return {k: resolve_config(v, root) for k, v in cfg.items()}
+    if isinstance(cfg, list):
+        return [resolve_config(v, root) for v in cfg]
+    if isinstance(cfg, str) and "${" in cfg:
+        whole = re.fullmatch(r"\$\{([^${}:]+)\}", cfg)
+        if whole:
+            return lookup(whole.group(1))
+        cfg = re.sub(r"\$\{hydra:runtime\.cwd\}", os.getcwd().replace("\\", "/"), cfg)
+        return re.sub(r"\$\{([^${}:]+)\}", lambda m: str(lookup(m.group(1))), cfg)
+    return cfg
+
+
+def instantiate(node: Any, **extra: Any) -> Any:
+    """The subset of ``hydra.utils.instantiate`` the sampling entry points use: ``_target_`` (a dotted path, the
+    reference's ``fdiff.*`` names resolve through the ``fdiff`` package of this repository), ``_partial_``,
+    nested nodes."""
+    import functools
+    import importlib
+
+    if isinstance(node, list):
+        return [instantiate(v) for v in node]
+    if not isinstance(node, dict):
+        return node
+    if "_target_" not in node:
+        return {k: instantiate(v) for k, v in node.items()}
+    mod, _, name = node["_target_"].rpartition(".")
+    fn = getattr(importlib.import_module(mod), name)
+    kwargs = {k: instantiate(v) for k, v in node.items() if k not in ("_target_", "_partial_")}
+    kwargs.update(extra)
+    return functools.partial(fn, **kwargs) if node.get("_partial_") else fn(**kwargs)
+
+
+def load_run(model_path: str, model_id: str) -> Dict[str, Any]:
+    """What cmd/sample.py:31-75 reads from ``<model_path>/<model_id>``: ``train_config.yaml`` (datamodule, domain,
+    standardisation) and the best checkpoint.  Missing pieces raise ``FileNotFoundError`` as the reference does --
+    there is no silent fall-back to a random-init model when a model id is given."""
+    import yaml
+
+    run_dir = os.path.join(model_path, str(model_id))
+    if not os.path.isdir(run_dir):
+        avail = sorted(d for d in os.listdir(model_path) if os.path.isdir(os.path.join(model_path, d))) \
+            if os.path.isdir(model_path) else []
+        raise FileNotFoundError(f"Model directory not found: {run_dir}\nAvailable model IDs: {', '.join(avail[:10])}")
+    cfg_path = os.path.join(run_dir, "train_config.yaml")
+    if not os.path.exists(cfg_path):
+        raise FileNotFoundError(f"Training config not found: {cfg_path}\nThis model may not have been trained yet.")
+    with open(cfg_path) as f:
+        train_cfg = resolve_config(yaml.safe_load(f))
+    ckpt = find_best_checkpoint(os.path.join(run_dir, "checkpoints"))
+    if ckpt is None:
+        raise FileNotFoundError(f"no '*epoch=N-val_loss=X.ckpt' checkpoint under {run_dir}/checkpoints")
+    return {"run_dir": run_dir, "train_cfg": train_cfg, "checkpoint": ckpt}
+
+
 def build_model(cfg: Dict[str, Any]):
-    """ScoreModule on the GPU: weights from a reference checkpoint's ``state_dict`` when one is found,
-    else random init under ``random_seed`` (same init as the reference under the same seed)."""
+    """ScoreModule on the GPU.  With ``model_id``: the trained run -- architecture, SDE and domain from the
+    checkpoint's hyper-parameters and ``train_config.yaml`` (cmd/sample.py:50-75), never from the CLI defaults.
+    Without: random init under ``random_seed`` on the named dataset's shape (same init as the reference under the
+    same seed; no datasets / checkpoints ship with this repository).  Returns (model, checkpoint path or None)."""
     from . import ScoreModule
 
+    if cfg.get("model_id"):
+        run = load_run(cfg["model_path"], cfg["model_id"])
+        model = ScoreModule.load_from_checkpoint(run["checkpoint"], precision=cfg.get("precision"))
+        cfg["_run"] = run
+        return model.to("cuda").eval(), run["checkpoint"]
     max_len, n_channels = DATASET_SHAPES[cfg["datamodule"]]
     torch.manual_seed(cfg["random_seed"])
     sched = build_scheduler(cfg["noise_scheduler"], bool(cfg["fourier_transform"]))
@@ -84,11 +153,5 @@ def build_model(cfg: Dict[str, Any]):
                         fourier_noise_scaling=bool(cfg["fourier_transform"]), d_model=cfg["score_model.d_model"],
                         num_layers=cfg["score_model.num_layers"], n_head=cfg["score_model.n_head"],
                         precision=cfg.get("precision"))
-    ckpt = find_checkpoint(cfg["model_path"], cfg["model_id"])
-    if ckpt is not None:
-        sd = torch.load(ckpt, map_location="cpu", weights_only=False)
-        sd = sd.get("state_dict", sd)
-        sd = {k: v for k, v in sd.items() if not k.startswith("cached_backbone")}
-        model.load_state_dict(sd, strict=True)
     sched.set_noise_scaling(max_len)
-    return model.to("cuda").eval(), ckpt
+    return model.to("cuda").eval(), None

@@ -18,6 +18,11 @@ void set_error(const char* fmt, ...) {
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED); }
 
+// every branch of this model runs on the tensor-core kernels: no fp32 staging buffers are needed (carve)
+static bool lean_workspace(const ffd_dims& m, int precision) {
+  return precision == FFD_PREC_BF16 && tc_attn_supported(m) && tc_attn_own_fused(m);
+}
+
 static int check_dims(const ffd_dims& m) {
   FFD_CHECK_ARG(m.max_len > 0 && m.n_channels > 0 && m.d_model > 0 && m.n_head > 0 && m.d_ff > 0 && m.n_layers > 0,
                 "non-positive model dimension");
@@ -61,9 +66,15 @@ static int run_layer(const ffd_forward_args& a, const Arena& ar, const Workspace
         return rc;
       kv_src = ws.qkv;
     }
-    if ((rc = tc_attn_own(m, tc_attn_image(m, a.packed, layer), ws.kvimg_own, kv_src, 3 * d, d, 2 * d, a.weights,
-                          layer, ws.h, ws.h, M, s, branch == 2 ? ws.kvimg : nullptr, a.n_own, a.own_mask)))
-      return rc;
+    // the per-sample operand images are built and consumed OWN_CHUNK samples at a time
+    for (int64_t b0 = 0; b0 < a.B; b0 += OWN_CHUNK) {
+      const int64_t nb = a.B - b0 < OWN_CHUNK ? a.B - b0 : OWN_CHUNK;
+      float* hc = ws.h + b0 * L * d;
+      if ((rc = tc_attn_own(m, tc_attn_image(m, a.packed, layer), ws.kvimg_own, kv_src ? kv_src + b0 * L * 3 * d : nullptr,
+                            3 * d, d, 2 * d, a.weights, layer, hc, hc, nb * L, s, branch == 2 ? ws.kvimg : nullptr,
+                            a.n_own, a.own_mask)))
+        return rc;
+    }
     if (branch == 2 && (rc = launch_scatter_kv(ws.kvtmp, 2 * d, 0, d, a.own_mask, a.n_own, kc, vc, L, H, hd, s)))
       return rc;
     return tc_ffn_ln(m, a.packed, a.weights, layer, ws.h, ws.h, M, s);
@@ -220,9 +231,8 @@ int ffd_pack_weights(const ffd_dims* dims, const float* weights, void* packed, f
 }
 
 int64_t ffd_workspace_bytes(const ffd_dims* dims, int64_t B, int precision) {
-  (void)precision;
   if (!dims || B < 0) return -1;
-  return carve(*dims, B, nullptr).bytes;
+  return carve(*dims, B, nullptr, lean_workspace(*dims, precision)).bytes;
 }
 
 int ffd_has_tensor_path(void) {
@@ -244,7 +254,7 @@ int ffd_dft_apply(const float* T, const float* x, const float* scale, const floa
   return launch_dft_apply(T, x, scale, shift, y, B, L, C, (cudaStream_t)stream);
 }
 
-int64_t ffd_fresca_scratch_floats(int64_t B, int L, int C) { return B * L * C + (int64_t)L * C + L / 2 + 1; }
+int64_t ffd_fresca_scratch_floats(int64_t B, int L, int C) { return fresca_scratch_floats(B, L, C); }
 
 int ffd_fresca(const float* U, const float* V, const float* score, float* out, float* scratch, int64_t B, int L, int C,
                float low_scale, float high_scale, float cutoff_ratio, int strategy, ffd_stream_t stream) {
@@ -314,7 +324,7 @@ int ffd_score_forward(const ffd_forward_args* a, ffd_stream_t stream) {
   if (a->B == 0) return FFD_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const Arena ar = arena_of(a->dims);
-  const Workspace ws = carve(a->dims, a->B, a->workspace);
+  const Workspace ws = carve(a->dims, a->B, a->workspace, lean_workspace(a->dims, a->precision));
   if ((rc = forward_hidden(*a, ar, ws, s))) return rc;
   const ffd_dims& m = a->dims;
   return launch_unembed_step(ws.h, a->weights + ar.unemb_w, a->weights + ar.unemb_b, a->score, 0, nullptr, nullptr,
@@ -365,7 +375,7 @@ int ffd_attn_cached_ln(const ffd_dims* dims, int precision, const float* weights
   if (M == 0) return FFD_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const Arena ar = arena_of(m);
-  const Workspace ws = carve(m, B, workspace);
+  const Workspace ws = carve(m, B, workspace, lean_workspace(m, precision));
   const float* w = weights + ar.layer0 + (int64_t)layer * ar.layer_stride;
   if (precision == FFD_PREC_BF16) {
     FFD_CHECK_ARG(packed != nullptr, "FFD_PREC_BF16 needs the packed weight image");
@@ -439,6 +449,11 @@ int ffd_sample_steps(const ffd_sample_args* a, ffd_stream_t stream) {
     FFD_CHECK_ARG(e.R > 0 && e.K >= 0, "ffd_event_args: R must be positive, K non-negative");
     FFD_CHECK_ARG(a->fwd.k_cache && a->fwd.v_cache, "the event-driven schedule needs the K/V cache");
   }
+  if (a->fresca) {
+    const ffd_fresca_args& fr = *a->fresca;
+    FFD_CHECK_ARG(fr.U && fr.V && fr.scratch && fr.high_scale_host, "null pointer in ffd_fresca_args");
+    FFD_CHECK_ARG(fr.strategy == 0 || fr.strategy == 1, "unknown cutoff strategy %d (0 spatial, 1 energy)", fr.strategy);
+  }
   ffd_forward_args f = a->fwd;
   f.X = a->x;
   f.time_emb = a->time_emb_table;  // placeholder for the null check
@@ -448,7 +463,7 @@ int ffd_sample_steps(const ffd_sample_args* a, ffd_stream_t stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const ffd_dims& m = f.dims;
   const Arena ar = arena_of(m);
-  const Workspace ws = carve(m, f.B, f.workspace);
+  const Workspace ws = carve(m, f.B, f.workspace, lean_workspace(m, f.precision));
   const int64_t n_elem = f.B * m.max_len * m.n_channels;
   float* cur = a->x;
   float* nxt = a->x_tmp;
@@ -471,6 +486,28 @@ int ffd_sample_steps(const ffd_sample_args* a, ffd_stream_t stream) {
     if (!(a->store_crf_host && a->store_crf_host[i])) fi.crf_out = nullptr;
     if ((rc = forward_hidden(fi, ar, ws, s, a->event, i))) return rc;
     const float* z = a->noise ? a->noise + (int64_t)(i - a->noise_step0) * n_elem : nullptr;
+    if (a->fresca && !(a->fresca->low_scale == 1.0f && a->fresca->high_scale_host[i] == 1.0f)) {
+      // score -> FreSca filter -> SDE update (sampler.py:79-101); three more launches, no host sync
+      const ffd_fresca_args& fr = *a->fresca;
+      float* raw = fr.scratch + fresca_scratch_floats(f.B, m.max_len, m.n_channels);
+      float* filt = raw + n_elem;
+      if ((rc = launch_unembed_step(ws.h, f.weights + ar.unemb_w, f.weights + ar.unemb_b, raw, 0, nullptr, nullptr,
+                                    nullptr, nullptr, 0, 0, nullptr, f.B * m.max_len, m.max_len, m.n_channels,
+                                    m.d_model, s)))
+        return rc;
+      if ((rc = launch_fresca(fr.U, fr.V, raw, filt, fr.scratch, f.B, m.max_len, m.n_channels, fr.low_scale,
+                              fr.high_scale_host[i], fr.cutoff_ratio, fr.strategy, s)))
+        return rc;
+      if (f.score)
+        FFD_CHECK_CUDA(cudaMemcpyAsync(f.score, filt, sizeof(float) * n_elem, cudaMemcpyDeviceToDevice, s));
+      if ((rc = launch_sde_step(&c, a->G, cur, filt, z, a->seed, a->stream_base + (uint64_t)i, nxt, f.B, m.max_len,
+                                m.n_channels, s)))
+        return rc;
+      float* t = cur;
+      cur = nxt;
+      nxt = t;
+      continue;
+    }
     if ((rc = launch_unembed_step(ws.h, f.weights + ar.unemb_w, f.weights + ar.unemb_b, f.score, 1, &c, a->G, cur, z,
                                   a->seed, a->stream_base + (uint64_t)i, nxt, f.B * m.max_len, m.max_len,
                                   m.n_channels, m.d_model, s)))

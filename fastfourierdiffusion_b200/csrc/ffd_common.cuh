@@ -96,7 +96,14 @@ struct Workspace {
   int64_t bytes;
 };
 
-static inline Workspace carve(const ffd_dims& m, int64_t B, void* base) {
+// Samples per pass of the per-sample K/V operand images (stock / mixed attention on the tcgen05 kernel): the images are
+// 147 KB per ECG sample, so a full step walks the batch in groups of this many samples instead of holding B images.
+constexpr int64_t OWN_CHUNK = 2048;
+
+// lean: the tensor-core path covers every branch of the model (bf16 precision, tcgen05 attention with the fused K/V
+// projection), so only the residual stream and the operand images are needed -- 54 KB per ECG sample instead of
+// 323 KB + 147 KB, which is what lets one sampler batch hold 2^20 samples in 180 GB.
+static inline Workspace carve(const ffd_dims& m, int64_t B, void* base, bool lean) {
   Workspace w;
   const int64_t M = B * m.max_len, d = m.d_model;
   char* p = (char*)base;
@@ -107,14 +114,15 @@ static inline Workspace carve(const ffd_dims& m, int64_t B, void* base) {
     return r;
   };
   w.h = take(M * d);
-  w.tmp = take(M * d);
-  w.attn = take(M * d);
-  w.qkv = take(M * 3 * d);
+  w.tmp = lean ? nullptr : take(M * d);
+  w.attn = lean ? nullptr : take(M * d);
+  w.qkv = lean ? nullptr : take(M * 3 * d);
   w.kvtmp = take((int64_t)m.max_len * 2 * d);
   // [NL, H, NCH] x (K image [CK x 16] bf16 + V image [16 x CK] fp16)
   w.kvimg = take((int64_t)m.n_layers * m.n_head * attn_key_chunks(m.max_len) * attn_chunk_keys(m.max_len) * 16);
-  // [B, H, NCH] x (K image + V image): 64 bytes per key slot
-  w.kvimg_own = take(B * m.n_head * attn_key_chunks(m.max_len) * attn_chunk_keys(m.max_len) * 16);
+  // [min(B, OWN_CHUNK), H, NCH] x (K image + V image): 64 bytes per key slot
+  const int64_t own = B < OWN_CHUNK ? B : OWN_CHUNK;
+  w.kvimg_own = take(own * m.n_head * attn_key_chunks(m.max_len) * attn_chunk_keys(m.max_len) * 16);
   w.bytes = o;
   return w;
 }

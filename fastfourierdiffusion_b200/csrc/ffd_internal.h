@@ -32,6 +32,7 @@ int launch_dft_matrix(float* out, int L, int inverse, cudaStream_t s);
 int launch_dft_apply(const float* T, const float* x, const float* scale, const float* shift, float* y, int64_t B,
                      int L, int C, cudaStream_t s);
 
+int64_t fresca_scratch_floats(int64_t B, int L, int C);
 int launch_fresca(const float* U, const float* V, const float* score, float* out, float* scratch, int64_t B, int L,
                   int C, float low, float high, float cutoff_ratio, int strategy, cudaStream_t s);
 

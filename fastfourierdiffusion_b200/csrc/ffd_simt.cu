@@ -749,9 +749,83 @@ dft_apply_kernel(const float* __restrict__ T, const float* __restrict__ x, const
   }
 }
 
+// The same product for a GROUP of samples per CTA, so that every element of T is read from shared memory once per 16
+// output columns instead of once per column from L2 (the one-sample kernel streams the whole L x L matrix per sample:
+// 2.3 GB of L2 reads for an ECG batch of 16384).  A CTA owns NB = 16 / C samples = up to 16 columns j = (b - b0) C + c;
+// thread k accumulates y[., k, .] for all of them over n ASCENDING with fmaf -- the same rounding order as
+// dft_apply_kernel, so both kernels return identical bits.  T enters in [256 k x 32 n] tiles (coalesced rows).
+constexpr int DFT_COLS = 16;
+constexpr int DFT_KT = 256;
+__global__ void __launch_bounds__(DFT_KT)
+dft_apply_tiled_kernel(const float* __restrict__ T, const float* __restrict__ x, const float* __restrict__ scale,
+                       const float* __restrict__ shift, float* __restrict__ y, int64_t B, int L, int C, int NB) {
+  extern __shared__ float sm[];
+  float* xs = sm;                                  // [L][DFT_COLS]
+  float* Ts = sm + (size_t)L * DFT_COLS;           // [DFT_KT][33]
+  const int64_t b0 = (int64_t)blockIdx.x * NB;
+  const int nb = (int)(B - b0 < NB ? B - b0 : NB);
+  const int cols = nb * C;
+  for (int e = threadIdx.x; e < L * DFT_COLS; e += DFT_KT) {
+    const int n = e / DFT_COLS, j = e % DFT_COLS;
+    float v = 0.f;
+    if (j < cols) {
+      const int bb = j / C, c = j % C;
+      v = x[((b0 + bb) * L + n) * C + c];
+      if (scale) v = __fmul_rn(v, scale[n * C + c]);
+      if (shift) v = __fadd_rn(v, shift[n * C + c]);
+    }
+    xs[e] = v;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k0 = 0; k0 < L; k0 += DFT_KT) {
+    const int k = k0 + threadIdx.x;
+    float acc[DFT_COLS];
+#pragma unroll
+    for (int j = 0; j < DFT_COLS; ++j) acc[j] = 0.f;
+    for (int n0 = 0; n0 < L; n0 += 32) {
+      __syncthreads();  // xs written / previous tile consumed
+      for (int r = warp; r < DFT_KT; r += DFT_KT / 32) {
+        const int kk = k0 + r, n = n0 + lane;
+        Ts[r * 33 + lane] = (kk < L && n < L) ? T[(int64_t)kk * L + n] : 0.f;
+      }
+      __syncthreads();
+      const int nn_end = L - n0 < 32 ? L - n0 : 32;
+      for (int nn = 0; nn < nn_end; ++nn) {
+        const float t = Ts[threadIdx.x * 33 + nn];
+        const float4* xr = reinterpret_cast<const float4*>(xs + (size_t)(n0 + nn) * DFT_COLS);
+#pragma unroll
+        for (int q = 0; q < DFT_COLS / 4; ++q) {
+          const float4 v = xr[q];
+          acc[4 * q] = fmaf(t, v.x, acc[4 * q]);
+          acc[4 * q + 1] = fmaf(t, v.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(t, v.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(t, v.w, acc[4 * q + 3]);
+        }
+      }
+    }
+    if (k < L) {
+#pragma unroll
+      for (int j = 0; j < DFT_COLS; ++j)
+        if (j < cols) y[((b0 + j / C) * L + k) * C + j % C] = acc[j];
+    }
+  }
+}
+
 int launch_dft_apply(const float* T, const float* x, const float* scale, const float* shift, float* y, int64_t B,
                      int L, int C, cudaStream_t s) {
   if (B == 0) return FFD_OK;
+  if (C <= DFT_COLS && B >= 64) {
+    const int NB = DFT_COLS / C;
+    const size_t smem = ((size_t)L * DFT_COLS + (size_t)DFT_KT * 33) * sizeof(float);
+    if (smem <= 200 * 1024) {
+      if (smem > 48 * 1024)
+        FFD_CHECK_CUDA(cudaFuncSetAttribute(dft_apply_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+      dft_apply_tiled_kernel<<<(unsigned)((B + NB - 1) / NB), DFT_KT, smem, s>>>(T, x, scale, shift, y, B, L, C, NB);
+      FFD_CHECK_LAUNCH("dft_apply_tiled_kernel");
+      return FFD_OK;
+    }
+  }
   const size_t smem = (size_t)L * C * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("L*C = %d too large for the boundary DFT kernel", L * C);
@@ -768,9 +842,12 @@ int launch_dft_apply(const float* T, const float* x, const float* scale, const f
 // FreSca score filter (src/fdiff/utils/fresca.py:111-268): rfft along L, low band x l, high band x h, irfft.
 // In the real-packed DFT basis (fourier.py layout) that is a per-frequency gain between two dense transforms.
 // ------------------------------------------------------------------------------------
-// spec[k] += sum over this block's samples and all channels of |X_k| (packed layout: Re at row k, Im at nr-1+k)
+// part[block, k] = sum over this block's samples and all channels of |X_k| (packed layout: Re at row k, Im at
+// nr-1+k).  No atomics: the partial sums are reduced in a fixed order by fresca_gain_kernel, so that the band
+// boundary the "energy" strategy derives from them is the same in every run.
+constexpr int FRESCA_BLOCKS = 592;
 __global__ void __launch_bounds__(256)
-fresca_spectrum_kernel(const float* __restrict__ xt, float* __restrict__ spec, int64_t B, int L, int C, int n_freq) {
+fresca_spectrum_kernel(const float* __restrict__ xt, float* __restrict__ part, int64_t B, int L, int C, int n_freq) {
   const int nr = (L + 2) / 2;  // = n_freq
   const int64_t per = (B + gridDim.x - 1) / gridDim.x;
   const int64_t b0 = (int64_t)blockIdx.x * per, b1 = b0 + per < B ? b0 + per : B;
@@ -783,15 +860,25 @@ fresca_spectrum_kernel(const float* __restrict__ xt, float* __restrict__ spec, i
         const float im = has_im ? xt[(b * L + nr - 1 + k) * C + c] : 0.f;
         acc += sqrtf(re * re + im * im);
       }
-    atomicAdd(spec + k, acc);
+    part[(int64_t)blockIdx.x * n_freq + k] = acc;
   }
 }
 
 // cutoff index and per-row gains.  strategy 0 = spatial (k <= r0 * n_freq), 1 = energy: first i whose cumulative
 // mean magnitude reaches r0 * total (fresca.py:41-60); gain[row, c] = l for rows of frequencies <= Rc, else h.
-__global__ void fresca_gain_kernel(const float* __restrict__ spec, float* __restrict__ gain, int L, int C, int n_freq,
-                                   float low, float high, float cutoff_ratio, int strategy, float inv_count) {
+// n_part > 0: spec[k] is first reduced from the per-block partial spectra, blocks in ascending order.
+__global__ void fresca_gain_kernel(float* __restrict__ spec, const float* __restrict__ part, int n_part,
+                                   float* __restrict__ gain, int L, int C, int n_freq, float low, float high,
+                                   float cutoff_ratio, int strategy, float inv_count) {
   __shared__ int rc_s;
+  if (strategy == 1) {
+    for (int k = threadIdx.x; k < n_freq; k += blockDim.x) {
+      float acc = 0.f;
+      for (int b = 0; b < n_part; ++b) acc += part[(int64_t)b * n_freq + k];
+      spec[k] = acc;
+    }
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     int rc = 0;
     if (strategy == 0) {
@@ -823,22 +910,27 @@ __global__ void fresca_gain_kernel(const float* __restrict__ spec, float* __rest
   }
 }
 
+int64_t fresca_scratch_floats(int64_t B, int L, int C) {
+  return B * L * C + (int64_t)L * C + (int64_t)(FRESCA_BLOCKS + 1) * (L / 2 + 1);
+}
+
 int launch_fresca(const float* U, const float* V, const float* score, float* out, float* scratch, int64_t B, int L,
                   int C, float low, float high, float cutoff_ratio, int strategy, cudaStream_t s) {
-  // scratch: [B*L*C] transformed scores, then [L*C] gains, then [n_freq] spectrum
+  // scratch: [B*L*C] transformed scores, [L*C] gains, [n_freq] spectrum, [FRESCA_BLOCKS][n_freq] partial spectra
   const int n_freq = L / 2 + 1;
   float* xt = scratch;
   float* gain = scratch + B * L * C;
   float* spec = gain + (int64_t)L * C;
+  float* part = spec + n_freq;
   int rc;
   if ((rc = launch_dft_apply(U, score, nullptr, nullptr, xt, B, L, C, s))) return rc;
+  unsigned blocks = 0;
   if (strategy == 1) {
-    FFD_CHECK_CUDA(cudaMemsetAsync(spec, 0, sizeof(float) * n_freq, s));
-    const unsigned blocks = (unsigned)(B < 592 ? B : 592);
-    fresca_spectrum_kernel<<<blocks, 256, 0, s>>>(xt, spec, B, L, C, n_freq);
+    blocks = (unsigned)(B < FRESCA_BLOCKS ? B : FRESCA_BLOCKS);
+    fresca_spectrum_kernel<<<blocks, 256, 0, s>>>(xt, part, B, L, C, n_freq);
     FFD_CHECK_LAUNCH("fresca_spectrum_kernel");
   }
-  fresca_gain_kernel<<<1, 256, 0, s>>>(spec, gain, L, C, n_freq, low, high, cutoff_ratio, strategy,
+  fresca_gain_kernel<<<1, 256, 0, s>>>(spec, part, (int)blocks, gain, L, C, n_freq, low, high, cutoff_ratio, strategy,
                                        1.0f / (float)(B * C));
   FFD_CHECK_LAUNCH("fresca_gain_kernel");
   return launch_dft_apply(V, xt, gain, nullptr, out, B, L, C, s);

@@ -52,28 +52,34 @@ class DiffusionSampler:
     # -- single step (API parity; the fused loop below does not go through here) --------
     def reverse_diffusion_step(self, batch: DiffusableBatch, step: int = 0,
                                recompute_tokens: Optional[Set[int]] = None,
-                               noise: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """sampler.py:48-103.  ``noise`` (extra, optional) injects z instead of drawing ``randn_like``."""
+                               noise: Optional[torch.Tensor] = None, t: Optional[float] = None) -> torch.Tensor:
+        """sampler.py:48-103.  ``noise`` (extra, optional) injects z instead of drawing ``randn_like``; ``t`` (extra,
+        optional) is the batch's shared timestep as a host float."""
         X, timesteps = batch.X, batch.timesteps
         assert timesteps is not None and timesteps.size(0) == len(batch)
-        assert torch.min(timesteps) == torch.max(timesteps)
         model = self.score_model
+        # One shared t per batch (sampler.py:59-60).  The loops of this class pass it as ``t`` so that the three
+        # ``.item()`` reads the reference makes per step (device syncs when ``timesteps`` is a CUDA tensor) do not
+        # happen; a caller that only has the tensor pays for one read.
+        if t is None:
+            assert torch.min(timesteps) == torch.max(timesteps)
+            t = float(timesteps[0].item())
         if self.use_cache and recompute_tokens is not None:
-            score, crf = model(batch, recompute_tokens=recompute_tokens, step=step, return_crf=True)
+            score, crf = model(batch, recompute_tokens=recompute_tokens, step=step, return_crf=True, t=t)
             if model.cache is not None:
-                model.cache.update_crf(crf, timestep=timesteps[0].item())
+                model.cache.update_crf(crf, timestep=t)
                 model.cache.current_step = step
         else:
-            score = model(batch)
+            score = model(batch, t=t)
         if self.use_fresca:  # sampler.py:79-93
             from .fresca import apply_fresca_to_score
 
             strategy = "energy" if self.fresca_cutoff_strategy == "energy" else "spatial"
             score = apply_fresca_to_score(score, low_scale=self.fresca_low_scale, high_scale=self.fresca_high_scale,
                                           cutoff_ratio=self.fresca_cutoff_ratio, cutoff_strategy=strategy,
-                                          timestep=timesteps[0].item(),
+                                          timestep=t,
                                           num_steps=getattr(self, "_num_diffusion_steps", None))
-        out = self.noise_scheduler.step(model_output=score, timestep=timesteps[0].item(), sample=X, noise=noise)
+        out = self.noise_scheduler.step(model_output=score, timestep=t, sample=X, noise=noise)
         return out.prev_sample
 
     # -- the loop ---------------------------------------------------------------------------
@@ -104,7 +110,12 @@ class DiffusionSampler:
 
         return self._sample(num_samples, num_diffusion_steps, tail)
 
-    def _sample(self, num_samples: int, num_diffusion_steps: Optional[int], tail) -> torch.Tensor:
+    def sample_on_device(self, num_samples: int, num_diffusion_steps: Optional[int] = None) -> torch.Tensor:
+        """``sample`` without the final copy to the host: the ``[N, L, C]`` result stays on the model's device (what
+        a rank of a batch-sharded run hands to the final NCCL gather, ``distributed.sample_sharded``)."""
+        return self._sample(num_samples, num_diffusion_steps, None, to_host=False)
+
+    def _sample(self, num_samples: int, num_diffusion_steps: Optional[int], tail, to_host: bool = True) -> torch.Tensor:
         if num_diffusion_steps is not None:
             self._num_diffusion_steps = num_diffusion_steps
         model = self.score_model
@@ -121,14 +132,11 @@ class DiffusionSampler:
                 if self.use_cache and model.cache is not None and batch_idx == 0:
                     model.cache.reset()
                     global_step = 0
-                if self.use_fresca:
-                    X = self.run_steps_unfused(X, global_step)
-                else:
-                    X = self.run_steps(X, global_step, batch_idx=batch_idx)
+                X = self.run_steps(X, global_step, batch_idx=batch_idx)
                 global_step += n_steps
                 if tail is not None:
                     X = tail(X)
-                all_samples.append(X.cpu())
+                all_samples.append(X.cpu() if to_host else X)
         return torch.cat(all_samples, dim=0)
 
     def sample_prior(self, batch_size: int, batch_idx: int = 0) -> torch.Tensor:
@@ -147,9 +155,11 @@ class DiffusionSampler:
 
     def run_steps_unfused(self, X: torch.Tensor, global_step0: int = 0,
                           noise: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """The reference's own per-step loop (sampler.py:157-210) over ``reverse_diffusion_step``: used when the
-        FreSca filter sits between the score model and the SDE update.  Still no host synchronisation beyond
-        the ``.item()`` calls the mirrored API makes on host-side tensors."""
+        """The reference's own per-step loop (sampler.py:157-210) over ``reverse_diffusion_step``: one Python
+        iteration per step over the same kernels.  ``sample`` does not use it (FreSca included, the loop is the fused
+        ``ffd_sample_steps`` call of ``run_steps``); it is kept as the step-by-step form of the public API and as the
+        cross-check of the fused loop in the tests.  The shared timestep is passed as a host float, so there is no
+        ``.item()`` on a device tensor."""
         model = self.score_model
         dev = model.device
         X = X.to(device=dev, dtype=torch.float32).contiguous()
@@ -166,7 +176,7 @@ class DiffusionSampler:
                 cache.current_step = gs
                 recompute = cache.determine_recompute_set(x_tilde=None, event_intensity=0.1, step=gs)
             X = self.reverse_diffusion_step(batch, step=step_idx, recompute_tokens=recompute,
-                                            noise=None if noise is None else noise[step_idx])
+                                            noise=None if noise is None else noise[step_idx], t=t)
         return X
 
     def step_tables(self, global_step0: int):
@@ -222,6 +232,28 @@ class DiffusionSampler:
             # the device-decided schedule: K/V rows live with the first cache of the model
             event = cache.event_args(model.dims.d_model)
             a.event = C.pointer(event)
+        fresca_keep = None
+        if self.use_fresca:
+            # FreSca between score and SDE update (sampler.py:79-93) inside the fused loop: the time-dependent
+            # high-band scale is a per-step host table, both cut-off strategies are decided on the device
+            from .fourier import transform_matrix
+            from .fresca import dynamic_high_scale
+
+            L, Cn = self.max_len, self.n_channels
+            fr = _lib.FrescaArgs()
+            U, V = transform_matrix(L, False, dev), transform_matrix(L, True, dev)
+            scratch = torch.empty(lib.ffd_fresca_scratch_floats(B, L, Cn) + 2 * B * L * Cn, device=dev,
+                                  dtype=torch.float32)
+            num_steps = getattr(self, "_num_diffusion_steps", None)
+            hs = (C.c_float * n)(*[dynamic_high_scale(self.fresca_high_scale, float(t), num_steps)
+                                   for t in sched.timesteps.tolist()])
+            fr.U, fr.V, fr.scratch = _lib.ptr(U), _lib.ptr(V), _lib.ptr(scratch)
+            fr.high_scale_host = hs
+            fr.low_scale = float(self.fresca_low_scale)
+            fr.cutoff_ratio = float(self.fresca_cutoff_ratio)
+            fr.strategy = 1 if self.fresca_cutoff_strategy == "energy" else 0
+            a.fresca = C.pointer(fr)
+            fresca_keep = (fr, U, V, scratch, hs)
         x_tmp = torch.empty_like(X)
         a.x = _lib.ptr(X)
         a.x_tmp = _lib.ptr(x_tmp)
@@ -250,6 +282,7 @@ class DiffusionSampler:
                 a.noise_step0 = s0
                 a.step_begin, a.step_end = s0, s1
                 _lib.check(lib.ffd_sample_steps(a, st))
+        del fresca_keep
         if cache is not None:
             owner = model._kv_owner
             for i in range(step_begin, step_end):

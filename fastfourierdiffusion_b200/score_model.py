@@ -194,10 +194,42 @@ class ScoreModule(nn.Module):
             a.v_cache = _lib.ptr(own._v_store)
         return a
 
+    # -- checkpoints ------------------------------------------------------------------
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, precision: Optional[str] = None,
+                             **_lightning_kwargs) -> "ScoreModule":
+        """A reference (PyTorch-Lightning) checkpoint -> ScoreModule, like ``LightningModule.load_from_checkpoint``
+        as cmd/sample.py:71-74 calls it: the constructor arguments come from the checkpoint's
+        ``hyper_parameters`` (score_models.py:72 ``save_hyperparameters``: shape, d_model / num_layers / n_head,
+        ``fourier_noise_scaling`` and the pickled noise scheduler -- VP or VE with its own constants), the weights
+        from its ``state_dict``.  Lightning / omegaconf / the reference package need not be installed: their
+        classes are unpickled as plain containers and ``fdiff.schedulers.sde.*`` as this package's schedulers."""
+        from .checkpoint import load_lightning_checkpoint
+
+        ckpt = load_lightning_checkpoint(checkpoint_path)
+        hp = dict(ckpt.get("hyper_parameters") or {})
+        missing = [k for k in ("n_channels", "max_len", "noise_scheduler") if k not in hp]
+        if missing:
+            raise _lib.FFDError(f"{checkpoint_path}: hyper_parameters lack {missing}; not a ScoreModule checkpoint")
+        sched = hp["noise_scheduler"]
+        if not isinstance(sched, SDE):
+            raise NotImplementedError(f"Scheduler {sched!r} not implemented yet, cannot set time encoder.")
+        known = ("n_channels", "max_len", "fourier_noise_scaling", "d_model", "num_layers", "n_head",
+                 "num_training_steps", "lr_max", "likelihood_weighting")
+        kwargs = {k: hp[k] for k in known if k in hp}
+        model = cls(noise_scheduler=sched, precision=precision, **kwargs)
+        sd = {k: v for k, v in ckpt["state_dict"].items() if not k.startswith("cached_backbone")}
+        model.load_state_dict(sd, strict=True)
+        if getattr(sched, "G", None) is None:
+            sched.set_noise_scaling(model.max_len)
+        return model
+
     # -- the reference surface --------------------------------------------------------
     def forward(self, batch: DiffusableBatch, recompute_tokens: Optional[Set[int]] = None, step: int = 0,
-                return_crf: bool = False) -> Union[torch.Tensor, Tuple[torch.Tensor, Optional[torch.Tensor]]]:
-        """score_models.py:79-119.  One timestep per batch (the sampler's contract, sampler.py:59-60)."""
+                return_crf: bool = False, t: Optional[float] = None
+                ) -> Union[torch.Tensor, Tuple[torch.Tensor, Optional[torch.Tensor]]]:
+        """score_models.py:79-119.  One timestep per batch (the sampler's contract, sampler.py:59-60); ``t`` (extra,
+        optional) gives it as a host float, which skips the device-side equality check and its synchronisation."""
         X = batch.X
         assert X.size()[1:] == (self.max_len, self.n_channels), (
             f"X has wrong shape, should be {(X.size(0), self.max_len, self.n_channels)}, but is {X.size()}")
@@ -208,9 +240,18 @@ class ScoreModule(nn.Module):
             raise _lib.FFDError("ScoreModule.forward needs the model on a CUDA device (no CPU fallback)")
         X = X.to(device=dev, dtype=torch.float32).contiguous()
         B = X.shape[0]
-        if B > 0 and not bool(torch.min(timesteps) == torch.max(timesteps)):
-            raise _lib.FFDError("the CUDA score model evaluates one shared timestep per batch (sampler.py:59-60)")
-        te = self.time_embedding(timesteps[:1]) if B > 0 else torch.zeros(1, self.d_model, device=dev)
+        if self.use_cache and recompute_tokens is not None and self.cache is not None \
+                and getattr(self.cache, "event_driven", False):
+            raise NotImplementedError(
+                "event_driven=True decides the recompute set on the device inside the fused step loop "
+                "(DiffusionSampler.sample / run_steps -> ffd_sample_steps); the per-step forward would silently reuse "
+                "stale sample-0 K/V rows, so it is refused")
+        if t is not None:
+            te = self.time_embedding(torch.tensor([t], dtype=torch.float32))
+        else:
+            if B > 0 and not bool(torch.min(timesteps) == torch.max(timesteps)):
+                raise _lib.FFDError("the CUDA score model evaluates one shared timestep per batch (sampler.py:59-60)")
+            te = self.time_embedding(timesteps[:1]) if B > 0 else torch.zeros(1, self.d_model, device=dev)
         a = self.forward_args(B)
         a.X = _lib.ptr(X)
         a.time_emb = _lib.ptr(te)

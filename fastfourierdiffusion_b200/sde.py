@@ -56,7 +56,8 @@ class SDE:
 
     def G_device(self, device: torch.device) -> torch.Tensor:
         assert self.G is not None, "call set_noise_scaling(max_len) first"
-        if self._G_dev is None or self._G_dev.device != device:
+        cached = getattr(self, "_G_dev", None)  # absent on a scheduler unpickled from a reference checkpoint
+        if cached is None or cached.device != device:
             self._G_dev = self.G.to(device=device, dtype=torch.float32).contiguous()
         return self._G_dev
 

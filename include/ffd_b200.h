@@ -162,6 +162,13 @@ int ffd_score_forward(const ffd_forward_args* a, ffd_stream_t stream);
 int ffd_ffn_ln(const ffd_dims* dims, int precision, const float* weights, const void* packed, int layer,
                const float* x, float* y, float* scratch, int64_t M, ffd_stream_t stream);
 
+/* y = LayerNorm1(x + out_proj(softmax(q K_c^T / sqrt(hd)) V_c)) of one PURE-CACHE encoder layer on M token rows
+ * (cached_transformer.py:228-258,309-321): K_c/V_c are the sample-0 cache rows [NL, H, L, hd] shared by the batch.
+ * x, y: [M, d] fp32 (y may alias x for FFD_PREC_BF16); workspace as for ffd_score_forward with B = ceil(M / L). */
+int ffd_attn_cached_ln(const ffd_dims* dims, int precision, const float* weights, const void* packed, int layer,
+                       const float* k_cache, const float* v_cache, const float* x, float* y, void* workspace,
+                       int64_t workspace_bytes, int64_t M, ffd_stream_t stream);
+
 /* ---- SDE ------------------------------------------------------------------ */
 typedef struct ffd_step_coef {
   int32_t kind;     /* FFD_SDE_* */
@@ -173,13 +180,6 @@ typedef struct ffd_step_coef {
 
 /* x_out = x - drift*dt + sqrt_dt*(coef*G)*z, same rounding order as sde.py:228-244 / :143-163.
  * z == NULL: z is drawn in-kernel, Philox-4x32-10 keyed (seed, stream_id), element index = counter. */
-/* y = LayerNorm1(x + out_proj(softmax(q K_c^T / sqrt(hd)) V_c)) of one PURE-CACHE encoder layer on M token rows
- * (cached_transformer.py:228-258,309-321): K_c/V_c are the sample-0 cache rows [NL, H, L, hd] shared by the batch.
- * x, y: [M, d] fp32 (y may alias x for FFD_PREC_BF16); workspace as for ffd_score_forward with B = ceil(M / L). */
-int ffd_attn_cached_ln(const ffd_dims* dims, int precision, const float* weights, const void* packed, int layer,
-                       const float* k_cache, const float* v_cache, const float* x, float* y, void* workspace,
-                       int64_t workspace_bytes, int64_t M, ffd_stream_t stream);
-
 int ffd_sde_step(const ffd_step_coef* c, const float* G, const float* x, const float* score, const float* z,
                  uint64_t seed, uint64_t stream_id, float* x_out, int64_t B, int L, int C, ffd_stream_t stream);
 int ffd_prior(const float* G, const float* z, uint64_t seed, uint64_t stream_id, float scale, float* x_out,
@@ -227,6 +227,18 @@ int ffd_event_refresh_kv(const ffd_dims* dims, const float* weights, int layer, 
                          float* k_cache, float* v_cache, ffd_stream_t stream);
 
 /* ---- the step loop -------------------------------------------------------- */
+/* FreSca between the score model and the SDE update of every step (sampler.py:79-93), inside the fused loop: no host
+ * synchronisation, both cut-off strategies decided on the device. */
+typedef struct ffd_fresca_args {
+  const float* U;        /* ffd_dft_matrix(L, 0) */
+  const float* V;        /* ffd_dft_matrix(L, 1) */
+  float* scratch;        /* DEVICE, ffd_fresca_scratch_floats(B, L, C) + 2 * B * L * C floats (raw + filtered score) */
+  const float* high_scale_host; /* [n_steps] HOST array: the time-dependent high-band scale (fresca.py:243-256) */
+  float low_scale;
+  float cutoff_ratio;
+  int32_t strategy;      /* 0 spatial, 1 energy */
+} ffd_fresca_args;
+
 typedef struct ffd_sample_args {
   ffd_forward_args fwd;        /* X is updated in place; score may be NULL */
   const float* G;              /* [L] */
@@ -242,6 +254,8 @@ typedef struct ffd_sample_args {
   float* x_tmp;                /* [B, L, C] scratch */
   int32_t step_begin, step_end;
   const ffd_event_args* event; /* HOST struct or NULL: device-decided schedule for cached steps with n_own_host == 0 */
+  const ffd_fresca_args* fresca; /* HOST struct or NULL: filter the score of every step (a step whose scales are both
+                                    1 is left alone, fresca.py:150-152) */
 } ffd_sample_args;
 
 int ffd_sample_steps(const ffd_sample_args* a, ffd_stream_t stream);

@@ -72,6 +72,14 @@ def load_reference():
     src = os.path.join(REFERENCE_ROOT, "src")
     if src not in sys.path:
         sys.path.insert(0, src)
+    # The upstream ``fdiff`` is a namespace package (no top-level __init__.py); this repository's drop-in ``fdiff``
+    # package (a regular package) would win the import whatever the path order.  Bind the name to the upstream
+    # directory explicitly, dropping any already-imported drop-in modules.
+    for name in [m for m in sys.modules if m == "fdiff" or m.startswith("fdiff.")]:
+        del sys.modules[name]
+    pkg = types.ModuleType("fdiff")
+    pkg.__path__ = [os.path.join(src, "fdiff")]
+    sys.modules["fdiff"] = pkg
     from fdiff.models.score_models import ScoreModule  # type: ignore
     from fdiff.sampling.sampler import DiffusionSampler  # type: ignore
     from fdiff.schedulers.sde import VEScheduler, VPScheduler  # type: ignore

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fastfourierdiffusion_b200.distributed import gather_samples, sample_sharded, shard_bounds
+from fastfourierdiffusion_b200.distributed import gather_samples, sample_sharded, shard_bounds, warm_communicator
 
 
 def test_shard_bounds_cover_exactly_once():
@@ -33,6 +33,8 @@ def _worker(rank, world, port, n, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        warm_communicator(torch.device("cpu"))
+
         def fake_sampler(n_local, r):
             b, _ = shard_bounds(n, world, r)
             # sample i of the global batch is filled with the value i: the gather must restore the order
@@ -45,6 +47,9 @@ def _worker(rank, world, port, n, out_dir):
         b, e = shard_bounds(n, world, rank)
         again = gather_samples(full[b:e].clone(), n)
         assert torch.equal(again, full)
+        # ... and into a preallocated result
+        pre = torch.full((n, 5, 2), -1.0)
+        assert gather_samples(full[b:e].clone(), n, out=pre) is pre and torch.equal(pre, full)
         torch.save(full, os.path.join(out_dir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()

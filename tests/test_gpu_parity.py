@@ -573,11 +573,22 @@ def test_tiny_sampler_trace_with_fresca(prec):
         Xn = s.reverse_diffusion_step(F.DiffusableBatch(X=X, timesteps=ts), step=i, recompute_tokens=S,
                                       noise=torch.from_numpy(g["step_z"][i]).cuda())
         assert rel(Xn.cpu().numpy(), g["keep_Xn"][i]) < TOL[prec]["step"], i
-    # free run through the public loop
+    # free run through the FUSED loop (ffd_sample_steps with ffd_fresca_args: what sample() calls) ...
     X0 = m.noise_scheduler.prior_from_noise(torch.from_numpy(g["prior_z"]))
     m.cache.reset()
-    out = s.run_steps_unfused(X0, 0, noise=torch.from_numpy(g["step_z"]).cuda())
-    assert rel(out.cpu().numpy(), g["final"]) < TOL[prec]["traj"]
+    from fastfourierdiffusion_b200 import _lib
+
+    lib = _lib.load()
+    n0 = lib.ffd_launch_count()
+    out = s.run_steps(X0, 0, noise=torch.from_numpy(g["step_z"]).cuda())
+    assert lib.ffd_launch_count() > n0
+    err = rel(out.cpu().numpy(), g["final"])
+    print(f"fresca fused free run [{prec}]: rel {err:.2e}")
+    assert err < TOL[prec]["traj"]
+    # ... and through the step-by-step form of the public API: same kernels, same values
+    m.cache.reset()
+    out2 = s.run_steps_unfused(X0, 0, noise=torch.from_numpy(g["step_z"]).cuda())
+    assert rel(out2.cpu().numpy(), out.cpu().numpy()) < (1e-6 if prec == "fp32" else TOL[prec]["traj"])
 
 
 @pytest.mark.parametrize("tag", ["tiny", "ecg", "sat", "nasa"])

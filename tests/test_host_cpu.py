@@ -140,23 +140,6 @@ def test_no_cpu_fallback():
         F.DiffusionSampler(m, 2).sample(2, 4)
 
 
-def test_cli_overrides_and_checkpoint_lookup(tmp_path):
-    from fastfourierdiffusion_b200.cli import DATASET_SHAPES, SAMPLE_DEFAULTS, find_checkpoint, parse_overrides
-
-    cfg = parse_overrides(["num_samples=7", "use_cache=true", "cache_kwargs={'K': 3, 'R': 20}",
-                           "sampler.sample_batch_size=4", "datamodule=nasdaq"], SAMPLE_DEFAULTS)
-    assert cfg["num_samples"] == 7 and cfg["use_cache"] is True and cfg["cache_kwargs"] == {"K": 3, "R": 20}
-    assert cfg["sampler.sample_batch_size"] == 4 and DATASET_SHAPES[cfg["datamodule"]] == (252, 5)
-    with pytest.raises(SystemExit):
-        parse_overrides(["nope=1"], SAMPLE_DEFAULTS)
-    d = tmp_path / "abc" / "checkpoints"
-    d.mkdir(parents=True)
-    for name in ("epoch=3-val_loss=0.52.ckpt", "epoch=9-val_loss=0.31.ckpt", "last.ckpt"):
-        (d / name).write_bytes(b"")
-    assert find_checkpoint(str(tmp_path), "abc").endswith("epoch=9-val_loss=0.31.ckpt")
-    assert find_checkpoint(str(tmp_path), None) is None
-
-
 def test_event_driven_cache_kwargs_and_schedule():
     """event_driven is an extra, default-off constructor argument: the index schedule is untouched without it, only
     the full step stays host-scheduled with it, and R must be positive."""
