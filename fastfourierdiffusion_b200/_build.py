@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libffd_b200.so")
-SOURCES = ["ffd_api.cu", "ffd_simt.cu", "ffd_metrics.cu", "ffd_event.cu", "ffd_tc.cu", "ffd_tc_attn.cu"]
+SOURCES = ["ffd_api.cu", "ffd_simt.cu", "ffd_metrics.cu", "ffd_event.cu", "ffd_tc.cu", "ffd_tc_attn.cu", "ffd_tc_layer.cu"]
 
 
 def _nvcc() -> str:
@@ -28,21 +28,24 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = "") -> str:
+    """``out`` (or FFD_LIB_OUT): write a VARIANT build somewhere else (A/B timing, stamp builds) instead of the product
+    library; select it at run time with FFD_LIB."""
+    out = out or os.environ.get("FFD_LIB_OUT", "")
+    if not out and not force and not needs_build():
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     cmd += os.environ.get("FFD_NVCC_FLAGS", "").split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out or LIB]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

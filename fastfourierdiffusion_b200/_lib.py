@@ -26,7 +26,7 @@ EXPORTS = [
     "ffd_version", "ffd_last_error", "ffd_weights_count", "ffd_layer_stride", "ffd_layer0_offset",
     "ffd_packed_bytes", "ffd_pack_weights", "ffd_workspace_bytes", "ffd_has_tensor_path",
     "ffd_dft_matrix", "ffd_dft_apply", "ffd_posemb_renorm", "ffd_time_embedding", "ffd_score_forward",
-    "ffd_sde_step", "ffd_prior", "ffd_philox_normal", "ffd_sample_steps", "ffd_ffn_ln", "ffd_launch_count", "ffd_attn_cached_ln", "ffd_fresca", "ffd_fresca_scratch_floats", "ffd_event_intensity",
+    "ffd_sde_step", "ffd_prior", "ffd_philox_normal", "ffd_sample_steps", "ffd_ffn_ln", "ffd_launch_count", "ffd_attn_cached_ln", "ffd_layer_cached_ln", "ffd_fresca", "ffd_fresca_scratch_floats", "ffd_event_intensity",
     "ffd_event_decide", "ffd_event_refresh_kv",
     "ffd_metric_project", "ffd_metric_sort_rows", "ffd_metric_w2_sorted", "ffd_metric_row_std", "ffd_spectral_density",
 ]
@@ -128,6 +128,7 @@ def load() -> C.CDLL:
     lib.ffd_metric_row_std.argtypes = [vp, i32, i64, vp, vp]
     lib.ffd_spectral_density.argtypes = [vp, vp, i64, i32, i32, vp]
     lib.ffd_attn_cached_ln.argtypes = [pd, i32, vp, vp, i32, vp, vp, vp, vp, vp, i64, i64, vp]
+    lib.ffd_layer_cached_ln.argtypes = [pd, i32, vp, vp, i32, vp, vp, vp, vp, vp, i64, i64, vp]
     for n in EXPORTS:
         f = getattr(lib, n)
         if f.restype is C.c_int:  # default: int-returning status

@@ -44,8 +44,12 @@ static int run_layer(const ffd_forward_args& a, const Arena& ar, const Workspace
   float* vc = a.v_cache ? a.v_cache + (int64_t)layer * H * L * hd : nullptr;
   int rc;
   // branch: 0 = stock attention (all K/V own), 1 = pure cache, 2 = mixed
+  if (branch == 1 && a.precision == FFD_PREC_BF16 && tc_layer_enabled(m)) {
+    // pure-cache layer on tensor cores, ONE launch: attention block and FFN block overlapped on every SM
+    return tc_layer_cached(m, a.packed, ws.kvimg96, a.weights, layer, ws.h, ws.h, M, s);
+  }
   if (branch == 1 && a.precision == FFD_PREC_BF16 && tc_attn_supported(m)) {
-    // pure-cache layer on tensor cores: attention block and FFN block, two launches
+    // the same as two launches (models the fused kernel is not instantiated for, or FFD_FUSED_LAYER=0)
     if ((rc = tc_attn_cached(m, tc_attn_image(m, a.packed, layer), ws.kvimg, a.weights, layer, ws.h, ws.h, M, s)))
       return rc;
     return tc_ffn_ln(m, a.packed, a.weights, layer, ws.h, ws.h, M, s);
@@ -134,7 +138,10 @@ static int forward_hidden(const ffd_forward_args& a, const Arena& ar, const Work
   if (tc_images && !event_refresh) {
     // the fp32 cache is the source of truth (it may have been reset or refreshed since the last
     // call); its bf16 operand images are 1.5 MB, so they are simply rebuilt every pure-cache step
-    if ((rc = tc_pack_kv(m, a.k_cache, a.v_cache, ws.kvimg, s))) return rc;
+    const bool fused = branch == 1 && tc_layer_enabled(m);
+    if (fused ? (rc = tc_pack_kv96(m, a.k_cache, a.v_cache, ws.kvimg96, s))
+              : (rc = tc_pack_kv(m, a.k_cache, a.v_cache, ws.kvimg, s)))
+      return rc;
   }
   for (int l = 0; l < m.n_layers; ++l) {
     if (event_refresh) {
@@ -144,7 +151,9 @@ static int forward_hidden(const ffd_forward_args& a, const Arena& ar, const Work
                                         a.k_cache + (int64_t)l * H * L * hd, a.v_cache + (int64_t)l * H * L * hd, L, d,
                                         H, s)))
         return rc;
-      if (tc_images && (rc = tc_pack_kv_layer(m, l, a.k_cache, a.v_cache, ws.kvimg, s))) return rc;
+      if (tc_images && (tc_layer_enabled(m) ? (rc = tc_pack_kv96_layer(m, l, a.k_cache, a.v_cache, ws.kvimg96, s))
+                                            : (rc = tc_pack_kv_layer(m, l, a.k_cache, a.v_cache, ws.kvimg, s))))
+        return rc;
     }
     if ((rc = run_layer(a, ar, ws, l, branch, s))) return rc;
     if (populate) {
@@ -209,6 +218,8 @@ extern "C" {
 void ffd_debug_set_attn_stamps(long long* dev_buf) { ffd::g_attn_dbg = dev_buf; }
 // test / A-B hook (not part of the ABI header): 1 = FFN on CTA pairs, 0 = one-CTA kernel, -1 = FFD_FFN_CTA2 / default
 void ffd_debug_set_ffn_pairs(int mode) { ffd::tc_debug_set_ffn_pairs(mode); }
+// 1 = pure-cache layers as ONE fused kernel, 0 = attention + FFN kernels, -1 = FFD_FUSED_LAYER / default (off)
+void ffd_debug_set_fused_layer(int mode) { ffd::tc_debug_set_fused_layer(mode); }
 int ffd_version(void) { return 1; }
 uint64_t ffd_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 const char* ffd_last_error(void) { return g_err; }
@@ -393,6 +404,37 @@ int ffd_attn_cached_ln(const ffd_dims* dims, int precision, const float* weights
   if ((rc = launch_attention(ws.qkv, 3 * d, kc, vc, nullptr, 0, ws.attn, B, L, d, H, s))) return rc;
   if ((rc = launch_linear(ws.attn, d, w + ar.out_w, d, w + ar.out_b, ws.tmp, d, M, d, d, 0, s))) return rc;
   return launch_add_ln(x, ws.tmp, w + ar.n1w, w + ar.n1b, y, M, d, s);
+}
+
+int ffd_layer_cached_ln(const ffd_dims* dims, int precision, const float* weights, const void* packed, int layer,
+                        const float* k_cache, const float* v_cache, const float* x, float* y, void* workspace,
+                        int64_t workspace_bytes, int64_t M, ffd_stream_t stream) {
+  FFD_CHECK_ARG(dims && weights && k_cache && v_cache && x && y && workspace && M >= 0, "bad ffd_layer_cached_ln arguments");
+  int rc = check_dims(*dims);
+  if (rc) return rc;
+  const ffd_dims& m = *dims;
+  FFD_CHECK_ARG(layer >= 0 && layer < m.n_layers, "layer %d out of range", layer);
+  FFD_CHECK_ARG(M % m.max_len == 0, "M must be a whole number of samples (M %% max_len == 0)");
+  if (precision == FFD_PREC_BF16 && tc_layer_enabled(m)) {
+    FFD_CHECK_ARG(packed != nullptr, "FFD_PREC_BF16 needs the packed weight image");
+    const int64_t B = M / m.max_len;
+    if (workspace_bytes < ffd_workspace_bytes(dims, B, precision)) {
+      set_error("workspace too small");
+      return FFD_ERR_WORKSPACE;
+    }
+    if (M == 0) return FFD_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Workspace ws = carve(m, B, workspace, lean_workspace(m, precision));
+    if ((rc = tc_pack_kv96(m, k_cache, v_cache, ws.kvimg96, s))) return rc;
+    return tc_layer_cached(m, packed, ws.kvimg96, weights, layer, x, y, M, s);
+  }
+  // everything else: the attention block, then the FFN block (y doubles as the intermediate)
+  if ((rc = ffd_attn_cached_ln(dims, precision, weights, packed, layer, k_cache, v_cache, x, y, workspace,
+                               workspace_bytes, M, stream)))
+    return rc;
+  if (precision == FFD_PREC_BF16) return ffd_ffn_ln(dims, precision, weights, packed, layer, y, y, nullptr, M, stream);
+  const Workspace ws = carve(m, M / m.max_len, workspace, false);
+  return ffd_ffn_ln(dims, precision, weights, packed, layer, y, y, ws.tmp, M, stream);
 }
 
 int ffd_sde_step(const ffd_step_coef* c, const float* G, const float* x, const float* score, const float* z,

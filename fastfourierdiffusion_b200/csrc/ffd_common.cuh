@@ -93,6 +93,7 @@ struct Workspace {
   float* kvtmp; // [L, 2d] sample-0 K/V of a full step
   void* kvimg;  // bf16 K/V operand images of the cache for the tcgen05 attention kernel
   void* kvimg_own;  // the same per sample (stock attention on the tcgen05 kernel)
+  void* kvimg96;    // the cache images again in chunks of 96 keys (fused layer kernel)
   int64_t bytes;
 };
 
@@ -123,6 +124,8 @@ static inline Workspace carve(const ffd_dims& m, int64_t B, void* base, bool lea
   // [min(B, OWN_CHUNK), H, NCH] x (K image + V image): 64 bytes per key slot
   const int64_t own = B < OWN_CHUNK ? B : OWN_CHUNK;
   w.kvimg_own = take(own * m.n_head * attn_key_chunks(m.max_len) * attn_chunk_keys(m.max_len) * 16);
+  // [NL, H, ceil(L / 96)] x (K image [96 x 16] bf16 + V image [16 x 96] fp16)
+  w.kvimg96 = take((int64_t)m.n_layers * m.n_head * ((m.max_len + 95) / 96) * 96 * 16);
   w.bytes = o;
   return w;
 }

@@ -88,4 +88,20 @@ int tc_attn_own(const ffd_dims& m, const void* attn_img, void* kvimg_own, const 
                 int v_off, const float* weights, int layer, const float* x, float* y, int64_t M, cudaStream_t s,
                 const void* kvimg_shared = nullptr, int n_prefix = 0, const int32_t* own_mask = nullptr);
 
+// per-layer pieces of the packed weight image
+const void* tc_ffn_image(const ffd_dims& m, const void* packed, int layer);       // W1 / W2 128-wide slice images
+const void* tc_ffn_half_image(const ffd_dims& m, const void* packed, int layer);  // the same as per-CTA halves
+
+// ffd_tc_layer.cu: ONE kernel per pure-cache layer (attention block + FFN block, MUFU and tensor pipe overlapped)
+bool tc_layer_supported(const ffd_dims& m);
+bool tc_layer_enabled(const ffd_dims& m);   // supported and not switched off (FFD_FUSED_LAYER=0)
+void tc_debug_set_fused_layer(int mode);
+int64_t tc_kv96_image_bytes(const ffd_dims& m);
+// K/V operand images in chunks of 96 keys (the fused kernel's virtual heads), all layers / one layer
+int tc_pack_kv96(const ffd_dims& m, const float* kc, const float* vc, void* kvimg96, cudaStream_t s);
+int tc_pack_kv96_layer(const ffd_dims& m, int layer, const float* kc, const float* vc, void* kvimg96, cudaStream_t s);
+// y = LN2(y1 + FFN(y1)), y1 = LN1(x + cached attention(x)); y may alias x
+int tc_layer_cached(const ffd_dims& m, const void* packed, const void* kvimg96, const float* weights, int layer,
+                    const float* x, float* y, int64_t M, cudaStream_t s);
+
 }  // namespace ffd

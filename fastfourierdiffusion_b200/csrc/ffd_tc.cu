@@ -959,6 +959,14 @@ int64_t tc_packed_bytes(const ffd_dims& m) {
   return layer_image_bytes(m) * m.n_layers;
 }
 
+const void* tc_ffn_image(const ffd_dims& m, const void* packed, int layer) {
+  return (const uint8_t*)packed + (size_t)layer * layer_image_bytes(m);
+}
+
+const void* tc_ffn_half_image(const ffd_dims& m, const void* packed, int layer) {
+  return (const uint8_t*)packed + (size_t)layer * layer_image_bytes(m) + halves_offset(m);
+}
+
 const void* tc_attn_image(const ffd_dims& m, const void* packed, int layer) {
   return (const uint8_t*)packed + (size_t)layer * layer_image_bytes(m) + tc_ffn_image_bytes(m);
 }

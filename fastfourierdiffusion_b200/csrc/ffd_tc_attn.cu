@@ -1215,6 +1215,27 @@ int tc_pack_kv_layer(const ffd_dims& m, int layer, const float* kc, const float*
   return FFD_OK;
 }
 
+// the same images in chunks of 96 keys (virtual heads of the fused layer kernel, ffd_tc_layer.cu)
+int tc_pack_kv96(const ffd_dims& m, const float* kc, const float* vc, void* kvimg96, cudaStream_t s) {
+  const AttnGeom g = attn_geom(m);
+  const int NCH = (m.max_len + 95) / 96;
+  tc::pack_kv_kernel<<<148, 256, 0, s>>>(kc, vc, (uint16_t*)kvimg96, m.n_layers * m.n_head, m.max_len, g.hd, m.n_head,
+                                         g.G, NCH, 96);
+  FFD_CHECK_LAUNCH("pack_kv_kernel");
+  return FFD_OK;
+}
+
+int tc_pack_kv96_layer(const ffd_dims& m, int layer, const float* kc, const float* vc, void* kvimg96, cudaStream_t s) {
+  const AttnGeom g = attn_geom(m);
+  const int NCH = (m.max_len + 95) / 96;
+  const int64_t cache_off = (int64_t)layer * m.n_head * m.max_len * g.hd;
+  const int64_t img_off = (int64_t)layer * m.n_head * NCH * 2 * 96 * tc::HP;  // 16-bit elements
+  tc::pack_kv_kernel<<<16, 256, 0, s>>>(kc + cache_off, vc + cache_off, (uint16_t*)kvimg96 + img_off, m.n_head,
+                                        m.max_len, g.hd, m.n_head, g.G, NCH, 96);
+  FFD_CHECK_LAUNCH("pack_kv_kernel");
+  return FFD_OK;
+}
+
 long long* g_attn_dbg = nullptr;  // optional device buffer of clock64 stamps (profiling aid)
 
 template <int DP, int KQ>

@@ -52,6 +52,28 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     if (++polls > (1u << 24)) __trap();
   }
 }
+// Wait for several mbarriers AT ONCE: every lane polls its own barrier (shared-memory address + parity; lanes without
+// a barrier of their own pass a copy of another lane's).  A try_wait round trip costs ~150 cycles even when the phase
+// is already complete, and an MMA-issuing warp pays them back to back -- measured: three waits in a row were half
+// of an issue loop that has to turn around in less than the tensor pipe needs for the MMAs it issues.  Safe as long
+// as none of the barriers can complete a SECOND phase before this warp moves on (each lane latches its result).
+__device__ __forceinline__ void mbar_wait_lanes(uint32_t bar_addr, uint32_t parity) {
+  uint32_t done = 0, polls = 0;
+  for (;;) {
+    if (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar_addr), "r"(parity), "r"(20000u)
+          : "memory");
+    }
+    if (__all_sync(0xffffffffu, done != 0)) break;
+    if (++polls > (1u << 24)) __trap();
+  }
+}
+
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -314,6 +336,80 @@ __device__ __forceinline__ void umma_ss_chain(uint32_t d, uint64_t ad, uint32_t 
   } else if constexpr (NK == 1) {
     asm volatile(FFD_SS_HEAD "}" FFD_SS_ARGS);
   }
+}
+
+// ---- whole issue steps of the fused layer kernel under ONE election (ffd_tc_layer.cu) -------------------------
+// FFN step:  Y += relu(H_b)[tmem a2 + 8 i] . W2[desc w2 + i * s2], i < 4   (accumulating)
+//            commit -> e2 (W2 slot free)  [, commit -> yf if `last`]
+//            if `more`:  H_b = X[tmem x + 8 i] . W1[desc w1 + i * s1], i < 5;  commit -> hf (H_b ready), e1 (W1 slot free)
+#ifdef FFD_L_NO_FFN_MMA
+#define FFD_FQ "qx"
+#define FFD_FQM "qx"
+#else
+#define FFD_FQ "q"
+#define FFD_FQM "qm"
+#endif
+#ifdef FFD_L_NO_ATTN_MMA
+#define FFD_AE "ex"
+#define FFD_AEM "ex"
+#else
+#define FFD_AE "e"
+#define FFD_AEM "em"
+#endif
+__device__ __forceinline__ void ffn_issue_step(uint32_t y, uint32_t a2, uint64_t w2, uint32_t s2, uint32_t idesc2,
+                                               uint32_t e2, uint32_t yf, uint32_t last, uint32_t more, uint32_t h,
+                                               uint32_t x, uint64_t w1, uint32_t s1, uint32_t idesc1, uint32_t hf,
+                                               uint32_t e1) {
+  asm volatile(
+      "{\n\t.reg .pred q, ql, qm, qx;\n\tsetp.ne.b32 qx, 0, 0;\n\t.reg .b32 ra;\n\t.reg .b64 bd, bs;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.and.b32 ql, %7, 0, q;\n\t"
+      "setp.ne.and.b32 qm, %8, 0, q;\n\t"
+      "mov.b32 ra, %1;\n\tmov.b64 bd, %2;\n\tcvt.u64.u32 bs, %3;\n\t"
+      "@" FFD_FQ " tcgen05.mma.cta_group::1.kind::f16 [%0], [ra], bd, %4, 1;\n\t"
+      "add.u32 ra, ra, 8;\n\tadd.u64 bd, bd, bs;\n\t@" FFD_FQ " tcgen05.mma.cta_group::1.kind::f16 [%0], [ra], bd, %4, 1;\n\t"
+      "add.u32 ra, ra, 8;\n\tadd.u64 bd, bd, bs;\n\t@" FFD_FQ " tcgen05.mma.cta_group::1.kind::f16 [%0], [ra], bd, %4, 1;\n\t"
+      "add.u32 ra, ra, 8;\n\tadd.u64 bd, bd, bs;\n\t@" FFD_FQ " tcgen05.mma.cta_group::1.kind::f16 [%0], [ra], bd, %4, 1;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+      "@ql tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+      "mov.b32 ra, %10;\n\tmov.b64 bd, %11;\n\tcvt.u64.u32 bs, %12;\n\t"
+      "@" FFD_FQM " tcgen05.mma.cta_group::1.kind::f16 [%9], [ra], bd, %13, 0;\n\t"
+      "add.u32 ra, ra, 8;\n\tadd.u64 bd, bd, bs;\n\t@" FFD_FQM " tcgen05.mma.cta_group::1.kind::f16 [%9], [ra], bd, %13, 1;\n\t"
+      "add.u32 ra, ra, 8;\n\tadd.u64 bd, bd, bs;\n\t@" FFD_FQM " tcgen05.mma.cta_group::1.kind::f16 [%9], [ra], bd, %13, 1;\n\t"
+      "add.u32 ra, ra, 8;\n\tadd.u64 bd, bd, bs;\n\t@" FFD_FQM " tcgen05.mma.cta_group::1.kind::f16 [%9], [ra], bd, %13, 1;\n\t"
+      "add.u32 ra, ra, 8;\n\tadd.u64 bd, bd, bs;\n\t@" FFD_FQM " tcgen05.mma.cta_group::1.kind::f16 [%9], [ra], bd, %13, 1;\n\t"
+      "@qm tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%14];\n\t"
+      "@qm tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%15];\n\t}" ::"r"(y),
+      "r"(a2), "l"(w2), "r"(s2), "r"(idesc2), "r"(e2), "r"(yf), "r"(last), "r"(more), "r"(h), "r"(x), "l"(w1), "r"(s1),
+      "r"(idesc1), "r"(hf), "r"(e1)
+      : "memory");
+}
+// Attention step:  O_g = P[tmem p + 48 g + 8 j] . V[desc v + (3 g + j) * sv], g < 2, j < 3   (two accumulators, o and o + 16)
+//                  commit -> of (O ready), ve (V slot free)
+//                  if `more`:  S = Q[desc q] . K[desc k] into tmem sd;  commit -> sf (scores ready), ke (K slot free)
+__device__ __forceinline__ void attn_issue_step(uint32_t o, uint32_t p, uint64_t v, uint32_t sv, uint32_t idesc_pv,
+                                                uint32_t of, uint32_t ve, uint32_t more, uint32_t sd, uint64_t q,
+                                                uint64_t k, uint32_t idesc_s, uint32_t sf, uint32_t ke) {
+  asm volatile(
+      "{\n\t.reg .pred e, em, ex;\n\tsetp.ne.b32 ex, 0, 0;\n\t.reg .b32 ra, rd;\n\t.reg .b64 bd, bs;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.and.b32 em, %7, 0, e;\n\t"
+      "mov.b32 ra, %1;\n\tmov.b32 rd, %0;\n\tmov.b64 bd, %2;\n\tcvt.u64.u32 bs, %3;\n\t"
+      "@" FFD_AE " tcgen05.mma.cta_group::1.kind::f16 [rd], [ra], bd, %4, 0;\n\t"
+      "add.u32 ra, ra, 8;\n\tadd.u64 bd, bd, bs;\n\t@" FFD_AE " tcgen05.mma.cta_group::1.kind::f16 [rd], [ra], bd, %4, 1;\n\t"
+      "add.u32 ra, ra, 8;\n\tadd.u64 bd, bd, bs;\n\t@" FFD_AE " tcgen05.mma.cta_group::1.kind::f16 [rd], [ra], bd, %4, 1;\n\t"
+      "add.u32 ra, ra, 32;\n\tadd.u32 rd, rd, 16;\n\tadd.u64 bd, bd, bs;\n\t"
+      "@" FFD_AE " tcgen05.mma.cta_group::1.kind::f16 [rd], [ra], bd, %4, 0;\n\t"
+      "add.u32 ra, ra, 8;\n\tadd.u64 bd, bd, bs;\n\t@" FFD_AE " tcgen05.mma.cta_group::1.kind::f16 [rd], [ra], bd, %4, 1;\n\t"
+      "add.u32 ra, ra, 8;\n\tadd.u64 bd, bd, bs;\n\t@" FFD_AE " tcgen05.mma.cta_group::1.kind::f16 [rd], [ra], bd, %4, 1;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+      "@" FFD_AEM " tcgen05.mma.cta_group::1.kind::f16 [%8], %9, %10, %11, 0;\n\t"
+      "@em tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t"
+      "@em tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%13];\n\t}" ::"r"(o),
+      "r"(p), "l"(v), "r"(sv), "r"(idesc_pv), "r"(of), "r"(ve), "r"(more), "r"(sd), "l"(q), "l"(k), "r"(idesc_s),
+      "r"(sf), "r"(ke)
+      : "memory");
 }
 
 #define FFD_TMEM_ST16(taddr, r)                                                                                     \

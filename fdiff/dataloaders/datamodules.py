@@ -92,8 +92,29 @@ class ECGDatamodule(Datamodule):
 
 
 class SyntheticDatamodule(Datamodule):
+    """datamodules.py:244-303: sine waves with random phase and Beta(2, 2) frequency -- the one dataset of the
+    reference that is generated rather than downloaded, so it is generated here too (same process; the reference
+    draws from the unseeded global numpy generator, here the generator is seeded with ``random_seed``)."""
+
     dataset_name = "synthetic"
     shape_key = "synthetic"
+
+    def __init__(self, *args: Any, max_len: int = 100, num_samples: int = 1000, **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
+        self.max_len = max_len
+        self.num_samples = num_samples
+
+    def setup(self, stage: str = "fit") -> None:
+        import numpy as np
+
+        rng = np.random.RandomState(self.random_seed)
+        n = 2 * self.num_samples
+        phase = rng.normal(size=n).reshape(-1, 1)
+        frequency = rng.beta(a=2, b=2, size=n).reshape(-1, 1)
+        X = np.sin(np.arange(self.max_len) * frequency + phase)
+        self.X_train = torch.tensor(X[: self.num_samples], dtype=torch.float32).unsqueeze(2)
+        self.X_test = torch.tensor(X[self.num_samples:], dtype=torch.float32).unsqueeze(2)
+        self.synthetic = True
 
 
 class MIMICIIIDatamodule(Datamodule):

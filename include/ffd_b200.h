@@ -169,6 +169,15 @@ int ffd_attn_cached_ln(const ffd_dims* dims, int precision, const float* weights
                        const float* k_cache, const float* v_cache, const float* x, float* y, void* workspace,
                        int64_t workspace_bytes, int64_t M, ffd_stream_t stream);
 
+/* One whole PURE-CACHE encoder layer, y = LayerNorm2(y1 + FFN(y1)) with y1 the result of ffd_attn_cached_ln
+ * (cached_transformer.py:228-258,309-327): the two blocks back to back.  With FFD_FUSED_LAYER=1 (opt-in, default model
+ * width only) FFD_PREC_BF16 runs it as ONE kernel that overlaps the MUFU-bound softmax with the tensor-bound FFN GEMMs
+ * per SM -- correct, but hand-off-latency bound and slower than the two kernels on B200, hence
+ * not the default.  x, y: [M, d] fp32 (y may alias x for FFD_PREC_BF16). */
+int ffd_layer_cached_ln(const ffd_dims* dims, int precision, const float* weights, const void* packed, int layer,
+                        const float* k_cache, const float* v_cache, const float* x, float* y, void* workspace,
+                        int64_t workspace_bytes, int64_t M, ffd_stream_t stream);
+
 /* ---- SDE ------------------------------------------------------------------ */
 typedef struct ffd_step_coef {
   int32_t kind;     /* FFD_SDE_* */

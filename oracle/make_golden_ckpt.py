@@ -26,7 +26,7 @@ from oracle import ref_harness as rh  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "ref_run")
 MODEL_ID = "tinyve01"
-DIMS = dict(n_channels=2, max_len=16, d_model=12, num_layers=2, n_head=2)
+DIMS = dict(n_channels=1, max_len=16, d_model=12, num_layers=2, n_head=2)
 
 TRAIN_CONFIG = """random_seed: 42
 fourier_transform: true
@@ -53,6 +53,8 @@ datamodule:
   fourier_transform: ${fourier_transform}
   standardize: ${standardize}
   batch_size: 64
+  max_len: 16
+  num_samples: 64
 """
 
 

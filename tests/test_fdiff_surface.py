@@ -90,7 +90,7 @@ def test_run_directory_and_checkpoint_loading(tmp_path):
     model = F.ScoreModule.load_from_checkpoint(run["checkpoint"])
     assert isinstance(model.noise_scheduler, F.VEScheduler) and model.noise_scheduler.sigma_max == 2.0
     d = model.dims
-    assert (d.max_len, d.n_channels, d.d_model, d.n_head, d.n_layers) == (16, 2, 12, 2, 2)
+    assert (d.max_len, d.n_channels, d.d_model, d.n_head, d.n_layers) == (16, 1, 12, 2, 2)
     assert model.scale_noise is True and model.noise_scheduler.G is not None
     # a model id that has no run directory / no config / no checkpoint raises like the reference (cmd/sample.py:38-59)
     with pytest.raises(FileNotFoundError):
@@ -134,6 +134,6 @@ def test_sample_entry_point_with_trained_run(tmp_path):
     mod.main([f"model_path={RUN_ROOT}", "model_id=tinyve01", "num_samples=4", "num_diffusion_steps=6",
               "sampler.sample_batch_size=4", "precision=fp32", f"output_dir={out}"])
     X = torch.load(out / "samples.pt")
-    assert X.shape == (4, 16, 2) and torch.isfinite(X).all()
+    assert X.shape == (4, 16, 1) and torch.isfinite(X).all()
     with pytest.raises(FileNotFoundError):
         mod.main([f"model_path={RUN_ROOT}", "model_id=absent", f"output_dir={out}"])

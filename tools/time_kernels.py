@@ -47,7 +47,12 @@ def ffn():
     _lib.check(lib.ffd_ffn_ln(model.dims, 1, _lib.ptr(arena), _lib.ptr(packed), 3, _lib.ptr(x), _lib.ptr(y), None, M, st))
 
 
-for name, fn in (("attn", attn), ("ffn", ffn)):
+def layer():
+    _lib.check(lib.ffd_layer_cached_ln(model.dims, 1, _lib.ptr(arena), _lib.ptr(packed), 3, _lib.ptr(kc), _lib.ptr(vc),
+                                       _lib.ptr(x), _lib.ptr(y), _lib.ptr(ws), ws.numel() * ws.element_size(), M, st))
+
+
+for name, fn in (("attn", attn), ("ffn", ffn), ("layer", layer)):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
