@@ -357,6 +357,9 @@ def run_ours(args):
     e2e_sampler = F.DiffusionSampler(model, SB, use_cache=True, cache_kwargs={}, noise="torch")
     Ke = min(K, args.e2e_steps) if args.e2e_steps > 0 else K
     gather_ms = None
+    if args.sweep:
+        return finish_sweep_line(args, world, rank, B, SB, n_chunks, K, W, value, ms_per_step, ms_step0, ms_rest, launches,
+                                 clocks, strong, X, dev)
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
@@ -397,7 +400,7 @@ def run_ours(args):
     xbuf = torch.randn(M, ECG["d_model"], device=dev)
     ybuf = torch.empty_like(xbuf)
     scratch = torch.empty_like(xbuf) if args.precision == "fp32" else None
-    prec = 1 if args.precision == "bf16" else 0
+    prec = 1 if args.precision == "fp16" else 0
     st = _lib.stream_handle(dev)
 
     def ffn():
@@ -420,7 +423,7 @@ def run_ours(args):
     # second kernel of a pure-cache layer: the attention block.  It is bound by MUFU.EX2 (one exponential per
     # (token, head, key): 16 lanes/clk/SM), not by HBM or the tensor pipe, so it gets its own informational entry.
     attn_entry = None
-    if args.precision == "bf16":
+    if args.precision == "fp16":
         kc, vc = model.cache._k_store, model.cache._v_store
         wsb = model.workspace(Bk)
 
@@ -447,7 +450,7 @@ def run_ours(args):
                       "frac": n_exp / (attn_ms * 1e-3) / mufu_peak, "ms_per_launch": attn_ms,
                       "tensor_tflops_algorithmic": attn_flops / (attn_ms * 1e-3) / 1e12,
                       "peak_source": "148 SMs x 16 MUFU lanes x SM clock under load"}
-    peak = pk["bf16"] if args.precision == "bf16" else 72.0  # fp32 FMA peak: 148 SMs x 128 lanes x 2 x 1.9 GHz
+    peak = pk["bf16"] if args.precision == "fp16" else 72.0  # fp32 FMA peak: 148 SMs x 128 lanes x 2 x 1.9 GHz
     # DRAM traffic per launch comes from an ncu --set full capture (it cannot be measured inside a timed run): the
     # committed summary of that capture, valid for the ECG M it was taken at; labelled as static
     traffic, traffic_source = None, None
@@ -495,7 +498,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None,
-        "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
+        "dtype": "f16" if args.precision == "fp16" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "noise": "Philox in-kernel",
                    "batch_per_gpu": B, "global_batch": world * B, "sampler_batch": SB,
                    "sampler_batches_per_gpu": n_chunks, "schedule_steps_timed": f"0..{K - 1}",
@@ -515,7 +518,7 @@ def run_ours(args):
                         "per rank DiffusionSampler.sample_on_device() (host prior noise -> H2D -> steps) -> ONE NCCL "
                         "all_gather_into_tensor of the samples -> D2H of [world*B, L, C] on rank 0, all timed")},
         "gpu_launches": launches,
-        "roofline": {"kernel": FFN_KERNEL_NAME if args.precision == "bf16" else "ffn_kernel+add_ln_kernel",
+        "roofline": {"kernel": FFN_KERNEL_NAME if args.precision == "fp16" else "ffn_kernel+add_ln_kernel",
                      "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source, "peak_source": pk["src"] + " (burst)",
                      "flops_per_launch": ffn_flops, "ms_per_launch": ffn_ms,
@@ -524,6 +527,46 @@ def run_ours(args):
         "cpu_baseline": cpu,
     }
     emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def finish_sweep_line(args, world, rank, B, SB, n_chunks, K, W, value, ms_per_step, ms_step0, ms_rest, launches, clocks,
+                      strong, X, dev):
+    """--sweep: the device-resident throughput and (N > 1) the final NCCL gather only -- one short JSON line per
+    configuration for tools/sweep.py (profiles/r2_sweep.json).  No e2e / roofline / CPU legs: those belong to the
+    driver's bench line of the default workload."""
+    import torch
+    import torch.distributed as dist
+
+    gather_ms = None
+    if world > 1:
+        from fastfourierdiffusion_b200.distributed import gather_samples
+
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        g0.record()
+        allX = gather_samples(X, world * X.shape[0])
+        g1.record()
+        torch.cuda.synchronize()
+        gm = torch.tensor([g0.elapsed_time(g1)], device=dev)
+        dist.all_reduce(gm, op=dist.ReduceOp.MAX)
+        gather_ms = float(gm.item())
+        assert allX.shape[0] == world * X.shape[0]
+        del allX
+    if rank == 0:
+        flops = sum(flops_per_sample_step(0 if i else ECG["max_len"]) for i in range(K)) * B
+        emit({"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+              "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+              "dtype": "f16" if args.precision == "fp16" else "f32", "data": "synthetic",
+              "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B, "sampler_batch": SB,
+                         "sampler_batches_per_gpu": n_chunks, "ms_step0_full_recompute": ms_step0,
+                         "ms_per_step_after_step0": ms_rest, "final_gather_ms": gather_ms,
+                         "gathered_samples_per_rank": int(X.shape[0]),
+                         "step_frac_of_sustained_bf16_peak": (flops / (ms_per_step * K * 1e-3) / 1e12
+                                                              / peaks()["bf16_sustained"]) if args.precision == "fp16" else None},
+              "clocks": clocks.summary(), "gpu_launches": launches})
     if world > 1:
         dist.destroy_process_group()
 
@@ -540,12 +583,16 @@ def main():
     ap.add_argument("--sampler-batch", type=int, default=0,
                     help="> 0: samples per sampler batch (sample_batch_size); a GPU's batch runs in chunks of this size")
     ap.add_argument("--workload", default="ecg", choices=sorted(SHAPES))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"],
+                    help="fp16: tcgen05 GEMMs on fp16 operands, fp32 accumulate (bf16 = its former name); fp32: CUDA cores")
     ap.add_argument("--e2e-steps", type=int, default=0, help="cap the steps of the e2e leg (0 = same as --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="short line: device-resident throughput (+ final gather) only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     set_workload(args.workload)
+    if args.precision == "bf16":
+        args.precision = "fp16"
     claim_stdout()
     if args.impl == "reference":
         run_reference(args)

@@ -18,7 +18,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 # the in-tree product file
 LIB_PATH = os.environ.get("FFD_LIB") or os.path.join(_PKG, "libffd_b200.so")
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_FP16 = 0, 1
+PREC_BF16 = PREC_FP16  # former name (the tensor-core operands were bf16 until they became fp16)
 SDE_VP, SDE_VE = 0, 1
 MODE_STOCK, MODE_CACHED = 0, 1
 

@@ -20,7 +20,7 @@ void count_launch() { __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED); }
 
 // every branch of this model runs on the tensor-core kernels: no fp32 staging buffers are needed (carve)
 static bool lean_workspace(const ffd_dims& m, int precision) {
-  return precision == FFD_PREC_BF16 && tc_attn_supported(m) && tc_attn_own_fused(m);
+  return precision == FFD_PREC_FP16 && tc_attn_supported(m) && tc_attn_own_fused(m);
 }
 
 static int check_dims(const ffd_dims& m) {
@@ -32,7 +32,7 @@ static int check_dims(const ffd_dims& m) {
   return FFD_OK;
 }
 
-// one encoder layer, fp32 arithmetic (FFD_PREC_BF16 swaps in the tcgen05 FFN)
+// one encoder layer, fp32 arithmetic (FFD_PREC_FP16 swaps in the tcgen05 FFN)
 //   x = LN1(x + MHA(x));  x = LN2(x + FFN(x))      cached_transformer.py:123-134 / :309-327
 static int run_layer(const ffd_forward_args& a, const Arena& ar, const Workspace& ws, int layer, int branch,
                      cudaStream_t s) {
@@ -44,17 +44,17 @@ static int run_layer(const ffd_forward_args& a, const Arena& ar, const Workspace
   float* vc = a.v_cache ? a.v_cache + (int64_t)layer * H * L * hd : nullptr;
   int rc;
   // branch: 0 = stock attention (all K/V own), 1 = pure cache, 2 = mixed
-  if (branch == 1 && a.precision == FFD_PREC_BF16 && tc_layer_enabled(m)) {
+  if (branch == 1 && a.precision == FFD_PREC_FP16 && tc_layer_enabled(m)) {
     // pure-cache layer on tensor cores, ONE launch: attention block and FFN block overlapped on every SM
     return tc_layer_cached(m, a.packed, ws.kvimg96, a.weights, layer, ws.h, ws.h, M, s);
   }
-  if (branch == 1 && a.precision == FFD_PREC_BF16 && tc_attn_supported(m)) {
+  if (branch == 1 && a.precision == FFD_PREC_FP16 && tc_attn_supported(m)) {
     // the same as two launches (models the fused kernel is not instantiated for, or FFD_FUSED_LAYER=0)
     if ((rc = tc_attn_cached(m, tc_attn_image(m, a.packed, layer), ws.kvimg, a.weights, layer, ws.h, ws.h, M, s)))
       return rc;
     return tc_ffn_ln(m, a.packed, a.weights, layer, ws.h, ws.h, M, s);
   }
-  if ((branch == 0 || branch == 2) && a.precision == FFD_PREC_BF16 && tc_attn_supported(m)) {
+  if ((branch == 0 || branch == 2) && a.precision == FFD_PREC_FP16 && tc_attn_supported(m)) {
     // stock attention (all K/V own) on the same tensor-core kernel: K/V projection + per-sample operand images
     // (one tcgen05 kernel; fp32 projection + pack kernel for head dims > 7), attention block, FFN block.  Q is
     // projected inside the attention kernel.  Mixed branch (2): the same, with the key rows outside the recompute
@@ -96,7 +96,7 @@ static int run_layer(const ffd_forward_args& a, const Arena& ar, const Workspace
   if ((rc = launch_attention(ws.qkv, 3 * d, kc, vc, mask, n_prefix, ws.attn, a.B, L, d, H, s))) return rc;
   if ((rc = launch_linear(ws.attn, d, w + ar.out_w, d, w + ar.out_b, ws.tmp, d, M, d, d, 0, s))) return rc;
   if ((rc = launch_add_ln(ws.h, ws.tmp, w + ar.n1w, w + ar.n1b, ws.h, M, d, s))) return rc;
-  if (a.precision == FFD_PREC_BF16) {
+  if (a.precision == FFD_PREC_FP16) {
     if ((rc = tc_ffn_ln(m, a.packed, a.weights, layer, ws.h, ws.h, M, s))) return rc;
   } else {
     if ((rc = launch_ffn(ws.h, w + ar.w1, w + ar.b1, w + ar.w2, w + ar.b2, ws.tmp, M, d, F, s))) return rc;
@@ -133,7 +133,7 @@ static int forward_hidden(const ffd_forward_args& a, const Arena& ar, const Work
     return rc;
   int populate = 0;
   const int branch = pick_branch(a, &populate);
-  const bool tc_images = (branch == 1 || branch == 2) && a.precision == FFD_PREC_BF16 && tc_attn_supported(m);
+  const bool tc_images = (branch == 1 || branch == 2) && a.precision == FFD_PREC_FP16 && tc_attn_supported(m);
   const bool event_refresh = ev && branch == 1;
   if (tc_images && !event_refresh) {
     // the fp32 cache is the source of truth (it may have been reset or refreshed since the last
@@ -184,9 +184,9 @@ static int check_forward(const ffd_forward_args& a) {
   if (rc) return rc;
   FFD_CHECK_ARG(a.B >= 0, "negative batch");
   FFD_CHECK_ARG(a.weights && a.workspace && a.X && a.time_emb, "null pointer in ffd_forward_args");
-  FFD_CHECK_ARG(a.precision == FFD_PREC_FP32 || a.precision == FFD_PREC_BF16, "unknown precision %d", a.precision);
-  if (a.precision == FFD_PREC_BF16) {
-    FFD_CHECK_ARG(a.packed != nullptr, "FFD_PREC_BF16 needs the packed weight image");
+  FFD_CHECK_ARG(a.precision == FFD_PREC_FP32 || a.precision == FFD_PREC_FP16, "unknown precision %d", a.precision);
+  if (a.precision == FFD_PREC_FP16) {
+    FFD_CHECK_ARG(a.packed != nullptr, "FFD_PREC_FP16 needs the packed weight image");
     if (!tc_supported(a.dims)) {
       set_error("tensor-core path unsupported for these dims (needs d_model <= 80, d_ff %% 128 == 0)");
       return FFD_ERR_UNSUPPORTED;
@@ -351,8 +351,8 @@ int ffd_ffn_ln(const ffd_dims* dims, int precision, const float* weights, const 
   FFD_CHECK_ARG(layer >= 0 && layer < dims->n_layers, "layer %d out of range", layer);
   if (M == 0) return FFD_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  if (precision == FFD_PREC_BF16) {
-    FFD_CHECK_ARG(packed != nullptr, "FFD_PREC_BF16 needs the packed weight image");
+  if (precision == FFD_PREC_FP16) {
+    FFD_CHECK_ARG(packed != nullptr, "FFD_PREC_FP16 needs the packed weight image");
     if (!tc_supported(*dims)) {
       set_error("tensor-core path unsupported for these dims");
       return FFD_ERR_UNSUPPORTED;
@@ -388,8 +388,8 @@ int ffd_attn_cached_ln(const ffd_dims* dims, int precision, const float* weights
   const Arena ar = arena_of(m);
   const Workspace ws = carve(m, B, workspace, lean_workspace(m, precision));
   const float* w = weights + ar.layer0 + (int64_t)layer * ar.layer_stride;
-  if (precision == FFD_PREC_BF16) {
-    FFD_CHECK_ARG(packed != nullptr, "FFD_PREC_BF16 needs the packed weight image");
+  if (precision == FFD_PREC_FP16) {
+    FFD_CHECK_ARG(packed != nullptr, "FFD_PREC_FP16 needs the packed weight image");
     if (!tc_attn_supported(m)) {
       set_error("tensor-core attention unsupported for these dims");
       return FFD_ERR_UNSUPPORTED;
@@ -415,8 +415,8 @@ int ffd_layer_cached_ln(const ffd_dims* dims, int precision, const float* weight
   const ffd_dims& m = *dims;
   FFD_CHECK_ARG(layer >= 0 && layer < m.n_layers, "layer %d out of range", layer);
   FFD_CHECK_ARG(M % m.max_len == 0, "M must be a whole number of samples (M %% max_len == 0)");
-  if (precision == FFD_PREC_BF16 && tc_layer_enabled(m)) {
-    FFD_CHECK_ARG(packed != nullptr, "FFD_PREC_BF16 needs the packed weight image");
+  if (precision == FFD_PREC_FP16 && tc_layer_enabled(m)) {
+    FFD_CHECK_ARG(packed != nullptr, "FFD_PREC_FP16 needs the packed weight image");
     const int64_t B = M / m.max_len;
     if (workspace_bytes < ffd_workspace_bytes(dims, B, precision)) {
       set_error("workspace too small");
@@ -432,7 +432,7 @@ int ffd_layer_cached_ln(const ffd_dims* dims, int precision, const float* weight
   if ((rc = ffd_attn_cached_ln(dims, precision, weights, packed, layer, k_cache, v_cache, x, y, workspace,
                                workspace_bytes, M, stream)))
     return rc;
-  if (precision == FFD_PREC_BF16) return ffd_ffn_ln(dims, precision, weights, packed, layer, y, y, nullptr, M, stream);
+  if (precision == FFD_PREC_FP16) return ffd_ffn_ln(dims, precision, weights, packed, layer, y, y, nullptr, M, stream);
   const Workspace ws = carve(m, M / m.max_len, workspace, false);
   return ffd_ffn_ln(dims, precision, weights, packed, layer, y, y, ws.tmp, M, stream);
 }

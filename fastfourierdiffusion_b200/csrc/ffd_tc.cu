@@ -287,8 +287,8 @@ ffn_ln_tc_kernel(const float* x, float* y /* may alias x */, const uint8_t* __re
         } else if (c == d) {
           v.x = 1.f, v.y = 1.f;
         }
-        xp[2 * i] = pack_bf16(v.x, v.y);
-        xp[2 * i + 1] = pack_bf16(v.z, v.w);
+        xp[2 * i] = pack_op(v.x, v.y);
+        xp[2 * i + 1] = pack_op(v.z, v.w);
       }
       if (np > 0) {
         mbar_wait_relaxed(&x_free[s], (np - 1) & 1, 20);  // the previous pair's last GEMM1 has read X_s
@@ -420,7 +420,7 @@ ffn_ln_tc_kernel(const float* x, float* y /* may alias x */, const uint8_t* __re
       FFD_TMEM_LD16(hcol + 48, (r + 48));
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 32; ++e) pk[e] = relu_pack_bf16(r[2 * e], r[2 * e + 1]);
+      for (int e = 0; e < 32; ++e) pk[e] = relu_pack_op(r[2 * e], r[2 * e + 1]);
       // 64 fp32 columns -> 32 packed columns at the start of this group's own half
       FFD_TMEM_ST16(hcol, pk);
       FFD_TMEM_ST16(hcol + 16, (pk + 16));
@@ -725,8 +725,8 @@ ffn_ln_tc2_kernel(const float* x, float* y /* may alias x */, const uint8_t* __r
         } else if (c == d) {
           v.x = 1.f, v.y = 1.f;
         }
-        xp[2 * i] = pack_bf16(v.x, v.y);
-        xp[2 * i + 1] = pack_bf16(v.z, v.w);
+        xp[2 * i] = pack_op(v.x, v.y);
+        xp[2 * i + 1] = pack_op(v.z, v.w);
       }
       if (np > 0) {
         mbar_wait_relaxed(&x_free[s], (np - 1) & 1, 20);  // the previous pair's last GEMM1 has read X_s
@@ -858,7 +858,7 @@ ffn_ln_tc2_kernel(const float* x, float* y /* may alias x */, const uint8_t* __r
       FFD_TMEM_LD16(hcol + 48, (r + 48));
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 32; ++e) pk[e] = relu_pack_bf16(r[2 * e], r[2 * e + 1]);
+      for (int e = 0; e < 32; ++e) pk[e] = relu_pack_op(r[2 * e], r[2 * e + 1]);
       // 64 fp32 columns -> 32 packed columns at the start of this group's own half
       FFD_TMEM_ST16(hcol, pk);
       FFD_TMEM_ST16(hcol + 16, (pk + 16));
@@ -879,7 +879,7 @@ ffn_ln_tc2_kernel(const float* x, float* y /* may alias x */, const uint8_t* __r
 // Per layer: n_chunks W1 images [128 n x DP k] then n_chunks W2 images [DP n x 128 k], bf16, K-major
 // core-matrix order: byte(n, k) = (n/8)*128 + (k/8)*(rows*16) + (n%8)*16 + (k%8)*2.
 __global__ void pack_ffn_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
-                                const float* __restrict__ W2, __nv_bfloat16* __restrict__ out, int d, int F, int DP) {
+                                const float* __restrict__ W2, op16* __restrict__ out, int d, int F, int DP) {
   const int n_chunks = F / CHUNK;
   const int64_t per_img = (int64_t)CHUNK * DP;
   const int64_t total = 2 * n_chunks * per_img;
@@ -900,22 +900,22 @@ __global__ void pack_ffn_kernel(const float* __restrict__ W1, const float* __res
       if (k < d) {
         v = W1[(int64_t)f * d + k];
       } else if (k == d) {
-        v = __bfloat162float(__float2bfloat16_rn(b1[f]));
+        v = round_op(b1[f]);
       } else if (k == d + 1) {
-        v = b1[f] - __bfloat162float(__float2bfloat16_rn(b1[f]));
+        v = b1[f] - round_op(b1[f]);
       }
     } else {
       const int f = j * CHUNK + k;  // n = output feature, k = hidden unit inside the slice
       if (n < d) v = W2[(int64_t)n * F + f];
     }
-    out[i] = __float2bfloat16_rn(v);
+    out[i] = to_op(v);
   }
 }
 
 // Per-CTA halves of the weight slices for the CTA-pair kernel, from the full images: per slice j two W1 halves
 // [64 n x DP k] (rows 64 r .. 64 r + 63 of the slice) and two W2 halves [DP/2 n x 128 k] (output features DP/2 r ..),
 // each a self-contained K-major core-matrix image.
-__global__ void pack_ffn_halves_kernel(const __nv_bfloat16* __restrict__ full, __nv_bfloat16* __restrict__ out, int F,
+__global__ void pack_ffn_halves_kernel(const op16* __restrict__ full, op16* __restrict__ out, int F,
                                        int DP) {
   const int n_chunks = F / CHUNK;
   const int64_t per_img = (int64_t)CHUNK * DP;
@@ -977,11 +977,11 @@ int tc_pack_weights(const ffd_dims& m, const float* weights, void* packed, cudaS
   for (int l = 0; l < m.n_layers; ++l) {
     const float* w = weights + ar.layer0 + (int64_t)l * ar.layer_stride;
     tc::pack_ffn_kernel<<<256, 256, 0, s>>>(w + ar.w1, w + ar.b1, w + ar.w2,
-                                            (__nv_bfloat16*)((uint8_t*)packed + l * layer_image_bytes(m)),
+                                            (tc::op16*)((uint8_t*)packed + l * layer_image_bytes(m)),
                                             m.d_model, m.d_ff, DP);
     FFD_CHECK_LAUNCH("pack_ffn_kernel");
-    __nv_bfloat16* full = (__nv_bfloat16*)((uint8_t*)packed + l * layer_image_bytes(m));
-    tc::pack_ffn_halves_kernel<<<256, 256, 0, s>>>(full, (__nv_bfloat16*)((uint8_t*)full + halves_offset(m)), m.d_ff, DP);
+    tc::op16* full = (tc::op16*)((uint8_t*)packed + l * layer_image_bytes(m));
+    tc::pack_ffn_halves_kernel<<<256, 256, 0, s>>>(full, (tc::op16*)((uint8_t*)full + halves_offset(m)), m.d_ff, DP);
     FFD_CHECK_LAUNCH("pack_ffn_halves_kernel");
   }
   if (tc_attn_supported(m)) return tc_pack_attn(m, weights, packed, layer_image_bytes(m), tc_ffn_image_bytes(m), s);

@@ -354,8 +354,8 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     uint8_t* ob = smem + sm.obf;
     // constant columns of the out-proj operand: d, d+1 = 1 (bias hi/lo), the rest of the padding = 0
     for (int c = d; c < DP; ++c)
-      *reinterpret_cast<__nv_bfloat16*>(ob + row_off + (c >> 3) * (TILE_M * 16) + (c & 7) * 2) =
-          __float2bfloat16_rn((c == d || c == d + 1) ? 1.f : 0.f);
+      *reinterpret_cast<op16*>(ob + row_off + (c >> 3) * (TILE_M * 16) + (c & 7) * 2) =
+          to_op((c == d || c == d + 1) ? 1.f : 0.f);
     uint32_t n = 0;
     for (uint32_t t = 0; t < my_tiles; ++t) {
       for (int h = 0; h < H; ++h) {
@@ -404,8 +404,8 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
           for (int j = 0; j < 7; ++j) {
             if (j < hd) {
               const int col = h * hd + j;
-              *reinterpret_cast<__nv_bfloat16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
-                  __float2bfloat16_rn(acc[j] * inv);
+              *reinterpret_cast<op16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                  to_op(acc[j] * inv);
             }
           }
         } else {
@@ -450,8 +450,8 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
           for (int j = 0; j < HP - 1; ++j) {
             if (j < hd) {
               const int col = h * hd + j;
-              *reinterpret_cast<__nv_bfloat16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
-                  __float2bfloat16_rn(acc[j] * inv);
+              *reinterpret_cast<op16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                  to_op(acc[j] * inv);
             }
           }
         }
@@ -494,14 +494,14 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     // 16 fp32 accumulator columns -> two bf16 k-groups of the Q operand
     auto store_q16 = [&](const uint32_t (&r)[16], uint8_t* dst) {
       uint4 q0, q1;
-      q0.x = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));
-      q0.y = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
-      q0.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));
-      q0.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
-      q1.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));
-      q1.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
-      q1.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13]));
-      q1.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
+      q0.x = pack_op(__uint_as_float(r[0]), __uint_as_float(r[1]));
+      q0.y = pack_op(__uint_as_float(r[2]), __uint_as_float(r[3]));
+      q0.z = pack_op(__uint_as_float(r[4]), __uint_as_float(r[5]));
+      q0.w = pack_op(__uint_as_float(r[6]), __uint_as_float(r[7]));
+      q1.x = pack_op(__uint_as_float(r[8]), __uint_as_float(r[9]));
+      q1.y = pack_op(__uint_as_float(r[10]), __uint_as_float(r[11]));
+      q1.z = pack_op(__uint_as_float(r[12]), __uint_as_float(r[13]));
+      q1.w = pack_op(__uint_as_float(r[14]), __uint_as_float(r[15]));
       *reinterpret_cast<uint4*>(dst) = q0;
       *reinterpret_cast<uint4*>(dst + TILE_M * 16) = q1;
     };
@@ -531,10 +531,10 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
           b4.x = 1.f, b4.y = 1.f;
         }
         uint4 q;
-        q.x = pack_bf16(a.x, a.y);
-        q.y = pack_bf16(a.z, a.w);
-        q.z = pack_bf16(b4.x, b4.y);
-        q.w = pack_bf16(b4.z, b4.w);
+        q.x = pack_op(a.x, a.y);
+        q.y = pack_op(a.z, a.w);
+        q.z = pack_op(b4.x, b4.y);
+        q.w = pack_op(b4.z, b4.w);
         *reinterpret_cast<uint4*>(xo + row_off + kg * (TILE_M * 16)) = q;
       }
       fence_proxy_async();
@@ -734,7 +734,7 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
 // columns d, d+1.   bf16 core-matrix order.
 __global__ void pack_attn_kernel(const float* __restrict__ in_w, const float* __restrict__ in_b,
                                  const float* __restrict__ out_w, const float* __restrict__ out_b,
-                                 __nv_bfloat16* __restrict__ wq, __nv_bfloat16* __restrict__ wo, int d, int H, int DP,
+                                 op16* __restrict__ wq, op16* __restrict__ wo, int d, int H, int DP,
                                  int G, int QN) {
   const int hd = d / H;
   const float scale = 1.4426950408889634f / sqrtf((float)hd);
@@ -755,16 +755,16 @@ __global__ void pack_attn_kernel(const float* __restrict__ in_w, const float* __
         const int r = h * hd + c;
         const float b = in_b[r] * scale;
         if (k < d) v = in_w[r * d + k] * scale;
-        else if (k == d) v = __bfloat162float(__float2bfloat16_rn(b));
-        else if (k == d + 1) v = b - __bfloat162float(__float2bfloat16_rn(b));
+        else if (k == d) v = round_op(b);
+        else if (k == d + 1) v = b - round_op(b);
       }
     } else if (n < d) {
       const float b = out_b[n];
       if (k < d) v = out_w[n * d + k];
-      else if (k == d) v = __bfloat162float(__float2bfloat16_rn(b));
-      else if (k == d + 1) v = b - __bfloat162float(__float2bfloat16_rn(b));
+      else if (k == d) v = round_op(b);
+      else if (k == d + 1) v = b - round_op(b);
     }
-    (is_o ? wo : wq)[e] = __float2bfloat16_rn(v);
+    (is_o ? wo : wq)[e] = to_op(v);
   }
 }
 
@@ -775,7 +775,7 @@ __global__ void pack_attn_kernel(const float* __restrict__ in_w, const float* __
 //   WvP [8 H n x DP k]:  row 8 h + c = Wv[h hd + c, :] (c < hd); row 8 h + 7 picks the constant-1 column of X (the
 //       row-sum slot of the V image).
 __global__ void pack_kvproj_kernel(const float* __restrict__ in_w, const float* __restrict__ in_b,
-                                   __nv_bfloat16* __restrict__ wk, __nv_bfloat16* __restrict__ wv, int d, int H,
+                                   op16* __restrict__ wk, op16* __restrict__ wv, int d, int H,
                                    int DP, int G, int QN) {
   const int hd = d / H, NK = QN, NVR = 8 * H;
   const int total = (NK + NVR) * DP;
@@ -798,10 +798,10 @@ __global__ void pack_kvproj_kernel(const float* __restrict__ in_w, const float* 
     if (r >= 0) {
       const float b = in_b[r];
       if (k < d) v = in_w[(int64_t)r * d + k];
-      else if (k == d) v = __bfloat162float(__float2bfloat16_rn(b));
-      else if (k == d + 1) v = b - __bfloat162float(__float2bfloat16_rn(b));
+      else if (k == d) v = round_op(b);
+      else if (k == d + 1) v = b - round_op(b);
     }
-    (is_v ? wv : wk)[e] = __float2bfloat16_rn(v);
+    (is_v ? wv : wk)[e] = to_op(v);
   }
 }
 
@@ -863,10 +863,10 @@ kv_own_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wkimg,
       if ((lane & 1) == 0) {
         const int trow = warp * 32 + r;
         uint4 pk;
-        pk.x = pack_bf16(a.x, a.y);
-        pk.y = pack_bf16(a.z, a.w);
-        pk.z = pack_bf16(b4.x, b4.y);
-        pk.w = pack_bf16(b4.z, b4.w);
+        pk.x = pack_op(a.x, a.y);
+        pk.y = pack_op(a.z, a.w);
+        pk.z = pack_op(b4.x, b4.y);
+        pk.w = pack_op(b4.z, b4.w);
         *reinterpret_cast<uint4*>(xo + (uint32_t)(trow >> 3) * 128 + (uint32_t)(trow & 7) * 16 +
                                   (c4 >> 1) * (TILE_M * 16)) = pk;
       }
@@ -877,7 +877,7 @@ kv_own_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wkimg,
     const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
     for (int kg = d >> 3; kg < DP / 8; ++kg) {
       uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-      if (kg == (d >> 3) && valid) pk.x = pack_bf16(1.f, 1.f);
+      if (kg == (d >> 3) && valid) pk.x = pack_op(1.f, 1.f);
       *reinterpret_cast<uint4*>(xo + row_off + kg * (TILE_M * 16)) = pk;
     }
   } else {
@@ -895,10 +895,10 @@ kv_own_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wkimg,
         else if (c + 4 == d) b4.x = 1.f, b4.y = 1.f;
       }
       uint4 q;
-      q.x = pack_bf16(a.x, a.y);
-      q.y = pack_bf16(a.z, a.w);
-      q.z = pack_bf16(b4.x, b4.y);
-      q.w = pack_bf16(b4.z, b4.w);
+      q.x = pack_op(a.x, a.y);
+      q.y = pack_op(a.z, a.w);
+      q.z = pack_op(b4.x, b4.y);
+      q.w = pack_op(b4.z, b4.w);
       *reinterpret_cast<uint4*>(xo + row_off + kg * (TILE_M * 16)) = q;
     }
   }
@@ -939,10 +939,10 @@ kv_own_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wkimg,
         for (int sl = 0; sl < 15; ++sl) v[sl] = (sl >= lo && sl < hi) ? __uint_as_float(r[sl]) : 0.f;
         v[15] = valid ? 0.f : -29952.f;  // padded keys: score -29952 -> weight 0
         uint4 q0, q1;
-        q0.x = pack_bf16(v[0], v[1]), q0.y = pack_bf16(v[2], v[3]), q0.z = pack_bf16(v[4], v[5]);
-        q0.w = pack_bf16(v[6], v[7]);
-        q1.x = pack_bf16(v[8], v[9]), q1.y = pack_bf16(v[10], v[11]), q1.z = pack_bf16(v[12], v[13]);
-        q1.w = pack_bf16(v[14], v[15]);
+        q0.x = pack_op(v[0], v[1]), q0.y = pack_op(v[2], v[3]), q0.z = pack_op(v[4], v[5]);
+        q0.w = pack_op(v[6], v[7]);
+        q1.x = pack_op(v[8], v[9]), q1.y = pack_op(v[10], v[11]), q1.z = pack_op(v[12], v[13]);
+        q1.w = pack_op(v[14], v[15]);
         uint8_t* kimg = simg + (size_t)(h * NCH + ch) * img_stride;
         *reinterpret_cast<uint4*>(kimg + (size_t)kl * 16) = q0;
         *reinterpret_cast<uint4*>(kimg + (size_t)(CK + kl) * 16) = q1;
@@ -953,7 +953,7 @@ kv_own_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wkimg,
     // padded keys not covered by any tile (only when NCH CK > 128 tps)
     const uint4 z0 = make_uint4(0u, 0u, 0u, 0u);
     uint4 z1 = z0;
-    z1.w = pack_bf16(0.f, -29952.f);
+    z1.w = pack_op(0.f, -29952.f);
     for (int k2 = tps * TILE_M + row; k2 < n_keys; k2 += TILE_M) {
       const int ch = k2 / CK, kl = k2 - ch * CK;
       for (int h = 0; h < H; ++h) {
@@ -1048,7 +1048,7 @@ __global__ void pack_kv_kernel(const float* __restrict__ kc, const float* __rest
       if (key < L && slot < HP - 1 && dim >= 0 && dim < hd) v = kc[((int64_t)lh * L + key) * hd + dim];
       if (key >= L && slot == HP - 1) v = -29952.f;  // padded keys: score = -29952 -> weight 0
     }
-    img[i] = is_v ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    img[i] = is_v ? __half_as_ushort(__float2half_rn(v)) : op_bits(v);
   }
 }
 
@@ -1112,7 +1112,7 @@ __global__ void pack_kv_own_kernel(const float* __restrict__ src, int ld, int k_
         if (key >= L && slot == HP - 1) v[j] = -29952.f;
       }
       uint4 q;
-      q.x = pack_bf16(v[0], v[1]), q.y = pack_bf16(v[2], v[3]), q.z = pack_bf16(v[4], v[5]), q.w = pack_bf16(v[6], v[7]);
+      q.x = pack_op(v[0], v[1]), q.y = pack_op(v[2], v[3]), q.z = pack_op(v[4], v[5]), q.w = pack_op(v[6], v[7]);
       img[i] = q;
     } else {
       const int uu = u - 2 * CK;
@@ -1183,12 +1183,12 @@ int tc_pack_attn(const ffd_dims& m, const float* weights, void* img_base, int64_
   const int DP = tc::dp_of(m.d_model);
   for (int l = 0; l < m.n_layers; ++l) {
     const float* w = weights + ar.layer0 + (int64_t)l * ar.layer_stride;
-    __nv_bfloat16* wq = (__nv_bfloat16*)((uint8_t*)img_base + l * layer_stride_bytes + attn_off_bytes);
+    tc::op16* wq = (tc::op16*)((uint8_t*)img_base + l * layer_stride_bytes + attn_off_bytes);
     tc::pack_attn_kernel<<<32, 256, 0, s>>>(w + ar.in_w, w + ar.in_b, w + ar.out_w, w + ar.out_b, wq,
                                             wq + (size_t)g.QN * DP, m.d_model, m.n_head, DP, g.G, g.QN);
     FFD_CHECK_LAUNCH("pack_attn_kernel");
     if (kvproj_fused(m)) {
-      __nv_bfloat16* wk = wq + (size_t)g.QN * DP + (size_t)DP * DP;
+      tc::op16* wk = wq + (size_t)g.QN * DP + (size_t)DP * DP;
       tc::pack_kvproj_kernel<<<32, 256, 0, s>>>(w + ar.in_w, w + ar.in_b, wk, wk + (size_t)g.QN * DP, m.d_model,
                                                 m.n_head, DP, g.G, g.QN);
       FFD_CHECK_LAUNCH("pack_kvproj_kernel");

@@ -409,8 +409,8 @@ layer_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y /* may
     uint8_t* ob = smem + sm.obf;
     // constant columns of the out-proj operand: d, d+1 = 1 (bias hi/lo), the rest of the padding = 0
     for (int c = d; c < DP; ++c)
-      *reinterpret_cast<__nv_bfloat16*>(ob + row_off + (c >> 3) * (TILE_M * 16) + (c & 7) * 2) =
-          __float2bfloat16_rn((c == d || c == d + 1) ? 1.f : 0.f);
+      *reinterpret_cast<op16*>(ob + row_off + (c >> 3) * (TILE_M * 16) + (c & 7) * 2) =
+          to_op((c == d || c == d + 1) ? 1.f : 0.f);
     uint32_t n = 0;
     for (uint32_t t = 0; t < my_tiles; ++t) {
       for (int h = 0; h < H; ++h) {
@@ -451,8 +451,8 @@ layer_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y /* may
         for (int j = 0; j < 7; ++j) {
           if (j < hd) {
             const int col = h * hd + j;
-            *reinterpret_cast<__nv_bfloat16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
-                __float2bfloat16_rn(acc[j] * inv);
+            *reinterpret_cast<op16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                to_op(acc[j] * inv);
           }
         }
       }
@@ -479,7 +479,7 @@ layer_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y /* may
     uint32_t cs = 0;  // scratch passes so far
     // constant columns of the Q-projection operand (d, d+1 = 1: bias hi/lo; the rest of the padding = 0)
     {
-      uint4 pk = make_uint4(pack_bf16(1.f, 1.f), 0u, 0u, 0u);
+      uint4 pk = make_uint4(pack_op(1.f, 1.f), 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(xo + row_off + (d >> 3) * (TILE_M * 16)) = pk;
     }
     // residual rows of local tile t -> shared memory (one bulk copy; a tile of 128 rows is contiguous in HBM)
@@ -549,10 +549,10 @@ layer_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y /* may
           if ((lane & 1) == 0) {
             const int trow = quad * 32 + r;
             uint4 pk;
-            pk.x = pack_bf16(a[i].x, a[i].y);
-            pk.y = pack_bf16(a[i].z, a[i].w);
-            pk.z = pack_bf16(b4.x, b4.y);
-            pk.w = pack_bf16(b4.z, b4.w);
+            pk.x = pack_op(a[i].x, a[i].y);
+            pk.y = pack_op(a[i].z, a[i].w);
+            pk.z = pack_op(b4.x, b4.y);
+            pk.w = pack_op(b4.z, b4.w);
             *reinterpret_cast<uint4*>(xo + (uint32_t)(trow >> 3) * 128 + (uint32_t)(trow & 7) * 16 +
                                       (c4 >> 1) * (TILE_M * 16)) = pk;
           }
@@ -563,14 +563,14 @@ layer_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y /* may
     // 16 fp32 accumulator columns -> two bf16 k-groups of the Q operand
     auto store_q16 = [&](const uint32_t (&r)[16], uint8_t* dst) {
       uint4 q0, q1;
-      q0.x = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));
-      q0.y = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
-      q0.z = pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));
-      q0.w = pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
-      q1.x = pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));
-      q1.y = pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
-      q1.z = pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13]));
-      q1.w = pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
+      q0.x = pack_op(__uint_as_float(r[0]), __uint_as_float(r[1]));
+      q0.y = pack_op(__uint_as_float(r[2]), __uint_as_float(r[3]));
+      q0.z = pack_op(__uint_as_float(r[4]), __uint_as_float(r[5]));
+      q0.w = pack_op(__uint_as_float(r[6]), __uint_as_float(r[7]));
+      q1.x = pack_op(__uint_as_float(r[8]), __uint_as_float(r[9]));
+      q1.y = pack_op(__uint_as_float(r[10]), __uint_as_float(r[11]));
+      q1.z = pack_op(__uint_as_float(r[12]), __uint_as_float(r[13]));
+      q1.w = pack_op(__uint_as_float(r[14]), __uint_as_float(r[15]));
       *reinterpret_cast<uint4*>(dst) = q0;
       *reinterpret_cast<uint4*>(dst + TILE_M * 16) = q1;
     };
@@ -649,8 +649,8 @@ layer_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y /* may
           } else if (c == d) {
             o.x = 1.f, o.y = 1.f;  // the constant-1 columns that carry b1 (hi + lo parts) through GEMM1
           }
-          xp[2 * j] = pack_bf16(o.x, o.y);
-          xp[2 * j + 1] = pack_bf16(o.z, o.w);
+          xp[2 * j] = pack_op(o.x, o.y);
+          xp[2 * j + 1] = pack_op(o.z, o.w);
           yv[4 * j] = __float_as_uint(ob2.x);
           yv[4 * j + 1] = __float_as_uint(ob2.y);
           yv[4 * j + 2] = __float_as_uint(ob2.z);
@@ -769,13 +769,13 @@ layer_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y /* may
       FFD_TMEM_LD16(hcol + 16, (r + 16));
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) pk[e] = relu_pack_bf16(r[2 * e], r[2 * e + 1]);
+      for (int e = 0; e < 16; ++e) pk[e] = relu_pack_op(r[2 * e], r[2 * e + 1]);
       FFD_TMEM_LD16(hcol + 32, r);
       FFD_TMEM_LD16(hcol + 48, (r + 16));
       tmem_ld_wait();
       FFD_TMEM_ST16(hcol, pk);  // columns 0..15 <- hidden units 0..31 (their fp32 values are in registers / done)
 #pragma unroll
-      for (int e = 0; e < 16; ++e) pk[e] = relu_pack_bf16(r[2 * e], r[2 * e + 1]);
+      for (int e = 0; e < 16; ++e) pk[e] = relu_pack_op(r[2 * e], r[2 * e + 1]);
       FFD_TMEM_ST16(hcol + 16, pk);
       tmem_st_wait();
       tc_fence_before();

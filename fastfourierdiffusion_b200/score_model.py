@@ -84,6 +84,8 @@ class ScoreModule(nn.Module):
         self.use_cache: bool = False
         self._kv_owner: Optional[E2CRFCache] = None  # first cache ever created
         self._precision = precision or os.environ.get("FFD_PRECISION")
+        if self._precision == "bf16":  # former name of the 16-bit tensor-core path
+            self._precision = "fp16"
         self._arena: Optional[torch.Tensor] = None
         self._arena_key = None
         self._packed: Optional[torch.Tensor] = None
@@ -102,18 +104,18 @@ class ScoreModule(nn.Module):
 
     @property
     def precision(self) -> str:
-        """'bf16' (tcgen05 GEMMs, fp32 accumulate and residual stream) when the kernels
-        support the model shape, else 'fp32' (CUDA-core FMA)."""
+        """'fp16' (tcgen05 GEMMs on fp16 operands, fp32 accumulate and residual stream) when the kernels
+        support the model shape, else 'fp32' (CUDA-core FMA).  'bf16' is accepted as the former name of 'fp16'."""
         if self._precision is None:
             lib = _lib.load()
             d = self.dims
             ok = lib.ffd_has_tensor_path() and lib.ffd_packed_bytes(d) > 0 and self._tc_ok()
-            self._precision = "bf16" if ok else "fp32"
+            self._precision = "fp16" if ok else "fp32"
         return self._precision
 
     def set_precision(self, precision: str) -> None:
-        assert precision in ("fp32", "bf16")
-        self._precision = precision
+        assert precision in ("fp32", "fp16", "bf16")
+        self._precision = "fp16" if precision == "bf16" else precision
         self._arena_key = None
 
     def _tc_ok(self) -> bool:
@@ -130,7 +132,7 @@ class ScoreModule(nn.Module):
         return ps
 
     def device_weights(self) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-        """(fp32 arena, bf16 tensor-core image or None); rebuilt when a parameter changed."""
+        """(fp32 arena, 16-bit tensor-core operand images or None); rebuilt when a parameter changed."""
         dev = self.device
         if dev.type != "cuda":
             raise _lib.FFDError("ScoreModule parameters must be on a CUDA device (no CPU fallback): call .to('cuda')")
@@ -149,7 +151,7 @@ class ScoreModule(nn.Module):
             d = self.dims
             assert self._arena.numel() == lib.ffd_weights_count(d)
             self._packed = None
-            if self.precision == "bf16":
+            if self.precision == "fp16":
                 nbytes = lib.ffd_packed_bytes(d)
                 self._packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
                 _lib.check(lib.ffd_pack_weights(d, _lib.ptr(self._arena), _lib.ptr(self._packed), st))
@@ -163,7 +165,7 @@ class ScoreModule(nn.Module):
         return self._workspace
 
     def _prec_code(self) -> int:
-        return _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
+        return _lib.PREC_FP16 if self.precision == "fp16" else _lib.PREC_FP32
 
     def time_embedding(self, timesteps: torch.Tensor) -> torch.Tensor:
         """[n] -> [n, d]: dense([sin, cos](2 pi t W))[:d]  (transformer.py:80-91)."""

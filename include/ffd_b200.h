@@ -45,7 +45,9 @@ extern "C" {
 
 /* arithmetic of the score-model GEMMs */
 #define FFD_PREC_FP32 0 /* CUDA-core fp32 FMA everywhere */
-#define FFD_PREC_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate in TMEM; fp32 residual stream */
+#define FFD_PREC_FP16 1 /* tcgen05: fp16 operands (saturating conversions), fp32 accumulate in TMEM; fp32 residual stream */
+#define FFD_PREC_BF16 FFD_PREC_FP16 /* former name: the operands were bf16 until the switch to fp16 (same speed, 8x the
+                                       mantissa: csrc/ffd_tc_ptx.cuh FFD_TC_FP16) */
 
 #define FFD_SDE_VP 0
 #define FFD_SDE_VE 1
@@ -140,7 +142,7 @@ typedef struct ffd_forward_args {
   int32_t mode;           /* FFD_MODE_* */
   int64_t B;
   const float* weights;   /* fp32 arena */
-  const void* packed;     /* bf16 image (FFD_PREC_BF16 only) */
+  const void* packed;     /* 16-bit operand images (FFD_PREC_FP16 only) */
   void* workspace;
   int64_t workspace_bytes;
   const float* X;         /* [B, L, C] */
@@ -164,16 +166,16 @@ int ffd_ffn_ln(const ffd_dims* dims, int precision, const float* weights, const 
 
 /* y = LayerNorm1(x + out_proj(softmax(q K_c^T / sqrt(hd)) V_c)) of one PURE-CACHE encoder layer on M token rows
  * (cached_transformer.py:228-258,309-321): K_c/V_c are the sample-0 cache rows [NL, H, L, hd] shared by the batch.
- * x, y: [M, d] fp32 (y may alias x for FFD_PREC_BF16); workspace as for ffd_score_forward with B = ceil(M / L). */
+ * x, y: [M, d] fp32 (y may alias x for FFD_PREC_FP16); workspace as for ffd_score_forward with B = ceil(M / L). */
 int ffd_attn_cached_ln(const ffd_dims* dims, int precision, const float* weights, const void* packed, int layer,
                        const float* k_cache, const float* v_cache, const float* x, float* y, void* workspace,
                        int64_t workspace_bytes, int64_t M, ffd_stream_t stream);
 
 /* One whole PURE-CACHE encoder layer, y = LayerNorm2(y1 + FFN(y1)) with y1 the result of ffd_attn_cached_ln
  * (cached_transformer.py:228-258,309-327): the two blocks back to back.  With FFD_FUSED_LAYER=1 (opt-in, default model
- * width only) FFD_PREC_BF16 runs it as ONE kernel that overlaps the MUFU-bound softmax with the tensor-bound FFN GEMMs
+ * width only) FFD_PREC_FP16 runs it as ONE kernel that overlaps the MUFU-bound softmax with the tensor-bound FFN GEMMs
  * per SM -- correct, but hand-off-latency bound and slower than the two kernels on B200, hence
- * not the default.  x, y: [M, d] fp32 (y may alias x for FFD_PREC_BF16). */
+ * not the default.  x, y: [M, d] fp32 (y may alias x for FFD_PREC_FP16). */
 int ffd_layer_cached_ln(const ffd_dims* dims, int precision, const float* weights, const void* packed, int layer,
                         const float* k_cache, const float* v_cache, const float* x, float* y, void* workspace,
                         int64_t workspace_bytes, int64_t M, ffd_stream_t stream);

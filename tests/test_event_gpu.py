@@ -129,7 +129,7 @@ def _oracle_event_run(g, cfg, n, B):
     return X, osamp, decisions
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
 @pytest.mark.parametrize("B", [1, 3])
 def test_event_driven_sampler_against_oracle(prec, B):
     """Whole event-driven runs of the tiny model through DiffusionSampler.run_steps (ffd_sample_steps with
@@ -138,10 +138,10 @@ def test_event_driven_sampler_against_oracle(prec, B):
     import fastfourierdiffusion_b200 as F
     from fastfourierdiffusion_b200 import _lib
 
-    if prec == "bf16" and not _lib.load().ffd_has_tensor_path():
+    if prec == "fp16" and not _lib.load().ffd_has_tensor_path():
         pytest.skip("tensor path not available")
     m = build_tiny_model(precision=prec)
-    if prec == "bf16" and not m._tc_ok():
+    if prec == "fp16" and not m._tc_ok():
         pytest.skip("model shape not supported by the tcgen05 kernels")
     g = load_golden("tiny_vp_freq_cache.npz")
     n = 40
@@ -185,7 +185,7 @@ def test_event_driven_is_one_launch_loop_without_host_sync():
 
     if not _lib.load().ffd_has_tensor_path():
         pytest.skip("tensor path not available")
-    m = build_seeded_model(ECG, 42, precision="bf16").to("cuda").eval()
+    m = build_seeded_model(ECG, 42, precision="fp16").to("cuda").eval()
     B, n = 64, 12
     outs = {}
     for tag, tau0 in (("never", 1e30), ("always", 0.0), ("mixed", 1.0)):

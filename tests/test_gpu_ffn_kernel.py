@@ -27,7 +27,7 @@ def _run(model, layer, x, precision):
     arena, packed = model.device_weights()
     y = torch.empty_like(x)
     scratch = torch.empty_like(x)
-    _lib.check(_lib.load().ffd_ffn_ln(model.dims, 1 if precision == "bf16" else 0, _lib.ptr(arena), _lib.ptr(packed),
+    _lib.check(_lib.load().ffd_ffn_ln(model.dims, 1 if precision == "fp16" else 0, _lib.ptr(arena), _lib.ptr(packed),
                                       layer, _lib.ptr(x), _lib.ptr(y), _lib.ptr(scratch), x.shape[0],
                                       _lib.stream_handle()))
     torch.cuda.synchronize()
@@ -49,12 +49,14 @@ def test_ffn_ln_fp32_and_tensor_path(which, M):
     assert rel(got32.cpu().numpy(), want.cpu().numpy()) < 5e-6
     if not _lib.load().ffd_has_tensor_path() or not model._tc_ok():
         pytest.skip("tensor path not available")
-    got16 = _run(model, layer, x, "bf16")
+    got16 = _run(model, layer, x, "fp16")
     assert torch.isfinite(got16).all()
-    # bf16 operands (8-bit mantissa), fp32 accumulate, fp32 residual and LayerNorm
-    assert rel(got16.cpu().numpy(), want.cpu().numpy()) < 1e-2
+    # fp16 operands (11-bit mantissa), fp32 accumulate, fp32 residual and LayerNorm
+    e_max = rel(got16.cpu().numpy(), want.cpu().numpy())
     err = (got16.double() - want).abs()
-    assert float(err.mean() / want.abs().mean()) < 2e-3
+    e_mean = float(err.mean() / want.abs().mean())
+    print(f"ffn_ln [{which}, M={M}] fp16 operands vs float64: max-rel {e_max:.2e}, mean-rel {e_mean:.2e}")
+    assert e_max < 2e-3 and e_mean < 3e-4
     # in place
     xin = x.clone()
     arena, packed = model.device_weights()
@@ -95,7 +97,7 @@ def test_attn_cached_ln_fp32_and_tensor_path(which, B):
         arena, packed = model.device_weights()
         ws = model.workspace(B)
         y = torch.empty_like(x)
-        _lib.check(_lib.load().ffd_attn_cached_ln(model.dims, 1 if prec == "bf16" else 0, _lib.ptr(arena),
+        _lib.check(_lib.load().ffd_attn_cached_ln(model.dims, 1 if prec == "fp16" else 0, _lib.ptr(arena),
                                                   _lib.ptr(packed), layer, _lib.ptr(kc), _lib.ptr(vc), _lib.ptr(x),
                                                   _lib.ptr(y), _lib.ptr(ws), ws.numel(), B * L, _lib.stream_handle()))
         torch.cuda.synchronize()
@@ -104,13 +106,15 @@ def test_attn_cached_ln_fp32_and_tensor_path(which, B):
     assert rel(run("fp32").cpu().numpy(), want.cpu().numpy()) < 5e-6
     if not _lib.load().ffd_has_tensor_path() or not model._tc_ok():
         pytest.skip("tensor path not available")
-    got = run("bf16")
+    got = run("fp16")
     assert torch.isfinite(got).all()
-    assert rel(got.cpu().numpy(), want.cpu().numpy()) < 2e-2
-    assert float((got.double() - want).abs().mean() / want.abs().mean()) < 3e-3
+    e_max = rel(got.cpu().numpy(), want.cpu().numpy())
+    e_mean = float((got.double() - want).abs().mean() / want.abs().mean())
+    print(f"attn_cached_ln [{which}, B={B}] fp16 operands vs float64: max-rel {e_max:.2e}, mean-rel {e_mean:.2e}")
+    assert e_max < 4e-3 and e_mean < 6e-4
     # large scores (|s| ~ 1e2): the split-K softmax must stay exact where a bounded shift would underflow
     kc2 = kc * 40
-    model.set_precision("bf16")
+    model.set_precision("fp16")
     arena, packed = model.device_weights()
     ws = model.workspace(B)
     y2 = torch.empty_like(x)
@@ -137,18 +141,18 @@ def test_ffn_cta_pair_kernel_equals_one_cta_kernel(M):
     lib = _lib.load()
     if not lib.ffd_has_tensor_path():
         pytest.skip("tensor path not available")
-    model = build_seeded_model(ECG, 42, precision="bf16").to("cuda").eval()
+    model = build_seeded_model(ECG, 42, precision="fp16").to("cuda").eval()
     torch.manual_seed(M)
     x = torch.randn(M, model.d_model, device="cuda") * 1.3
     try:
         lib.ffd_debug_set_ffn_pairs(0)
-        one = _run(model, 3, x, "bf16")
+        one = _run(model, 3, x, "fp16")
         lib.ffd_debug_set_ffn_pairs(1)
-        pair = _run(model, 3, x, "bf16")
+        pair = _run(model, 3, x, "fp16")
         # identical tiles at different iterations of the persistent loop give identical rows
         if M >= 148 * 256 * 2:
             xx = torch.cat([x[:148 * 256], x[:148 * 256], x[:M - 2 * 148 * 256]]).contiguous()
-            yy = _run(model, 3, xx, "bf16")
+            yy = _run(model, 3, xx, "fp16")
             assert torch.equal(yy[:148 * 256], yy[148 * 256:2 * 148 * 256])
     finally:
         lib.ffd_debug_set_ffn_pairs(-1)
@@ -165,14 +169,14 @@ def test_ffn_rows_do_not_depend_on_the_loop_iteration(dims):
 
     if not _lib.load().ffd_has_tensor_path():
         pytest.skip("tensor path not available")
-    model = build_seeded_model(dims, 7, precision="bf16").to("cuda").eval()
+    model = build_seeded_model(dims, 7, precision="fp16").to("cuda").eval()
     if not model._tc_ok():
         pytest.skip("model shape not supported by the tcgen05 kernels")
     blk = 148 * 256  # rows one wave of CTAs (two tiles each) covers
     torch.manual_seed(3)
     x0 = torch.randn(blk, model.d_model, device="cuda")
     x = torch.cat([x0, x0, x0, x0[:1000]]).contiguous()
-    y = _run(model, len(model.backbone.layers) - 1, x, "bf16")
+    y = _run(model, len(model.backbone.layers) - 1, x, "fp16")
     assert torch.equal(y[:blk], y[blk:2 * blk]) and torch.equal(y[:blk], y[2 * blk:3 * blk])
     assert torch.equal(y[:1000], y[3 * blk:])
     assert rel(y[:blk].cpu().numpy(), _ffn_ref(model, len(model.backbone.layers) - 1, x0).cpu().numpy()) < 1e-2
@@ -186,7 +190,7 @@ def test_attention_rows_do_not_depend_on_the_loop_iteration():
     lib = _lib.load()
     if not lib.ffd_has_tensor_path():
         pytest.skip("tensor path not available")
-    model = build_seeded_model(ECG, 42, precision="bf16").to("cuda").eval()
+    model = build_seeded_model(ECG, 42, precision="fp16").to("cuda").eval()
     L, d, H = ECG["max_len"], ECG["d_model"], ECG["n_head"]
     blk = 148 * 128
     M = (3 * blk + L - 1) // L * L

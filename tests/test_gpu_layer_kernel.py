@@ -57,7 +57,7 @@ def test_fused_layer_matches_the_two_kernels_and_float64(which, B):
 
     if not _lib.load().ffd_has_tensor_path():
         pytest.skip("tensor path not available")
-    model = build_seeded_model(SHAPES[which], 42, precision="bf16").to("cuda").eval()
+    model = build_seeded_model(SHAPES[which], 42, precision="fp16").to("cuda").eval()
     d, L, H = model.d_model, model.max_len, model.n_head
     NL = len(model.backbone.layers)
     layer = NL - 2
@@ -76,8 +76,8 @@ def test_fused_layer_matches_the_two_kernels_and_float64(which, B):
     print(f"fused layer [{which}, B={B}]: vs two kernels {err_two:.2e}, vs float64 max-rel {err_ref:.2e} mean-rel {err_mean:.2e}")
     # the same operand roundings; only the fp32 accumulation order of the FFN (64- instead of 128-wide slices, the
     # residual inside the accumulator) and of the softmax partials differs
-    assert err_two < 2e-3
-    assert err_ref < 2e-2 and err_mean < 3e-3
+    assert err_two < 5e-4
+    assert err_ref < 2e-3 and err_mean < 5e-4
     # in place (the sampling loop runs every layer in place on the residual stream)
     inpl, _ = _run_layer(model, layer, x, kc, vc, B, fused=True, inplace=True)
     assert torch.equal(inpl, one)
@@ -90,7 +90,7 @@ def test_fused_layer_large_scores_and_determinism():
 
     if not _lib.load().ffd_has_tensor_path():
         pytest.skip("tensor path not available")
-    model = build_seeded_model(ECG, 42, precision="bf16").to("cuda").eval()
+    model = build_seeded_model(ECG, 42, precision="fp16").to("cuda").eval()
     d, L, H = model.d_model, model.max_len, model.n_head
     NL, B = len(model.backbone.layers), 40
     torch.manual_seed(3)
@@ -101,6 +101,6 @@ def test_fused_layer_large_scores_and_determinism():
     b, _ = _run_layer(model, 0, x, kc, vc, B, fused=True)
     assert torch.equal(a, b)
     two, _ = _run_layer(model, 0, x, kc, vc, B, fused=False)
-    assert rel(a.cpu().numpy(), two.cpu().numpy()) < 2e-3
+    assert rel(a.cpu().numpy(), two.cpu().numpy()) < 2e-3  # |s| ~ 1e2: near-one-hot rows, see the attention kernel test
     want = _layer_ref(model, 0, x, kc, vc, B)
     assert float((a.double() - want).abs().mean() / want.abs().mean()) < 2e-2

@@ -21,21 +21,23 @@ def _precisions():
         from fastfourierdiffusion_b200 import _lib
 
         if torch.cuda.is_available() and _lib.load().ffd_has_tensor_path():
-            out.append("bf16")
+            out.append("fp16")
     except Exception:
         pass
     return out
 
 
-PRECS = ["fp32", "bf16"]
+PRECS = ["fp32", "fp16"]
 # per-precision tolerances: (score rel, one-step state rel, multi-step state rel)
-TOL = {"fp32": dict(score=2e-5, step=2e-6, traj=5e-4), "bf16": dict(score=3e-2, step=1e-3, traj=5e-2)}
+# fp16 = tensor-core path (fp16 operands, fp32 accumulate): measured on B200 -- scores 1e-3 (well conditioned) to 3.6e-3
+# (|X| ~ 126), one-step states 4e-5
+TOL = {"fp32": dict(score=2e-5, step=2e-6, traj=5e-4), "fp16": dict(score=5e-3, step=2e-4, traj=2e-2)}
 
 
 def _skip_unless(prec, model=None):
     if prec not in _precisions():
         pytest.skip("tensor path not available")
-    if prec == "bf16" and model is not None and not model._tc_ok():
+    if prec == "fp16" and model is not None and not model._tc_ok():
         pytest.skip("model shape not supported by the tcgen05 kernels")
 
 
@@ -277,7 +279,7 @@ def test_ecg_default_model_cached_trace(prec):
             assert rel(X.cpu().numpy(), g["keep_Xn"][keep[i]]) < TOL[prec]["step"], i
     assert rel(X.cpu().numpy(), g["final"]) < TOL[prec]["step"]
     c = m.cache
-    tol = 1e-4 if prec == "fp32" else 5e-2
+    tol = 1e-4 if prec == "fp32" else 1e-2
     assert rel(c.k_cache_tensor[[0, 9]].cpu().numpy(), g["k_cache"]) < tol
     assert rel(c.v_cache_tensor[[0, 9]].cpu().numpy(), g["v_cache"]) < tol
     crf = c.crf_cache[[0, 9]].cpu().numpy()
@@ -289,11 +291,66 @@ def test_ecg_default_model_cached_trace(prec):
         # one-hot, and bf16 operands flip the winning key for a few tokens (O(1) row errors at layer 0, damped by
         # the later LayerNorms).  So: the bulk of the rows at bf16 accuracy, the outliers bounded.
         err = np.abs(crf - g["crf"]).max(axis=-1) / np.abs(g["crf"]).max()
-        assert np.percentile(err, 90) < 1e-2 and err.max() < 0.5, (np.percentile(err, 90), err.max())
+        print(f"ecg-vp [fp16] CRF of the ill-conditioned mixed step (|X| ~ 470): row error median {np.median(err):.2e}, "
+              f"90th percentile {np.percentile(err, 90):.2e}, max {err.max():.2e}  (the well-conditioned counterpart, "
+              "with no allowance, is test_ecg_ve_well_conditioned_trace)")
+        assert np.percentile(err, 90) < 2e-3 and err.max() < 5e-2, (np.percentile(err, 90), err.max())
     st = c.get_cache_stats()
     ref = dict(zip(g["stats_keys"], g["stats_vals"]))
     for k in ref:
         assert st[k] == pytest.approx(ref[k], rel=1e-12), k
+
+
+# tensor-core arithmetic (fp16 operands) on a WELL-CONDITIONED trace: score and CRF within 2.5e-3 (max-norm relative),
+# K/V rows within 2e-3, per-step states within 2e-4 (the north star asks 1e-3) -- every row, no percentile allowance
+TIGHT = {"fp32": dict(score=2e-5, crf=2e-5, kv=1e-4, step=2e-6), "fp16": dict(score=2.5e-3, crf=2.5e-3, kv=2e-3, step=2e-4)}
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_ecg_ve_well_conditioned_trace(prec):
+    """Hydra-default ECG model under the reference's VE-SDE (sigma_max = 2: |X| stays O(1) over the whole run), E2-CRF
+    K = 5, R = 100: full step 0, pure-cache steps 1 / 2 / 50 / 99 / 101 / 103 and the MIXED step 100, teacher-forced
+    against the unmodified reference (oracle/make_golden_ecg_ve.py).  The cache only changes at steps 0 and 100, so
+    running the kept steps in order reproduces its state exactly.  Measured errors are printed."""
+    import fastfourierdiffusion_b200 as F
+
+    g = load_golden("ecg_ve_cache.npz")
+    m = build_seeded_model(ECG, 42, kind="ve", precision=prec, sigma_min=0.01, sigma_max=2.0)
+    _skip_unless(prec, m)
+    keys, cs = state_dict_checksums(m)
+    np.testing.assert_allclose(cs, g["ck_vals"], rtol=1e-12)
+    m = m.to("cuda").eval()
+    n = int(g["n_steps"])
+    sampler = F.DiffusionSampler(m, 2, use_cache=True, cache_kwargs=dict(K=5, R=100))
+    m.noise_scheduler.set_timesteps(n)
+    assert np.array_equal(m.noise_scheduler.timesteps.numpy(), g["timesteps"])
+    m.cache.reset()
+    tol = TIGHT[prec]
+    worst = dict(score=0.0, crf=0.0, step=0.0)
+    z = g["step_z"][0]
+    for j, step in enumerate(int(k) for k in g["keep_steps"]):
+        X = torch.from_numpy(g["keep_X"][j]).cuda()
+        t = float(g["keep_t"][j])
+        ts = torch.full((2,), t, dtype=torch.float32, device="cuda")
+        m.cache.current_step = step
+        S = m.cache.determine_recompute_set(None, 0.1, step)
+        assert len(S) == int(g["nS"][step])
+        score, crf = m(F.DiffusableBatch(X=X, timesteps=ts), recompute_tokens=S, step=step, return_crf=True, t=t)
+        e_s = rel(score.cpu().numpy(), g["keep_score"][j])
+        Xn = m.noise_scheduler.step(model_output=score, timestep=t, sample=X,
+                                    noise=torch.from_numpy(z[step]).cuda()).prev_sample
+        e_x = rel(Xn.cpu().numpy(), g["keep_Xn"][j])
+        worst["score"], worst["step"] = max(worst["score"], e_s), max(worst["step"], e_x)
+        print(f"ecg-ve [{prec}] step {step:3d} |S|={len(S):3d}: score rel {e_s:.2e}, state rel {e_x:.2e}")
+        assert e_s < tol["score"], (step, e_s)
+        assert e_x < tol["step"], (step, e_x)
+        m.cache.update_crf(crf, timestep=t)  # kept iff step % R == 0 (caching.py:474): steps 0 and 100
+    c = m.cache
+    e_k = rel(c.k_cache_tensor[[0, 9]].cpu().numpy(), g["k_cache"])
+    e_v = rel(c.v_cache_tensor[[0, 9]].cpu().numpy(), g["v_cache"])
+    e_c = rel(c.crf_cache[[0, 9]].cpu().numpy(), g["crf"])
+    print(f"ecg-ve [{prec}] after the mixed step: K rel {e_k:.2e}, V rel {e_v:.2e}, CRF rel {e_c:.2e} (every row)")
+    assert e_k < tol["kv"] and e_v < tol["kv"] and e_c < tol["crf"]
 
 
 @pytest.mark.parametrize("prec", PRECS)
@@ -345,7 +402,9 @@ def test_ecg_default_model_scores_and_free_run(prec):
         X = torch.from_numpy(g["keep_X"][i]).cuda()
         ts = torch.full((2,), float(g["keep_t"][i]), dtype=torch.float32, device="cuda")
         score = m(F.DiffusableBatch(X=X, timesteps=ts))
-        assert rel(score.cpu().numpy(), g["keep_score"][i]) < TOL[prec]["score"], st
+        e_s = rel(score.cpu().numpy(), g["keep_score"][i])
+        print(f"ecg-vp no cache [{prec}] step {int(st)}: score rel {e_s:.2e} (max |X| {float(X.abs().max()):.1f})")
+        assert e_s < TOL[prec]["score"], st
     sampler, out = _run_trace(m, g, False, None)
     assert rel(out, g["final"]) < TOL[prec]["traj"]
 
@@ -507,7 +566,7 @@ def test_other_shapes_against_oracle(prec, shape):
     m = build_seeded_model(shape, 5, precision=prec)
     if prec not in _precisions():
         pytest.skip("tensor path not available")
-    if prec == "bf16" and not m._tc_ok():
+    if prec == "fp16" and not m._tc_ok():
         pytest.skip("model shape not supported by the tcgen05 kernels")
     sd = {k: v.detach().numpy().copy() for k, v in m.state_dict().items()}
     m = m.to("cuda").eval()

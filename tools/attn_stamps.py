@@ -6,7 +6,7 @@ import ctypes, torch, bench
 import fastfourierdiffusion_b200 as F
 from fastfourierdiffusion_b200 import _lib
 lib = _lib.load()
-model = bench.build_model("bf16").cuda().eval()
+model = bench.build_model("fp16").cuda().eval()
 B = 16384
 s = F.DiffusionSampler(model, B, use_cache=True, noise="philox")
 model.noise_scheduler.set_timesteps(1000)

@@ -82,12 +82,12 @@ __global__ void __launch_bounds__(1024, 1) bench(int mode, int n_steps, long lon
       FFD_TMEM_LD16(hcol, r); FFD_TMEM_LD16(hcol + 16, (r + 16));
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) pk[e] = relu_pack_bf16(r[2 * e], r[2 * e + 1]);
+      for (int e = 0; e < 16; ++e) pk[e] = relu_pack_op(r[2 * e], r[2 * e + 1]);
       FFD_TMEM_LD16(hcol + 32, r); FFD_TMEM_LD16(hcol + 48, (r + 16));
       tmem_ld_wait();
       FFD_TMEM_ST16(hcol, pk);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) pk[e] = relu_pack_bf16(r[2 * e], r[2 * e + 1]);
+      for (int e = 0; e < 16; ++e) pk[e] = relu_pack_op(r[2 * e], r[2 * e + 1]);
       FFD_TMEM_ST16(hcol + 16, pk);
       tmem_st_wait();
       tc_fence_before();

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import ctypes, torch, bench
 from fastfourierdiffusion_b200 import _lib
 lib = _lib.load()
-model = bench.build_model("bf16").cuda().eval()
+model = bench.build_model("fp16").cuda().eval()
 M = 16384 * 187
 arena, packed = model.device_weights()
 x = torch.randn(M, 72, device="cuda"); y = torch.empty_like(x); st = _lib.stream_handle()

@@ -8,7 +8,7 @@ import torch, bench
 import fastfourierdiffusion_b200 as F
 from fastfourierdiffusion_b200 import _lib
 lib = _lib.load()
-model = bench.build_model("bf16").cuda().eval()
+model = bench.build_model("fp16").cuda().eval()
 B = 16384
 L, d, H = model.max_len, model.d_model, model.n_head
 M = B * L

@@ -26,7 +26,7 @@ import __graft_entry__ as e
 
 e.build()
 lib = _lib.load()
-model = bench.build_model("bf16").cuda().eval()
+model = bench.build_model("fp16").cuda().eval()
 M = a.batch * 187
 st = _lib.stream_handle()
 if a.kernel == "ffn":

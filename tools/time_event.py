@@ -23,7 +23,7 @@ ap.add_argument("--batch", type=int, default=16384)
 ap.add_argument("--steps", type=int, default=60)
 ap.add_argument("--out", default=None)
 a = ap.parse_args()
-model = bench.build_model("bf16").cuda().eval()
+model = bench.build_model("fp16").cuda().eval()
 B, n = a.batch, a.steps
 rows = []
 cases = [("index schedule (reference): K=5 R=10", dict(K=5, R=10))]

@@ -21,7 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16384)
 a = ap.parse_args()
 lib = _lib.load()
-model = bench.build_model("bf16").cuda().eval()
+model = bench.build_model("fp16").cuda().eval()
 B = a.batch
 L = model.max_len
 M = B * L

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, bench
 from fastfourierdiffusion_b200 import _lib
 lib = _lib.load()
-model = bench.build_model("bf16").cuda().eval()
+model = bench.build_model("fp16").cuda().eval()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 L, d, H = model.max_len, model.d_model, model.n_head
 M = B * L

@@ -11,7 +11,7 @@ import fastfourierdiffusion_b200 as F
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16384)
 a = ap.parse_args()
-model = bench.build_model("bf16").cuda().eval()
+model = bench.build_model("fp16").cuda().eval()
 B = a.batch
 s = F.DiffusionSampler(model, B, use_cache=True, noise="philox", cache_kwargs=dict(K=5, R=10))
 model.noise_scheduler.set_timesteps(1000)

@@ -24,7 +24,7 @@ out = {}
 for name, (L, C) in SHAPES.items():
     torch.manual_seed(42)
     sched = F.VPScheduler(fourier_noise_scaling=True)
-    model = F.ScoreModule(noise_scheduler=sched, fourier_noise_scaling=True, precision="bf16", max_len=L, n_channels=C,
+    model = F.ScoreModule(noise_scheduler=sched, fourier_noise_scaling=True, precision="fp16", max_len=L, n_channels=C,
                           d_model=72, num_layers=10, n_head=12).cuda().eval()
     sched.set_noise_scaling(L)
     B = max(128, a.rows // L // 128 * 128)

@@ -22,7 +22,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
 a = ap.parse_args()
 out = {"batch": a.batch}
-for prec in ("bf16", "fp32"):
+for prec in ("fp16", "fp32"):
     model = bench.build_model(prec).cuda().eval()
     model.noise_scheduler.set_timesteps(1000)
     for use_cache in (False, True):

@@ -13,7 +13,7 @@ ap.add_argument("--batch", type=int, default=16384)
 ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
-model = bench.build_model("bf16").cuda().eval()
+model = bench.build_model("fp16").cuda().eval()
 s = F.DiffusionSampler(model, a.batch, use_cache=True, noise="philox", cache_kwargs=dict(K=5, R=10))
 model.noise_scheduler.set_timesteps(1000)
 model.cache.reset()
