@@ -28,7 +28,7 @@ EXPORTS = [
     "ffd_packed_bytes", "ffd_pack_weights", "ffd_workspace_bytes", "ffd_has_tensor_path",
     "ffd_dft_matrix", "ffd_dft_apply", "ffd_posemb_renorm", "ffd_time_embedding", "ffd_score_forward",
     "ffd_sde_step", "ffd_prior", "ffd_philox_normal", "ffd_sample_steps", "ffd_ffn_ln", "ffd_launch_count", "ffd_attn_cached_ln", "ffd_layer_cached_ln", "ffd_fresca", "ffd_fresca_scratch_floats", "ffd_event_intensity",
-    "ffd_event_decide", "ffd_event_refresh_kv",
+    "ffd_event_decide", "ffd_event_refresh_kv", "ffd_graph_scratch_bytes",
     "ffd_metric_project", "ffd_metric_sort_rows", "ffd_metric_w2_sorted", "ffd_metric_row_std", "ffd_spectral_density",
 ]
 
@@ -79,7 +79,8 @@ class SampleArgs(C.Structure):
                 ("store_crf_host", C.POINTER(C.c_int32)), ("noise", C.c_void_p), ("noise_step0", C.c_int32), ("seed", C.c_uint64),
                 ("stream_base", C.c_uint64), ("x", C.c_void_p), ("x_tmp", C.c_void_p),
                 ("step_begin", C.c_int32), ("step_end", C.c_int32), ("event", C.POINTER(EventArgs)),
-                ("fresca", C.POINTER(FrescaArgs))]
+                ("fresca", C.POINTER(FrescaArgs)), ("graph", C.c_int32), ("graph_scratch", C.c_void_p),
+                ("graph_scratch_bytes", C.c_int64)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -117,6 +118,8 @@ def load() -> C.CDLL:
     lib.ffd_sample_steps.argtypes = [C.POINTER(SampleArgs), vp]
     lib.ffd_ffn_ln.argtypes = [pd, i32, vp, vp, i32, vp, vp, vp, i64, vp]
     lib.ffd_launch_count.restype = u64
+    lib.ffd_graph_scratch_bytes.restype = i64
+    lib.ffd_graph_scratch_bytes.argtypes = [i32]
     lib.ffd_fresca_scratch_floats.restype = i64
     lib.ffd_fresca_scratch_floats.argtypes = [i64, i32, i32]
     lib.ffd_fresca.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, f32, f32, f32, i32, vp]

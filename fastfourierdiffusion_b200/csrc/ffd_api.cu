@@ -123,13 +123,13 @@ static int pick_branch(const ffd_forward_args& a, int* populate) {
 // rows under the weights the previous step's decision left on the device, and every cached step ends with the
 // next decision; the full-recompute step (re)initialises the event state.
 static int forward_hidden(const ffd_forward_args& a, const Arena& ar, const Workspace& ws, cudaStream_t s,
-                          const ffd_event_args* ev = nullptr, int step = 0) {
+                          const ffd_event_args* ev = nullptr, int step = 0, const int32_t* step_ctr = nullptr) {
   const ffd_dims& m = a.dims;
   const int L = m.max_len, C = m.n_channels, d = m.d_model, H = m.n_head, hd = d / H;
   const int64_t M = a.B * L;
   int rc;
   if ((rc = launch_embed(a.X, a.weights + ar.emb_w, a.weights + ar.emb_b, a.weights + ar.pos, a.time_emb, ws.h, M,
-                         L, C, d, s)))
+                         L, C, d, s, step_ctr)))
     return rc;
   int populate = 0;
   const int branch = pick_branch(a, &populate);
@@ -205,6 +205,34 @@ static int check_forward(const ffd_forward_args& a) {
   return FFD_OK;
 }
 
+}  // namespace ffd
+
+
+// ---- the step loop as a replayed CUDA graph (launch-bound regime: small batches) ---------------------------------
+// A run of consecutive PURE-CACHE steps (no CRF store, no event schedule, no FreSca) launches the same ~23 kernels per
+// step with only four things changing: the time-embedding row, the SDE scalars, the Philox stream and the slice of
+// injected noise.  Those are read from device memory through a step cursor (StepSource, ffd_common.cuh), so TWO steps
+// (the state ping-pongs between x and x_tmp) are captured once and the graph is replayed: one launch per two steps
+// instead of 46.  At batch 64 the loop is launch-bound (0.54 ms per step for ~0.2 ms of GPU work).
+namespace ffd {
+struct GraphKey {
+  ffd_dims dims;
+  int32_t precision;
+  int64_t B;
+  const void *weights, *packed, *workspace, *k_cache, *v_cache, *score, *G, *te, *noise, *x, *x_tmp, *scratch;
+  int fused;
+};
+struct GraphEntry {
+  GraphKey key;
+  cudaGraphExec_t exec;
+  unsigned long long launches;  // kernels per replay
+  bool used;
+};
+static GraphEntry g_graphs[8];
+static int g_graph_next = 0;
+static bool g_pure_step_ran = false;  // a pure-cache step has run directly: every lazy initialisation of the launchers is done
+
+static size_t graph_coef_offset() { return 32; }
 }  // namespace ffd
 
 namespace ffd {
@@ -479,6 +507,10 @@ int ffd_event_refresh_kv(const ffd_dims* dims, const float* weights, int layer, 
                                  (cudaStream_t)stream);
 }
 
+int64_t ffd_graph_scratch_bytes(int32_t n_steps) {
+  return n_steps < 0 ? -1 : (int64_t)graph_coef_offset() + (int64_t)n_steps * (int64_t)sizeof(ffd_step_coef) + 64;
+}
+
 int ffd_sample_steps(const ffd_sample_args* a, ffd_stream_t stream) {
   FFD_CHECK_ARG(a != nullptr, "null args");
   FFD_CHECK_ARG(a->G && a->time_emb_table && a->coef_host && a->n_own_host && a->x && a->x_tmp,
@@ -509,12 +541,14 @@ int ffd_sample_steps(const ffd_sample_args* a, ffd_stream_t stream) {
   const int64_t n_elem = f.B * m.max_len * m.n_channels;
   float* cur = a->x;
   float* nxt = a->x_tmp;
-  for (int i = a->step_begin; i < a->step_end; ++i) {
+  // one step, directly (src.cur == nullptr) or as part of a capture (per-step parameters through the device cursor)
+  cudaStream_t ls = s;  // the stream run_step launches on: the caller's, or the capture stream
+  auto run_step = [&](int i, StepSource src) -> int {
     const ffd_step_coef& c = a->coef_host[i];
     FFD_CHECK_ARG(c.dt > 0.f, "step_size must be positive (sde.py:158,239)");
     ffd_forward_args fi = f;
     fi.X = cur;
-    fi.time_emb = a->time_emb_table + (int64_t)i * m.d_model;
+    fi.time_emb = src.cur ? a->time_emb_table : a->time_emb_table + (int64_t)i * m.d_model;
     const int n_own = a->n_own_host[i];
     if (n_own < 0) {
       fi.mode = FFD_MODE_STOCK;
@@ -526,37 +560,111 @@ int ffd_sample_steps(const ffd_sample_args* a, ffd_stream_t stream) {
       FFD_CHECK_ARG(n_own <= m.max_len && fi.k_cache && fi.v_cache, "bad cached step %d", i);
     }
     if (!(a->store_crf_host && a->store_crf_host[i])) fi.crf_out = nullptr;
-    if ((rc = forward_hidden(fi, ar, ws, s, a->event, i))) return rc;
-    const float* z = a->noise ? a->noise + (int64_t)(i - a->noise_step0) * n_elem : nullptr;
+    int rc2;
+    if ((rc2 = forward_hidden(fi, ar, ws, ls, a->event, i, src.cur ? &src.cur->ctr : nullptr))) return rc2;
+    const float* z = a->noise ? (src.cur ? a->noise : a->noise + (int64_t)(i - a->noise_step0) * n_elem) : nullptr;
     if (a->fresca && !(a->fresca->low_scale == 1.0f && a->fresca->high_scale_host[i] == 1.0f)) {
       // score -> FreSca filter -> SDE update (sampler.py:79-101); three more launches, no host sync
       const ffd_fresca_args& fr = *a->fresca;
       float* raw = fr.scratch + fresca_scratch_floats(f.B, m.max_len, m.n_channels);
       float* filt = raw + n_elem;
-      if ((rc = launch_unembed_step(ws.h, f.weights + ar.unemb_w, f.weights + ar.unemb_b, raw, 0, nullptr, nullptr,
-                                    nullptr, nullptr, 0, 0, nullptr, f.B * m.max_len, m.max_len, m.n_channels,
-                                    m.d_model, s)))
-        return rc;
-      if ((rc = launch_fresca(fr.U, fr.V, raw, filt, fr.scratch, f.B, m.max_len, m.n_channels, fr.low_scale,
-                              fr.high_scale_host[i], fr.cutoff_ratio, fr.strategy, s)))
-        return rc;
+      if ((rc2 = launch_unembed_step(ws.h, f.weights + ar.unemb_w, f.weights + ar.unemb_b, raw, 0, nullptr, nullptr,
+                                     nullptr, nullptr, 0, 0, nullptr, f.B * m.max_len, m.max_len, m.n_channels,
+                                     m.d_model, ls)))
+        return rc2;
+      if ((rc2 = launch_fresca(fr.U, fr.V, raw, filt, fr.scratch, f.B, m.max_len, m.n_channels, fr.low_scale,
+                               fr.high_scale_host[i], fr.cutoff_ratio, fr.strategy, ls)))
+        return rc2;
       if (f.score)
-        FFD_CHECK_CUDA(cudaMemcpyAsync(f.score, filt, sizeof(float) * n_elem, cudaMemcpyDeviceToDevice, s));
-      if ((rc = launch_sde_step(&c, a->G, cur, filt, z, a->seed, a->stream_base + (uint64_t)i, nxt, f.B, m.max_len,
-                                m.n_channels, s)))
-        return rc;
-      float* t = cur;
-      cur = nxt;
-      nxt = t;
-      continue;
+        FFD_CHECK_CUDA(cudaMemcpyAsync(f.score, filt, sizeof(float) * n_elem, cudaMemcpyDeviceToDevice, ls));
+      if ((rc2 = launch_sde_step(&c, a->G, cur, filt, z, a->seed, a->stream_base + (uint64_t)i, nxt, f.B, m.max_len,
+                                 m.n_channels, ls)))
+        return rc2;
+    } else if ((rc2 = launch_unembed_step(ws.h, f.weights + ar.unemb_w, f.weights + ar.unemb_b, f.score, 1, &c, a->G,
+                                          cur, z, a->seed, a->stream_base + (uint64_t)i, nxt, f.B * m.max_len,
+                                          m.max_len, m.n_channels, m.d_model, ls, src))) {
+      return rc2;
     }
-    if ((rc = launch_unembed_step(ws.h, f.weights + ar.unemb_w, f.weights + ar.unemb_b, f.score, 1, &c, a->G, cur, z,
-                                  a->seed, a->stream_base + (uint64_t)i, nxt, f.B * m.max_len, m.max_len,
-                                  m.n_channels, m.d_model, s)))
-      return rc;
     float* t = cur;
     cur = nxt;
     nxt = t;
+    if (!src.cur && n_own == 0) g_pure_step_ran = true;
+    return FFD_OK;
+  };
+  // a step that a captured pair may stand for: pure cache, nothing step-specific on the host side
+  auto graphable = [&](int i) {
+    return a->graph && a->graph_scratch && !a->event && !a->fresca && a->n_own_host[i] == 0 &&
+           !(a->store_crf_host && a->store_crf_host[i]) && f.k_cache && f.v_cache;
+  };
+  StepCursor* d_cur = (StepCursor*)a->graph_scratch;
+  ffd_step_coef* d_coefs = a->graph_scratch ? (ffd_step_coef*)((char*)a->graph_scratch + graph_coef_offset()) : nullptr;
+  bool tables_up = false;
+  int i = a->step_begin;
+  while (i < a->step_end) {
+    int run = 0;
+    while (i + run < a->step_end && graphable(i + run)) ++run;
+    run &= ~1;  // whole pairs: the state is back in `cur` after every replay
+    if (run < 4 || !g_pure_step_ran) {  // too short to pay for a capture (or nothing warmed up yet): direct launches
+      if ((rc = run_step(i, StepSource{nullptr, nullptr}))) return rc;
+      ++i;
+      continue;
+    }
+    FFD_CHECK_ARG(a->graph_scratch_bytes >= ffd_graph_scratch_bytes(a->step_end), "graph_scratch too small");
+    if (!tables_up) {
+      FFD_CHECK_CUDA(cudaMemcpyAsync(d_coefs, a->coef_host, sizeof(ffd_step_coef) * a->step_end, cudaMemcpyHostToDevice, s));
+      tables_up = true;
+    }
+    const StepCursor hc = {i, a->noise_step0, a->seed, a->stream_base};
+    FFD_CHECK_CUDA(cudaMemcpyAsync(d_cur, &hc, sizeof(hc), cudaMemcpyHostToDevice, s));
+    GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.dims = m, key.precision = f.precision, key.B = f.B, key.weights = f.weights, key.packed = f.packed;
+    key.workspace = f.workspace, key.k_cache = f.k_cache, key.v_cache = f.v_cache, key.score = f.score, key.G = a->G;
+    key.te = a->time_emb_table, key.noise = a->noise, key.x = cur, key.x_tmp = nxt, key.scratch = a->graph_scratch;
+    key.fused = tc_layer_enabled(m) ? 1 : 0;
+    GraphEntry* ge = nullptr;
+    for (auto& e : g_graphs)
+      if (e.used && memcmp(&e.key, &key, sizeof(key)) == 0) ge = &e;
+    if (!ge) {
+      // capture two steps (a pure-cache step has run directly before: every lazy initialisation is done)
+      // on a stream of the library's own: the caller's may be the legacy default stream, which cannot capture
+      static cudaStream_t cap = nullptr;
+      if (!cap) FFD_CHECK_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+      const unsigned long long l0 = g_launches;
+      FFD_CHECK_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed));
+      const StepSource src = {d_cur, d_coefs};
+      int rcc = FFD_OK;
+      ls = cap;
+      for (int k = 0; k < 2 && rcc == FFD_OK; ++k) {
+        rcc = run_step(i + k, src);
+        if (rcc == FFD_OK) rcc = launch_step_advance(d_cur, cap);
+      }
+      ls = s;
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+      if (rcc != FFD_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        (void)cudaGetLastError();
+        if (rcc == FFD_OK) set_error("CUDA graph capture of the step loop failed: %s", cudaGetErrorString(ce));
+        return rcc != FFD_OK ? rcc : FFD_ERR_CUDA;
+      }
+      GraphEntry& slot = g_graphs[g_graph_next];
+      g_graph_next = (g_graph_next + 1) % 8;
+      if (slot.used) cudaGraphExecDestroy(slot.exec);
+      slot.used = false;
+      FFD_CHECK_CUDA(cudaGraphInstantiate(&slot.exec, graph, 0));
+      cudaGraphDestroy(graph);
+      slot.key = key;
+      slot.launches = g_launches - l0;
+      g_launches = l0;  // nothing ran during the capture; replays are counted below
+      slot.used = true;
+      ge = &slot;
+    }
+    for (int r = 0; r < run / 2; ++r) {
+      FFD_CHECK_CUDA(cudaGraphLaunch(ge->exec, s));
+      __atomic_fetch_add(&g_launches, ge->launches, __ATOMIC_RELAXED);
+    }
+    i += run;
   }
   if (cur != a->x)
     FFD_CHECK_CUDA(cudaMemcpyAsync(a->x, cur, sizeof(float) * n_elem, cudaMemcpyDeviceToDevice, s));

@@ -130,6 +130,20 @@ static inline Workspace carve(const ffd_dims& m, int64_t B, void* base, bool lea
   return w;
 }
 
+// ---- per-step parameters read from DEVICE memory (CUDA-graph replay of the step loop, ffd_api.cu) ----------------
+// A graph node's arguments are frozen at capture; what changes from step to step (time-embedding row, SDE scalars,
+// Philox stream, injected-noise slice) is looked up through a step counter that a one-thread kernel advances.
+struct StepCursor {
+  int32_t ctr;          // absolute index of the step being executed
+  int32_t noise_step0;  // absolute step index of noise[0]
+  uint64_t seed;
+  uint64_t stream_base; // Philox stream id of step 0
+};
+struct StepSource {     // all DEVICE pointers; cur == nullptr: arguments are taken by value as usual
+  const StepCursor* cur;
+  const ffd_step_coef* coefs;  // [n_steps]
+};
+
 // ---- device helpers --------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

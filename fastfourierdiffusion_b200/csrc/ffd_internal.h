@@ -5,8 +5,9 @@
 namespace ffd {
 
 // ffd_simt.cu
+// step_ctr != nullptr: te is the whole [n_steps, d] table and the row is picked on the device (te + *step_ctr * d)
 int launch_embed(const float* X, const float* We, const float* be, const float* pos, const float* te, float* h,
-                 int64_t M, int L, int C, int d, cudaStream_t s);
+                 int64_t M, int L, int C, int d, cudaStream_t s, const int32_t* step_ctr = nullptr);
 int launch_linear(const float* A, int lda, const float* W, int ldw, const float* bias, float* Y, int ldy,
                   int64_t M, int N, int K, int relu, cudaStream_t s);
 int launch_attention(const float* qkv, int ldq, const float* kc, const float* vc, const int32_t* own_mask,
@@ -19,7 +20,10 @@ int launch_scatter_kv(const float* src, int lds, int k_off, int v_off, const int
                       float* kc, float* vc, int L, int H, int hd, cudaStream_t s);
 int launch_unembed_step(const float* h, const float* Wu, const float* bu, float* score_out, int do_step,
                         const ffd_step_coef* coef, const float* G, const float* x, const float* z, uint64_t seed,
-                        uint64_t stream_id, float* x_out, int64_t M, int L, int C, int d, cudaStream_t s);
+                        uint64_t stream_id, float* x_out, int64_t M, int L, int C, int d, cudaStream_t s,
+                        StepSource src = StepSource{nullptr, nullptr});
+// *ctr += 1 (one thread): closes a step of a captured step loop
+int launch_step_advance(StepCursor* cur, cudaStream_t s);
 int launch_sde_step(const ffd_step_coef* c, const float* G, const float* x, const float* score, const float* z,
                     uint64_t seed, uint64_t stream_id, float* x_out, int64_t B, int L, int C, cudaStream_t s);
 int launch_prior(const float* G, const float* z, uint64_t seed, uint64_t stream_id, float scale, float* x_out,

@@ -12,9 +12,10 @@ namespace ffd {
 __global__ void embed_kernel(const float* __restrict__ X, const float* __restrict__ We,
                              const float* __restrict__ be, const float* __restrict__ pos,
                              const float* __restrict__ te, float* __restrict__ h, int64_t M, int L, int C,
-                             int d) {
+                             int d, const int32_t* __restrict__ step_ctr) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * d) return;
+  if (step_ctr) te += (int64_t)*step_ctr * d;
   const int64_t m = idx / d;
   const int j = (int)(idx - m * d);
   const int l = (int)(m % L);
@@ -30,7 +31,8 @@ constexpr int EMB_ROWS = 128;
 __global__ void __launch_bounds__(256)
 embed4_kernel(const float* __restrict__ X, const float* __restrict__ We, const float* __restrict__ be,
               const float* __restrict__ pos, const float* __restrict__ te, float4* __restrict__ h, int64_t M, int L,
-              int C, int d4) {
+              int C, int d4, const int32_t* __restrict__ step_ctr) {
+  if (step_ctr) te += (int64_t)*step_ctr * (d4 * 4);
   const int64_t m0 = (int64_t)blockIdx.x * EMB_ROWS;
   const int rows = M - m0 < EMB_ROWS ? (int)(M - m0) : EMB_ROWS;
   const int l0 = (int)(m0 % L);
@@ -64,17 +66,17 @@ embed4_kernel(const float* __restrict__ X, const float* __restrict__ We, const f
 }
 
 int launch_embed(const float* X, const float* We, const float* be, const float* pos, const float* te, float* h,
-                 int64_t M, int L, int C, int d, cudaStream_t s) {
+                 int64_t M, int L, int C, int d, cudaStream_t s, const int32_t* step_ctr) {
   const bool aligned = d % 4 == 0 && ((uintptr_t)be % 16 == 0) && ((uintptr_t)pos % 16 == 0) &&
                        ((uintptr_t)te % 16 == 0) && ((uintptr_t)h % 16 == 0);
   if (aligned) {
     embed4_kernel<<<(unsigned)((M + EMB_ROWS - 1) / EMB_ROWS), 256, 0, s>>>(X, We, be, pos, te, (float4*)h, M, L, C,
-                                                                              d / 4);
+                                                                              d / 4, step_ctr);
     FFD_CHECK_LAUNCH("embed4_kernel");
     return FFD_OK;
   }
   const int64_t n = M * d;
-  embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(X, We, be, pos, te, h, M, L, C, d);
+  embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(X, We, be, pos, te, h, M, L, C, d, step_ctr);
   FFD_CHECK_LAUNCH("embed_kernel");
   return FFD_OK;
 }
@@ -435,9 +437,16 @@ unembed_step_kernel(const float* __restrict__ h, const float* __restrict__ Wu, c
                     float* __restrict__ score_out, int do_step, ffd_step_coef coef,
                     const float* __restrict__ G, const float* __restrict__ x, const float* __restrict__ z,
                     uint64_t seed, uint64_t stream_id, float* __restrict__ x_out, int64_t M, int L, int C,
-                    int d) {
+                    int d, StepSource src) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
+  if (src.cur) {  // per-step parameters from device memory (captured step loop)
+    const StepCursor sc = *src.cur;
+    coef = src.coefs[sc.ctr];
+    seed = sc.seed;
+    stream_id = sc.stream_base + (uint64_t)sc.ctr;
+    if (z) z += (int64_t)(sc.ctr - sc.noise_step0) * (M * C);
+  }
   const int lane = threadIdx.x & 31;
   float hv[8];
 #pragma unroll
@@ -480,8 +489,15 @@ unembed_step_tiled_kernel(const float* __restrict__ h, const float* __restrict__
                           float* __restrict__ score_out, int do_step, ffd_step_coef coef,
                           const float* __restrict__ G, const float* __restrict__ x, const float* __restrict__ z,
                           uint64_t seed, uint64_t stream_id, float* __restrict__ x_out, int64_t M, int L, int C,
-                          int d) {
+                          int d, StepSource step_src) {
   extern __shared__ float sm[];
+  if (step_src.cur) {  // per-step parameters from device memory (captured step loop)
+    const StepCursor sc = *step_src.cur;
+    coef = step_src.coefs[sc.ctr];
+    seed = sc.seed;
+    stream_id = sc.stream_base + (uint64_t)sc.ctr;
+    if (z) z += (int64_t)(sc.ctr - sc.noise_step0) * (M * C);
+  }
   float* hs = sm;                    // [UT][d+1]
   float* ws = sm + UT * (d + 1);     // [C][d]
   const int64_t row0 = (int64_t)blockIdx.x * UT;
@@ -540,7 +556,8 @@ unembed_step_tiled_kernel(const float* __restrict__ h, const float* __restrict__
 
 int launch_unembed_step(const float* h, const float* Wu, const float* bu, float* score_out, int do_step,
                         const ffd_step_coef* coef, const float* G, const float* x, const float* z, uint64_t seed,
-                        uint64_t stream_id, float* x_out, int64_t M, int L, int C, int d, cudaStream_t s) {
+                        uint64_t stream_id, float* x_out, int64_t M, int L, int C, int d, cudaStream_t s,
+                        StepSource src) {
   if (d > 256) {
     set_error("d_model %d > 256 unsupported", d);
     return FFD_ERR_UNSUPPORTED;
@@ -553,13 +570,21 @@ int launch_unembed_step(const float* h, const float* Wu, const float* bu, float*
       FFD_CHECK_CUDA(cudaFuncSetAttribute(unembed_step_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
     unembed_step_tiled_kernel<<<(unsigned)((M + UT - 1) / UT), UT, smem, s>>>(h, Wu, bu, score_out, do_step, c, G, x,
-                                                                              z, seed, stream_id, x_out, M, L, C, d);
+                                                                              z, seed, stream_id, x_out, M, L, C, d, src);
     FFD_CHECK_LAUNCH("unembed_step_tiled_kernel");
     return FFD_OK;
   }
   unembed_step_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(h, Wu, bu, score_out, do_step, c, G, x, z, seed,
-                                                              stream_id, x_out, M, L, C, d);
+                                                              stream_id, x_out, M, L, C, d, src);
   FFD_CHECK_LAUNCH("unembed_step_kernel");
+  return FFD_OK;
+}
+
+__global__ void step_advance_kernel(StepCursor* cur) { cur->ctr += 1; }
+
+int launch_step_advance(StepCursor* cur, cudaStream_t s) {
+  step_advance_kernel<<<1, 1, 0, s>>>(cur);
+  FFD_CHECK_LAUNCH("step_advance_kernel");
   return FFD_OK;
 }
 

@@ -267,7 +267,14 @@ typedef struct ffd_sample_args {
   const ffd_event_args* event; /* HOST struct or NULL: device-decided schedule for cached steps with n_own_host == 0 */
   const ffd_fresca_args* fresca; /* HOST struct or NULL: filter the score of every step (a step whose scales are both
                                     1 is left alone, fresca.py:150-152) */
+  int32_t graph;               /* != 0: runs of pure-cache steps are captured once (two steps) as a CUDA graph and replayed;
+                                  per-step scalars are then read from graph_scratch on the device.  For the launch-bound
+                                  regime (small batches): same kernels, same results. */
+  void* graph_scratch;         /* DEVICE, ffd_graph_scratch_bytes(step_end) bytes (only with graph != 0) */
+  int64_t graph_scratch_bytes;
 } ffd_sample_args;
+
+int64_t ffd_graph_scratch_bytes(int32_t n_steps);
 
 int ffd_sample_steps(const ffd_sample_args* a, ffd_stream_t stream);
 

@@ -775,3 +775,30 @@ def test_sample_time_domain_equals_idft_of_sample():
     want = O.idft(F.DiffusionSampler(m, 4, use_cache=True, cache_kwargs=dict(K=2, R=100), noise="philox",
                                      seed=9).sample(8, 12).numpy().astype(np.float64) * std.numpy() + mean.numpy())
     assert rel(outs[1].numpy(), want) < 2e-5
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("noise", ["philox", "torch"])
+def test_graph_replay_equals_direct_launches(prec, noise, monkeypatch):
+    """The captured-and-replayed step loop (ffd_sample_args.graph: two pure-cache steps per CUDA graph, per-step scalars
+    read from device memory) runs the same kernels on the same data as step-by-step launches: identical bits, for
+    in-kernel Philox noise and for injected (torch) noise, across several sampler batches that share one cache."""
+    import fastfourierdiffusion_b200 as F
+    from fastfourierdiffusion_b200 import _lib
+
+    m = build_seeded_model(ECG, 42, precision=prec)
+    _skip_unless(prec, m)
+    m = m.to("cuda").eval()
+    lib = _lib.load()
+    outs, launches = {}, {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("FFD_GRAPH", mode)
+        s = F.DiffusionSampler(m, 4, use_cache=True, cache_kwargs=dict(K=5, R=10), noise=noise, seed=9)
+        torch.manual_seed(5)
+        n0 = lib.ffd_launch_count()
+        outs[mode] = s.sample(12, 45)  # 3 sampler batches x 45 steps: CRF-store steps every 10 break the runs
+        launches[mode] = lib.ffd_launch_count() - n0
+        assert torch.isfinite(outs[mode]).all()
+    assert torch.equal(outs["0"], outs["1"])
+    # replays are counted kernel by kernel; the graph adds one 1-thread cursor kernel per replayed step
+    assert launches["0"] <= launches["1"] <= launches["0"] + 3 * 45, launches
