@@ -185,34 +185,55 @@ def build_model(precision: str):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_port_throughput(state_dict, budget_s: float, n_threads: int, steps=None, warmup=0):
-    """samples/sec of the torch-CPU port on a bounded sample; returns (value, sample description, ms/step)."""
+def cpu_backend():
+    """"reference": the unmodified reference classes from oracle/_ref (vendored by build() where the upstream checkout
+    exists; travels to the GPU box with the snapshot); "port": oracle/torch_port.py when that copy is absent."""
+    try:
+        from oracle import ref_runner
+
+        if ref_runner.available():
+            return "reference"
+    except Exception:
+        pass
+    return "port"
+
+
+def cpu_steps(kind, state_dict, batch, steps, n_threads):
+    """Seconds per schedule step (dict step -> s) of the CPU implementation on a fresh batch and a fresh cache."""
     import torch
 
+    torch.set_num_threads(n_threads)
+    if kind == "reference":
+        from oracle import ref_runner
+
+        t, _ = ref_runner.time_reference_steps(dict(ECG), batch, steps, N_DIFFUSION_STEPS, n_threads=n_threads)
+        return t
     from oracle.torch_port import TorchPort, time_cached_steps
 
-    torch.set_num_threads(n_threads)
     port = TorchPort(state_dict, ECG["max_len"], ECG["n_channels"], ECG["n_head"], "vp", True)
+    t, _ = time_cached_steps(port, batch, steps, N_DIFFUSION_STEPS)
+    return t
+
+
+def cpu_port_throughput(state_dict, budget_s: float, n_threads: int, steps=None, warmup=0):
+    """samples/sec of the reference's CPU implementation (oracle/_ref, else the torch-CPU port) on a bounded sample;
+    returns (value, sample description, ms/step, kind)."""
+    kind = cpu_backend()
     # calibrate the batch so the run fits the budget
-    probe, _ = time_cached_steps(port, 4, [0, 1], N_DIFFUSION_STEPS)
+    probe = cpu_steps(kind, state_dict, 4, [0, 1], n_threads)
     per_sample = max(probe[1], 1e-4) / 4
     if steps is None:  # cpu_baseline leg: full + 3 pure + refresh step, extrapolated over the schedule
         b = int(max(4, min(64, budget_s / (6 * per_sample))))
-        port.k_cache = port.v_cache = None
-        t, _ = time_cached_steps(port, b, [0, 1, 2, 3, 500], N_DIFFUSION_STEPS)
+        t = cpu_steps(kind, state_dict, b, [0, 1, 2, 3, 500], n_threads)
         pure = (t[1] + t[2] + t[3]) / 3
         total = t[0] + t[500] + (N_DIFFUSION_STEPS - 2) * pure
         return b / total, (f"batch {b}: schedule steps 0 (full), 1-3 (pure cache), 500 (refresh) timed, "
-                           f"1000-step run = full + refresh + 998 x mean pure step"), total / N_DIFFUSION_STEPS * 1e3
+                           f"1000-step run = full + refresh + 998 x mean pure step"), total / N_DIFFUSION_STEPS * 1e3, kind
     k = len(steps)
-    b = int(max(1, min(64, budget_s / ((k + warmup) * per_sample))))
-    port.k_cache = port.v_cache = None
-    if warmup:
-        time_cached_steps(port, b, list(range(1, 1 + warmup)), N_DIFFUSION_STEPS)
-        port.k_cache = port.v_cache = None
-    t, _ = time_cached_steps(port, b, steps, N_DIFFUSION_STEPS)
+    b = int(max(1, min(64, budget_s / ((k + warmup + 2) * per_sample))))
+    t = cpu_steps(kind, state_dict, b, list(steps), n_threads)  # the probe above was the warm-up (thread pool, allocator)
     mean = sum(t.values()) / k
-    return b / (mean * N_DIFFUSION_STEPS), f"batch {b}: schedule steps 0..{k - 1} of the 1000-step grid", mean * 1e3
+    return b / (mean * N_DIFFUSION_STEPS), f"batch {b}: schedule steps 0..{k - 1} of the 1000-step grid", mean * 1e3, kind
 
 
 def run_reference(args):
@@ -226,8 +247,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     model = build_model("fp32")
     sd = {k: v for k, v in model.state_dict().items()}
-    value, sample, ms = cpu_port_throughput(sd, budget_s=150.0, n_threads=cores, steps=list(range(args.steps)),
-                                            warmup=args.warmup)
+    value, sample, ms, kind = cpu_port_throughput(sd, budget_s=150.0, n_threads=cores, steps=list(range(args.steps)),
+                                                  warmup=args.warmup)
     # informational: the same ATen op sequence (stock torch eager, TF32 matmuls) on one GPU of the box -- what the
     # unmodified reference's operators would reach on this hardware.  Not the arm's value.
     on_gpu = None
@@ -262,9 +283,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "arm": "CPU torch port of the reference path (oracle/torch_port.py), fp32",
+        "config": {"workload": WORKLOAD,
+                   "arm": ("the UNMODIFIED reference classes (oracle/_ref, vendored from the upstream checkout by build()) "
+                           "driven step by step as DiffusionSampler.sample does, CPU fp32" if kind == "reference" else
+                           "CPU torch port of the reference path (oracle/torch_port.py), fp32"),
                    "torch_threads": torch.get_num_threads(), "reference_ops_on_gpu": on_gpu},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -503,8 +527,8 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        v, sample, _ = cpu_port_throughput(cpu_state, budget_s=20.0, n_threads=cores)
-        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
+        v, sample, _, kind = cpu_port_throughput(cpu_state, budget_s=20.0, n_threads=cores)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample}
 
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,

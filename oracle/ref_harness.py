@@ -21,8 +21,8 @@ from typing import Callable, Dict, List, Optional
 REFERENCE_ROOT = os.environ.get("FFD_REFERENCE_ROOT", "/root/reference")
 
 
-def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "fdiff"))
+def reference_available(root: Optional[str] = None) -> bool:
+    return os.path.isdir(os.path.join(root or REFERENCE_ROOT, "src", "fdiff"))
 
 
 def _install_stubs() -> None:
@@ -64,12 +64,14 @@ def _install_stubs() -> None:
         sys.modules["diffusers.optimization"] = do
 
 
-def load_reference():
-    """Return a namespace with the reference's hot-path classes."""
-    if not reference_available():
-        raise RuntimeError(f"reference checkout not found at {REFERENCE_ROOT}")
+def load_reference(root: Optional[str] = None):
+    """Return a namespace with the reference's hot-path classes (``root``: a directory holding ``src/fdiff``, default
+    the upstream checkout; ``oracle/_ref`` is the copy ``oracle/ref_runner.vendor`` makes for the GPU box)."""
+    root = root or REFERENCE_ROOT
+    if not reference_available(root):
+        raise RuntimeError(f"reference checkout not found at {root}")
     _install_stubs()
-    src = os.path.join(REFERENCE_ROOT, "src")
+    src = os.path.join(root, "src")
     if src not in sys.path:
         sys.path.insert(0, src)
     # The upstream ``fdiff`` is a namespace package (no top-level __init__.py); this repository's drop-in ``fdiff``

@@ -10,3 +10,6 @@ python tools/prof_kernels.py --kernel ffn > gpurun_out/plain_ffn_$T.log 2>&1 && 
 python tools/prof_kernels.py --kernel layer > gpurun_out/plain_attn_$T.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:attn_cached_tc -s 12 -c 1 -o gpurun_out/prof_attn_$T -f python tools/prof_kernels.py --kernel layer > gpurun_out/ncu_attn_$T.log 2>&1
 fi
 echo capture done
+if [ "$2" = "full" ]; then
+FFD_FUSED_LAYER=1 python tools/prof_layer.py 8192 > gpurun_out/plain_fused_$T.log 2>&1 && FFD_FUSED_LAYER=1 ncu --set full --clock-control none --import-source on -k regex:layer_cached -s 1 -c 1 -o gpurun_out/prof_fused_$T -f python tools/prof_layer.py 8192 > gpurun_out/ncu_fused_$T.log 2>&1
+fi
