@@ -238,6 +238,7 @@ static size_t graph_coef_offset() { return 32; }
 namespace ffd {
 extern long long* g_attn_dbg;
 void tc_debug_set_ffn_pairs(int mode);
+void tc_debug_set_attn_quarters(int mode);
 }
 using namespace ffd;
 
@@ -246,6 +247,8 @@ extern "C" {
 void ffd_debug_set_attn_stamps(long long* dev_buf) { ffd::g_attn_dbg = dev_buf; }
 // test / A-B hook (not part of the ABI header): 1 = FFN on CTA pairs, 0 = one-CTA kernel, -1 = FFD_FFN_CTA2 / default
 void ffd_debug_set_ffn_pairs(int mode) { ffd::tc_debug_set_ffn_pairs(mode); }
+// 1 = attention kernel v12 (four independent quarter streams), 0 = v11, -1 = FFD_ATTN_QUARTERS / default
+void ffd_debug_set_attn_quarters(int mode) { ffd::tc_debug_set_attn_quarters(mode); }
 // 1 = pure-cache layers as ONE fused kernel, 0 = attention + FFN kernels, -1 = FFD_FUSED_LAYER / default (off)
 void ffd_debug_set_fused_layer(int mode) { ffd::tc_debug_set_fused_layer(mode); }
 int ffd_version(void) { return 1; }

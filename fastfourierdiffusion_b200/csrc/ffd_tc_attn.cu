@@ -37,6 +37,7 @@
 // Lown > 0 runs STOCK attention with the same code: tiles are aligned to samples and every sample brings its own
 // K/V images (kv_own_tc_kernel below builds them with the K/V projection fused in).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "ffd_tc_ptx.cuh"
 
@@ -44,6 +45,7 @@ namespace ffd {
 namespace tc {
 
 constexpr int ATT_THREADS = 896;
+constexpr int ATT2_THREADS = 1024;  // v12: + one warpgroup of four MMA-issuing warps
 constexpr int K_STAGES = 3;    // K image ring
 constexpr int V_STAGES = 2;    // V image ring
 constexpr int HP = 16;         // slots per Q tile (UMMA K of the score MMA, N of the PV MMA)
@@ -57,6 +59,9 @@ constexpr int SCR_COLS = 64;   // TMEM scratch columns (Q projection / out-proj 
 #endif
 #ifndef FFD_STAGGER_NS
 #define FFD_STAGGER_NS 250   // start-up offset between the four softmax warps of a sub-partition
+#endif
+#ifndef FFD_ATTN_RING
+#define FFD_ATTN_RING 0  // v12: 1 / 2 = pass the exponential phase round the four softmax groups / two sets of two
 #endif
 constexpr uint32_t POLY_PAIRS = FFD_POLY_PAIRS;
 
@@ -728,6 +733,624 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
 #undef FFD_STAMP
 }
 
+// ---- v12 (EXPERIMENT, compiled only with -DFFD_BUILD_ATTN_QUARTERS): four independent quarter streams ------------
+// Timeline of v11 (tools/attn_stamps.py): every softmax warp spends ~1540 of ~2050 cycles per head in its exponential
+// phases; all sixteen move in lock-step through one score buffer and one P barrier, so the MUFU pipe idles the other
+// 25 % for everybody at once.  Here every quarter of the keys is its own pipeline: its own score MMA (N = 16 KQ) into
+// one of its own two score buffers, P written in place over the scores, its own P.V chain, barriers and MMA-issuing
+// warp (1024 threads).  TMEM: S/P 4 x 2 x 16 KQ, O 64, scratch 64 = 512 columns.  Results equal v11's to 2.5e-5.
+// Measured (ECG, 16 384 samples, attention block incl. image pack): v11 2.02 ms; v12 2.22 ms; v12 with the
+// exponential phase passed round the groups by named barriers (FFD_ATTN_RING) 2.33 ms (two sets of two groups) and
+// 2.91 ms (one group at a time).  Why it loses: one warp alone needs ~750 cycles for the 42 MUFU + 3 polynomial pairs
+// of a head (8 cycles per MUFU would be 336) -- the exponential phase is latency-bound per warp, and it is exactly the
+// four-warps-in-step interleaving of v11 that keeps the pipe at 75 %; left alone the four streams fall back into
+// step anyway (they re-align at every tile boundary) and then expose the un-prefetched TMEM load + max (~550 cycles)
+// that v11's software pipeline hides.  Kept as the record of the experiment; not in the library.
+#ifdef FFD_BUILD_ATTN_QUARTERS
+template <int DP, int KQ>
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attn_quarters_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const uint8_t* __restrict__ wqimg,
+                      const uint8_t* __restrict__ woimg, const uint8_t* __restrict__ kvimg,
+                      const float* __restrict__ lnw, const float* __restrict__ lnb, int64_t M, int d, int H, int hd,
+                      int G, int QN, int NCH, int64_t n_tiles, float eps, int Lown, int tps,
+                      long long* __restrict__ dbg) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int CK = 64 * KQ;   // keys per chunk
+  constexpr int NQ = 16 * KQ;   // key columns per softmax group
+  constexpr int NP = 8 * KQ;    // packed P columns per softmax group
+  const int NV = H * NCH;       // virtual heads per tile
+  const AttnSmem sm = attn_smem(DP, QN, CK, d);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);
+  uint64_t* k_full = bars;                       // [K_STAGES] tx
+  uint64_t* k_empty = k_full + K_STAGES;         // [K_STAGES] commit
+  uint64_t* v_full = k_empty + K_STAGES;         // [V_STAGES] tx
+  uint64_t* v_empty = v_full + V_STAGES;         // [V_STAGES] commit
+  uint64_t* w_full = v_empty + V_STAGES;         // [1] tx (Wq + Wo, once)
+  uint64_t* t_full = w_full + 1;                 // [2] tx: fp32 tile landed
+  uint64_t* y_ready = t_full + 2;                // [2] 128 arrivals: LayerNorm output written to the tile buffer
+  uint64_t* scr_full = y_ready + 2;              // [1] commit: a scratch pass has been computed
+  uint64_t* qbf_full = scr_full + 1;             // [2] 128 arrivals: bf16 Q tiles of a token tile written
+  uint64_t* s_full = qbf_full + 2;               // [4][2] commit: scores of quarter q of a virtual head (buffer n & 1)
+  uint64_t* p_full = s_full + 8;                 // [4][2] 128 arrivals: quarter q's P written in place over its scores
+  uint64_t* o_full = p_full + 8;                 // [1] 4 commits: the four quarter accumulators of a virtual head
+  uint64_t* o_empty = o_full + 1;                // [1] 128 arrivals (read-out warps)
+  uint64_t* obf_full = o_empty + 1;              // [1] 128 arrivals (read-out warps)
+  uint64_t* obf_empty = obf_full + 1;            // [1] commit: the out-projection has read its operand
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sm.tmem);
+  float* consts = reinterpret_cast<float*>(smem + sm.consts);
+  float* mq = reinterpret_cast<float*>(smem + sm.mq);   // [4][4][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t my_tiles = (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);  // >= 1
+  // Rows of this CTA's t-th tile.  Lown == 0: K/V are the shared cache, tiles are consecutive 128-row blocks of
+  // [0, M).  Lown > 0 (stock attention, cached_transformer.py:123-134 / nn.MultiheadAttention): every sample
+  // attends to its OWN keys, so tiles are aligned to samples (tps tiles of <= 128 rows per sample of Lown rows)
+  // and the K/V images are per sample.
+  auto tile_rows = [&](uint32_t t, int64_t& row0, int& rows, int64_t& sample) {
+    const int64_t gt = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+    if (Lown == 0) {
+      sample = 0;
+      row0 = gt * TILE_M;
+      rows = (int)(M - row0 < TILE_M ? M - row0 : TILE_M);
+    } else {
+      sample = gt / tps;
+      const int part = (int)(gt - sample * tps);
+      row0 = sample * Lown + (int64_t)part * TILE_M;
+      rows = Lown - part * TILE_M < TILE_M ? Lown - part * TILE_M : TILE_M;
+    }
+  };
+  const uint32_t n_heads = my_tiles * (uint32_t)NV;  // virtual heads this CTA runs through
+#ifdef FFD_ATTN_STAMPS  // timeline of local tile 2 of CTA 0 (tools/attn_stamps.py)
+#define FFD_STAMP(cond, slot) do { if (dbg && blockIdx.x == 0 && lane == 0 && (cond)) dbg[slot] = clock64(); } while (0)
+#else
+#define FFD_STAMP(cond, slot) do { } while (0)
+#endif
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < K_STAGES; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 4);  // the four quarter streams each commit once per image
+    }
+    for (int i = 0; i < V_STAGES; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 4);
+    }
+    mbar_init(w_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&t_full[b], 1);
+      mbar_init(&y_ready[b], 128);
+      mbar_init(&qbf_full[b], 128);
+    }
+    for (int q = 0; q < 8; ++q) {
+      mbar_init(&s_full[q], 1);
+      mbar_init(&p_full[q], 128);
+    }
+    mbar_init(scr_full, 1);
+    mbar_init(o_full, 4);
+    mbar_init(o_empty, 128);
+    mbar_init(obf_full, 128);
+    mbar_init(obf_empty, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 2 * DP; i += ATT2_THREADS) {
+    const int w = i / DP, c = i % DP;
+    consts[i] = c < d ? (w == 0 ? lnw[c] : lnb[c]) : 0.f;
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // provably warp-uniform
+
+  // register budget per warpgroup (896 threads x 72 at launch): the softmax warps hold two heads' scores
+  // (set at the top of each role branch so that ptxas allocates per branch)
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  if (warp == 0) {
+    // ================= K/V image producer =================
+    if (lane == 0) {
+      mbar_expect_tx(w_full, sm.wq_bytes + sm.wo_bytes);
+      bulk_load(smem + sm.wq, wqimg, sm.wq_bytes, w_full);
+      bulk_load(smem + sm.wo, woimg, sm.wo_bytes, w_full);
+      uint32_t nk = 0, nv = 0;
+      const size_t img_stride = (size_t)sm.k_bytes + sm.v_bytes;
+      const size_t sample_stride = Lown ? (size_t)NV * img_stride : 0;
+      auto load_k = [&](const uint8_t* base, uint32_t v) {
+        const uint32_t st = nk % K_STAGES, u = nk / K_STAGES;
+        mbar_wait_relaxed(&k_empty[st], (u & 1) ^ 1, 200);
+        mbar_expect_tx(&k_full[st], sm.k_bytes);
+        bulk_load(smem + sm.kring + st * sm.k_bytes, base + v * img_stride, sm.k_bytes, &k_full[st]);
+        ++nk;
+      };
+      auto load_v = [&](const uint8_t* base, uint32_t v) {
+        const uint32_t st = nv % V_STAGES, u = nv / V_STAGES;
+        mbar_wait_relaxed(&v_empty[st], (u & 1) ^ 1, 200);
+        mbar_expect_tx(&v_full[st], sm.v_bytes);
+        bulk_load(smem + sm.vring + st * sm.v_bytes, base + v * img_stride + sm.k_bytes, sm.v_bytes, &v_full[st]);
+        ++nv;
+      };
+      auto tile_base = [&](uint32_t t) {
+        int64_t row0, sample;
+        int rows;
+        tile_rows(t, row0, rows, sample);
+        return kvimg + (size_t)sample * sample_stride;
+      };
+      // K images run two virtual heads ahead of the V images (the score MMAs run ahead of the P.V MMAs)
+      uint32_t vk = 0, vv = 0, tk = 0, tv = 0;  // virtual head inside its tile / tile of the next K and V image
+      const uint8_t* kbase = tile_base(0);
+      const uint8_t* vbase = kbase;
+      auto next_k = [&]() {
+        load_k(kbase, vk);
+        if (++vk == (uint32_t)NV) {
+          vk = 0;
+          if (++tk < my_tiles) kbase = tile_base(tk);
+        }
+      };
+      next_k();
+      if (n_heads > 1) next_k();
+      for (uint32_t n = 0; n < n_heads; ++n) {
+        load_v(vbase, vv);
+        if (++vv == (uint32_t)NV) {
+          vv = 0;
+          if (++tv < my_tiles) vbase = tile_base(tv);
+        }
+        if (n + 2 < n_heads) next_k();
+      }
+    }
+  } else if (warp == 2) {
+    // ================= token-tile load / store =================
+    if (lane == 0) {
+      auto load_tile = [&](uint32_t t) {
+        const uint32_t b = t & 1;
+        int64_t row0, sample;
+        int rows;
+        tile_rows(t, row0, rows, sample);
+        mbar_expect_tx(&t_full[b], (uint32_t)(rows * d * 4));
+        bulk_load(smem + sm.x32 + b * sm.tile_stride, x + row0 * d, (uint32_t)(rows * d * 4), &t_full[b]);
+      };
+      load_tile(0);
+      if (my_tiles > 1) load_tile(1);
+      for (uint32_t t = 0; t < my_tiles; ++t) {
+        const uint32_t b = t & 1;
+        int64_t row0, sample;
+        int rows;
+        tile_rows(t, row0, rows, sample);
+        mbar_wait_relaxed(&y_ready[b], (t >> 1) & 1, 100);
+        bulk_store(y + row0 * d, smem + sm.x32 + b * sm.tile_stride, (uint32_t)(rows * d * 4));
+        bulk_commit();
+        bulk_wait_read();
+        if (t + 2 < my_tiles) load_tile(t + 2);  // the buffer is free again
+      }
+      bulk_wait_all();
+    }
+  }
+  } else if (warp >= 28) {
+    // ================= MMA issuers (whole warp converged, one elected lane issues): warp 28 + q serves quarter stream q.
+    // A stream's step: P.V of its quarter of virtual head n into its own accumulator, then -- behind it on the in-order
+    // tensor pipe, into the very columns P_n is read from -- the scores of its quarter of virtual head n + 2.  The
+    // scores of head n + 1 sit in the stream's other buffer already, so a softmax group never waits for an MMA round
+    // trip; the streams are independent up to the shared O read-out (one head) and the K/V image rings, so the four
+    // groups drift out of phase and the MUFU pipe of every sub-partition always finds one of its four warps in its
+    // exponential phase (v11: all sixteen warps leave it together, 25 % of every head).
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    const int q = warp - 28;
+    const uint32_t idesc_s = make_idesc(TILE_M, NQ);
+    constexpr uint32_t IDESC_PV = make_idesc_f16(TILE_M, HP);
+    constexpr uint32_t LBO128 = 128 * 16;
+    constexpr uint32_t VSTEP = (2 * HP * 16) >> 4;  // 16 keys of the V image, in 16-byte units
+    const uint32_t qbf = smem_u32(smem + sm.qbf);
+    const uint32_t kring = smem_u32(smem + sm.kring);
+    const uint32_t vring = smem_u32(smem + sm.vring);
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar = [&](const uint64_t* b) { return bar0 + (uint32_t)((b - bars) * 8); };
+    // incremental position of the NEXT score MMA of this stream: virtual head number, tile, head-in-tile counters
+    uint32_t s_n = 0, s_t = 0, s_v = 0, s_c = 0, s_g = 0, s_qt = 0;
+    auto s_advance = [&]() {
+      ++s_n;
+      if (++s_c == (uint32_t)NCH) {
+        s_c = 0;
+        if (++s_g == (uint32_t)G) s_g = 0, ++s_qt;
+      }
+      if (++s_v == (uint32_t)NV) s_v = 0, s_c = 0, s_g = 0, s_qt = 0, ++s_t;
+    };
+    auto issue_s = [&]() {  // scores of this quarter of virtual head s_n into buffer s_n & 1 (K image and Q tiles are there)
+      const uint32_t st = s_n % K_STAGES, bf = s_n & 1;
+      umma(tmem_base + COL_S + NQ * (2 * q + bf), make_desc(qbf + (s_t & 1) * sm.qbf_bytes + s_qt * 2 * LBO128, LBO128, 128),
+           make_desc(kring + st * sm.k_bytes + (uint32_t)(NQ * q / 8) * 128, CK * 16, 128), idesc_s, 0);
+      umma_commit(&s_full[2 * q + bf]);
+      umma_commit(&k_empty[st]);
+      s_advance();
+    };
+    // prologue: the first two virtual heads' scores
+    for (uint32_t i = 0; i < 2 && i < n_heads; ++i) {
+      if (s_v == 0) mbar_wait_relaxed(&qbf_full[s_t & 1], (s_t >> 1) & 1, 60);
+      mbar_wait(&k_full[s_n % K_STAGES], (s_n / K_STAGES) & 1);
+      tc_fence_after();
+      issue_s();
+    }
+    for (uint32_t n = 0; n < n_heads; ++n) {
+      const uint32_t bf = n & 1, use = n >> 1;
+      const uint32_t stv = n % V_STAGES, stk = s_n % K_STAGES;
+      const bool more = s_n < n_heads;  // s_n == n + 2 here
+      // all the barriers of this step in one round trip: lane 0 this quarter's P_n complete, 1 the previous virtual head's
+      // O read out, 2 V image landed, 3 K image of virtual head n + 2 landed, 4 its tile's Q tiles written
+      {
+        uint32_t wb = bar(&p_full[2 * q + bf]), wp = use & 1;
+        if (lane == 1) wb = bar(o_empty), wp = (n & 1) ^ 1;
+        if (lane == 2) wb = bar(&v_full[stv]), wp = (n / V_STAGES) & 1;
+        if (lane == 3 && more) wb = bar(&k_full[stk]), wp = (s_n / K_STAGES) & 1;
+        if (lane == 4 && more && s_v == 0) wb = bar(&qbf_full[s_t & 1]), wp = (s_t >> 1) & 1;
+        FFD_STAMP(n - 2u * NV < (uint32_t)NV, 1024 + (q * 32 + (n - 2u * NV)) * 4 + 0);
+        mbar_wait_lanes(wb, wp);
+      }
+      tc_fence_after();
+      FFD_STAMP(n - 2u * NV < (uint32_t)NV, 1024 + (q * 32 + (n - 2u * NV)) * 4 + 1);
+      umma_ts_chain<KQ>(tmem_base + COL_O + 16 * q, tmem_base + COL_S + NQ * (2 * q + bf), 8,
+                        make_desc(vring + stv * sm.v_bytes, HP * 16, 128) + (uint64_t)(q * KQ) * VSTEP, VSTEP, IDESC_PV, 0);
+      umma_commit(o_full);
+      umma_commit(&v_empty[stv]);
+      FFD_STAMP(n - 2u * NV < (uint32_t)NV, 1024 + (q * 32 + (n - 2u * NV)) * 4 + 2);
+      if (more) issue_s();
+      FFD_STAMP(n - 2u * NV < (uint32_t)NV, 1024 + (q * 32 + (n - 2u * NV)) * 4 + 3);
+    }
+    mbar_wait_relaxed(o_full, (n_heads - 1) & 1, 200);  // drain: nothing of this warp is in flight when the CTA exits
+  } else if (warp < 8) {
+    // ================= O read-out warps =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
+    uint8_t* ob = smem + sm.obf;
+    // constant columns of the out-proj operand: d, d+1 = 1 (bias hi/lo), the rest of the padding = 0
+    for (int c = d; c < DP; ++c)
+      *reinterpret_cast<op16*>(ob + row_off + (c >> 3) * (TILE_M * 16) + (c & 7) * 2) =
+          to_op((c == d || c == d + 1) ? 1.f : 0.f);
+    uint32_t n = 0;
+    for (uint32_t t = 0; t < my_tiles; ++t) {
+      for (int h = 0; h < H; ++h) {
+        // With hd <= 7 the row sum sits in slot 7 (pack_kv_kernel), so the low 8 columns of every quarter
+        // accumulator hold everything: ONE TMEM round trip per virtual head.  (The P.V MMA of the next head waits
+        // for this read: the round trip is on the kernel's critical loop.)
+        if (hd <= 7) {
+          float acc[8];
+          float mrun = 0.f;
+          for (int c = 0; c < NCH; ++c, ++n) {
+            mbar_wait_relaxed(o_full, n & 1, 32);
+            tc_fence_after();
+            FFD_STAMP(warp == 4 && t == 2, 256 + (h * NCH + c) * 2 + 0);
+            uint32_t r[32];
+            FFD_TMEM_LD8(tmem_base + lane_base + COL_O, r);
+            FFD_TMEM_LD8(tmem_base + lane_base + COL_O + 16, (r + 8));
+            FFD_TMEM_LD8(tmem_base + lane_base + COL_O + 32, (r + 16));
+            FFD_TMEM_LD8(tmem_base + lane_base + COL_O + 48, (r + 24));
+            // combine the four quarters: weights exp2(m_q - max m_q)
+            const float* mh = mq + ((n & 3) * 4) * TILE_M + row;
+            const float q0 = mh[0], q1 = mh[TILE_M], q2 = mh[2 * TILE_M], q3 = mh[3 * TILE_M];
+            float mm = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
+            if (c > 0) mm = fmaxf(mm, mrun);
+            const float w0 = exp2_poly3(q0 - mm), w1 = exp2_poly3(q1 - mm), w2 = exp2_poly3(q2 - mm),
+                        w3 = exp2_poly3(q3 - mm);
+            const float wp = c > 0 ? exp2_poly3(mrun - mm) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = c > 0 ? acc[j] * wp : 0.f;
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(o_empty);
+            FFD_STAMP(warp == 4 && t == 2, 256 + (h * NCH + c) * 2 + 1);
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[j]), __uint_as_float(r[j + 1]), w0, acc[j], acc[j + 1]);
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[8 + j]), __uint_as_float(r[9 + j]), w1, acc[j], acc[j + 1]);
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[16 + j]), __uint_as_float(r[17 + j]), w2, acc[j], acc[j + 1]);
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[24 + j]), __uint_as_float(r[25 + j]), w3, acc[j], acc[j + 1]);
+            }
+            mrun = mm;
+          }
+          const float inv = rcp_fma(acc[7]);
+          // the out-projection of the previous tile must have read its operand before the first overwrite
+          if (h == 0 && t >= 1) mbar_wait_relaxed(obf_empty, (t - 1) & 1, 60);
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {
+            if (j < hd) {
+              const int col = h * hd + j;
+              *reinterpret_cast<op16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                  to_op(acc[j] * inv);
+            }
+          }
+        } else {
+          float acc[HP];
+          float mrun = 0.f;
+          for (int c = 0; c < NCH; ++c, ++n) {
+            mbar_wait_relaxed(o_full, n & 1, 32);
+            tc_fence_after();
+            uint32_t r[32];
+            FFD_TMEM_LD16(tmem_base + lane_base + COL_O, r);
+            FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 16, (r + 16));
+            const float* mh = mq + ((n & 3) * 4) * TILE_M + row;
+            const float q0 = mh[0], q1 = mh[TILE_M], q2 = mh[2 * TILE_M], q3 = mh[3 * TILE_M];
+            float mm = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
+            if (c > 0) mm = fmaxf(mm, mrun);
+            const float w0 = exp2_poly3(q0 - mm), w1 = exp2_poly3(q1 - mm), w2 = exp2_poly3(q2 - mm),
+                        w3 = exp2_poly3(q3 - mm);
+            const float wp = c > 0 ? exp2_poly3(mrun - mm) : 0.f;
+#pragma unroll
+            for (int j = 0; j < HP; ++j) acc[j] = c > 0 ? acc[j] * wp : 0.f;
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < HP; j += 2) {
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[j]), __uint_as_float(r[j + 1]), w0, acc[j], acc[j + 1]);
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[16 + j]), __uint_as_float(r[17 + j]), w1, acc[j], acc[j + 1]);
+            }
+            FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 32, r);
+            FFD_TMEM_LD16(tmem_base + lane_base + COL_O + 48, (r + 16));
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(o_empty);
+#pragma unroll
+            for (int j = 0; j < HP; j += 2) {
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[j]), __uint_as_float(r[j + 1]), w2, acc[j], acc[j + 1]);
+              fma2(acc[j], acc[j + 1], __uint_as_float(r[16 + j]), __uint_as_float(r[17 + j]), w3, acc[j], acc[j + 1]);
+            }
+            mrun = mm;
+          }
+          const float inv = rcp_fma(acc[HP - 1]);
+          if (h == 0 && t >= 1) mbar_wait_relaxed(obf_empty, (t - 1) & 1, 60);
+#pragma unroll
+          for (int j = 0; j < HP - 1; ++j) {
+            if (j < hd) {
+              const int col = h * hd + j;
+              *reinterpret_cast<op16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                  to_op(acc[j] * inv);
+            }
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(obf_full);
+    }
+  } else if (warp < 12) {
+    // ================= tile warps: prepare tile t+1 / finish tile t-1 while the heads of tile t run ==========
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
+    const uint32_t scr = tmem_base + lane_base + COL_SCR;
+    uint8_t* xo = smem + sm.xo;
+    const bool lead = warp == 8;  // issues the scratch MMAs of the group (whole warp converged)
+    constexpr uint32_t LBO128 = 128 * 16;
+    const uint32_t xo_a = smem_u32(smem + sm.xo), obf_a = smem_u32(smem + sm.obf);
+    const uint32_t wq_a = smem_u32(smem + sm.wq), wo_a = smem_u32(smem + sm.wo);
+    uint32_t cs = 0;  // scratch passes so far
+    if (lead) mbar_wait(w_full, 0);
+    // One scratch pass: C[128 x N] = A[128 x DP] . W[n0.., :]^T into the scratch columns.  The group barrier makes
+    // the previous pass's reads (and this pass's operand writes) complete before the lead warp issues.
+    auto scratch_pass = [&](uint32_t a_addr, uint32_t w_addr, int w_rows, int n0, int N, uint64_t* also_commit) {
+      tc_fence_before();
+      named_bar_sync(1, 128);
+      if (lead) {
+        tc_fence_after();
+        umma_ss_chain<DP / 16>(tmem_base + COL_SCR, make_desc(a_addr, LBO128, 128), (2 * LBO128) >> 4,
+                               make_desc(w_addr + (n0 >> 3) * 128, w_rows * 16, 128), (2 * w_rows * 16) >> 4,
+                               make_idesc(TILE_M, N), 0);
+        umma_commit(scr_full);
+        if (also_commit) umma_commit(also_commit);
+      }
+      mbar_wait(scr_full, cs & 1);
+      ++cs;
+      tc_fence_after();
+    };
+    // 16 fp32 accumulator columns -> two bf16 k-groups of the Q operand
+    auto store_q16 = [&](const uint32_t (&r)[16], uint8_t* dst) {
+      uint4 q0, q1;
+      q0.x = pack_op(__uint_as_float(r[0]), __uint_as_float(r[1]));
+      q0.y = pack_op(__uint_as_float(r[2]), __uint_as_float(r[3]));
+      q0.z = pack_op(__uint_as_float(r[4]), __uint_as_float(r[5]));
+      q0.w = pack_op(__uint_as_float(r[6]), __uint_as_float(r[7]));
+      q1.x = pack_op(__uint_as_float(r[8]), __uint_as_float(r[9]));
+      q1.y = pack_op(__uint_as_float(r[10]), __uint_as_float(r[11]));
+      q1.z = pack_op(__uint_as_float(r[12]), __uint_as_float(r[13]));
+      q1.w = pack_op(__uint_as_float(r[14]), __uint_as_float(r[15]));
+      *reinterpret_cast<uint4*>(dst) = q0;
+      *reinterpret_cast<uint4*>(dst + TILE_M * 16) = q1;
+    };
+    // stage X of local tile t as the bf16 A operand, project it, and turn the result into bf16 Q tiles
+    auto prepare = [&](uint32_t t) {
+      const uint32_t tb = t & 1;
+      int64_t row0, sample;
+      int rows;
+      tile_rows(t, row0, rows, sample);
+      const bool valid = row < rows;
+      const float4* src = reinterpret_cast<const float4*>(smem + sm.x32 + tb * sm.tile_stride) + (size_t)row * (d / 4);
+      mbar_wait_relaxed(&t_full[tb], (t >> 1) & 1, 200);
+      FFD_STAMP(warp == 8 && t == 3, 404);
+      constexpr int NG = DP / 8;
+#pragma unroll 5
+      for (int kg = 0; kg < NG; ++kg) {
+        const int c = kg * 8;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
+        if (c < d) {
+          if (valid) a = src[2 * kg];
+        } else if (c == d) {
+          a.x = 1.f, a.y = 1.f;
+        }
+        if (c + 4 < d) {
+          if (valid) b4 = src[2 * kg + 1];
+        } else if (c + 4 == d) {
+          b4.x = 1.f, b4.y = 1.f;
+        }
+        uint4 q;
+        q.x = pack_op(a.x, a.y);
+        q.y = pack_op(a.z, a.w);
+        q.z = pack_op(b4.x, b4.y);
+        q.w = pack_op(b4.z, b4.w);
+        *reinterpret_cast<uint4*>(xo + row_off + kg * (TILE_M * 16)) = q;
+      }
+      fence_proxy_async();
+      FFD_STAMP(warp == 8 && t == 3, 403);
+      uint8_t* qb = smem + sm.qbf + tb * sm.qbf_bytes;
+      for (int n0 = 0; n0 < QN; n0 += SCR_COLS) {
+        const int N = QN - n0 < SCR_COLS ? QN - n0 : SCR_COLS;
+        scratch_pass(xo_a, wq_a, QN, n0, N, nullptr);
+        // two 16-column units in flight per TMEM round trip
+        for (int u = 0; u < N; u += 32) {
+          uint32_t ra[16], rb[16];
+          const bool two = u + 16 < N;
+          FFD_TMEM_LD16(scr + u, ra);
+          if (two) FFD_TMEM_LD16(scr + u + 16, rb);
+          tmem_ld_wait();
+          const int kg = (n0 + u) >> 3;
+          store_q16(ra, qb + row_off + kg * (TILE_M * 16));
+          if (two) store_q16(rb, qb + row_off + (kg + 2) * (TILE_M * 16));
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&qbf_full[tb]);
+    };
+    // out-projection of local tile t (A operand: the normalised O columns written by the read-out warps) +
+    // residual -> LayerNorm, in place in the fp32 tile buffer (one thread owns a row)
+    auto finish = [&](uint32_t t) {
+      const uint32_t tb = t & 1;
+      float4* myrow = reinterpret_cast<float4*>(smem + sm.x32 + tb * sm.tile_stride) + (size_t)row * (d / 4);
+      float s1 = 0.f, s2 = 0.f;
+      if (lead) mbar_wait_relaxed(obf_full, t & 1, 100);
+      for (int n0 = 0; n0 < DP; n0 += SCR_COLS) {
+        const int N = DP - n0 < SCR_COLS ? DP - n0 : SCR_COLS;
+        scratch_pass(obf_a, wo_a, DP, n0, N, n0 + SCR_COLS >= DP ? obf_empty : nullptr);
+        for (int u = 0; u < N; u += 16) {
+          uint32_t r[16];
+          FFD_TMEM_LD16(scr + u, r);
+          float4 res[4];  // residual: issued before the TMEM round trip completes
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = n0 + u + 4 * j;
+            res[j] = c < d ? myrow[c >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = n0 + u + 4 * j;
+            if (c < d) {
+              float4 v = res[j];
+              v.x += __uint_as_float(r[4 * j]);
+              v.y += __uint_as_float(r[4 * j + 1]);
+              v.z += __uint_as_float(r[4 * j + 2]);
+              v.w += __uint_as_float(r[4 * j + 3]);
+              myrow[c >> 2] = v;
+              s1 += (v.x + v.y) + (v.z + v.w);
+              s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+            }
+          }
+        }
+      }
+      const float mean = s1 / (float)d;
+      const float rstd = rsqrtf(fmaxf(s2 / (float)d - mean * mean, 0.f) + eps);
+#pragma unroll 6
+      for (int c = 0; c < d; c += 4) {
+        const float4 v = myrow[c >> 2];
+        float4 o;
+        o.x = (v.x - mean) * rstd * consts[c] + consts[DP + c];
+        o.y = (v.y - mean) * rstd * consts[c + 1] + consts[DP + c + 1];
+        o.z = (v.z - mean) * rstd * consts[c + 2] + consts[DP + c + 2];
+        o.w = (v.w - mean) * rstd * consts[c + 3] + consts[DP + c + 3];
+        myrow[c >> 2] = o;
+      }
+      fence_proxy_async();
+      mbar_arrive(&y_ready[tb]);
+    };
+    prepare(0);
+    for (uint32_t t = 0; t < my_tiles; ++t) {
+      FFD_STAMP(warp == 8 && t == 2, 400);
+      if (t >= 1) finish(t - 1);
+      FFD_STAMP(warp == 8 && t == 2, 401);
+      if (t + 1 < my_tiles) prepare(t + 1);
+      FFD_STAMP(warp == 8 && t == 2, 402);
+    }
+    finish(my_tiles - 1);
+    if (lead) mbar_wait_relaxed(obf_empty, (my_tiles - 1) & 1, 200);  // drain
+  } else {
+    // ================= softmax groups: group wg owns quarter wg of the key columns of every virtual head =============
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
+    const int wg = (warp - 12) >> 2;       // 0..3: quarter of the key columns
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t scol0 = tmem_base + lane_base + COL_S + 2 * wg * NQ;  // this group's two score buffers; P goes over S
+    // the four warps of a sub-partition (one per group) do identical work: start them a quarter of a head apart
+#if !FFD_ATTN_RING
+    __nanosleep(wg * FFD_STAGGER_NS);
+#endif
+    for (uint32_t n = 0; n < n_heads; ++n) {
+      const uint32_t bf = n & 1;
+      const uint32_t scol = scol0 + bf * NQ;
+      FFD_STAMP(quad == 0 && n - 2u * NV < (uint32_t)NV, 512 + (wg * 32 + (n - 2u * NV)) * 4 + 0);
+      mbar_wait(&s_full[2 * wg + bf], (n >> 1) & 1);
+      tc_fence_after();
+      FFD_STAMP(quad == 0 && n - 2u * NV < (uint32_t)NV, 512 + (wg * 32 + (n - 2u * NV)) * 4 + 1);
+      uint32_t r[16 * KQ];
+#pragma unroll
+      for (int j = 0; j < KQ; ++j) FFD_TMEM_LD16(scol + 16 * j, (r + 16 * j));
+      tmem_ld_wait();
+      // row maximum over this quarter (independent chains).  Padded keys need no mask: slot 15 of every Q tile is the
+      // constant 1 and slot 15 of a padded K row is -29952 (weight 0 in the combine).
+      float mj[KQ];
+#pragma unroll
+      for (int j = 0; j < KQ; ++j) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) m = max3(m, __uint_as_float(r[16 * j + e]), __uint_as_float(r[16 * j + e + 1]));
+        mj[j] = m;
+      }
+      float mb = mj[0];
+#pragma unroll
+      for (int j = 1; j < KQ; ++j) mb = fmaxf(mb, mj[j]);
+      float* mslot = &mq[((n & 3) * 4 + wg) * TILE_M + row];
+      *mslot = mb;
+      float mc = -mb;
+#if FFD_ATTN_RING
+      // the exponential phase goes round the four groups: every sub-partition then has exactly one of its four warps on
+      // the MUFU pipe while the other three load, reduce and store (left alone the four fall into step and the pipe
+      // idles while all of them wait on TMEM round trips)
+#if FFD_ATTN_RING == 2
+      if (n | (wg >> 1)) mc = -named_bar_sync_reload(8 + (wg >> 1), 512, mslot);  // two sets of two groups take turns
+#else
+      if (n | wg) mc = -named_bar_sync_reload(8 + wg, 256, mslot);
+#endif
+#endif
+      FFD_STAMP(quad == 0 && n - 2u * NV < (uint32_t)NV, 512 + (wg * 32 + (n - 2u * NV)) * 4 + 2);
+      // p = exp2(s - m_q) as fp16 pairs, written over this warp's own score columns: 16 KQ fp32 -> 8 KQ packed columns
+#pragma unroll
+      for (int j = 0; j < KQ; ++j) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2)
+          pk[e >> 1] = ((POLY_PAIRS >> (e >> 1)) & 1)
+                           ? ex2_pack_f16_shift_poly(__uint_as_float(r[16 * j + e]), __uint_as_float(r[16 * j + e + 1]), mc)
+                           : ex2_pack_f16_shift(__uint_as_float(r[16 * j + e]), __uint_as_float(r[16 * j + e + 1]), mc);
+        FFD_TMEM_ST8(scol + 8 * j, pk);
+      }
+#if FFD_ATTN_RING
+#if FFD_ATTN_RING == 2
+      if (wg < 2 || n + 1 < n_heads) named_bar_arrive(8 + ((wg >> 1) ^ 1), 512);
+#else
+      if (wg != 3 || n + 1 < n_heads) named_bar_arrive(8 + ((wg + 1) & 3), 256);
+#endif
+#endif
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[2 * wg + bf]);
+      FFD_STAMP(quad == 0 && n - 2u * NV < (uint32_t)NV, 512 + (wg * 32 + (n - 2u * NV)) * 4 + 3);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+#undef FFD_STAMP
+}
+#endif  // FFD_BUILD_ATTN_QUARTERS
+
 // ---- packing ---------------------------------------------------------------------------------------
 // WqP [QN n x DP k]: row 16 qt + g hd + c = Wq[(qt G + g) hd + c, :] * log2(e)/sqrt(hd), bias hi/lo in columns d,
 // d+1; row 16 qt + 15 picks the constant-1 column of X.  WoP [DP n x DP k]: row n = Wo[n, :], bias hi/lo in
@@ -1238,6 +1861,25 @@ int tc_pack_kv96_layer(const ffd_dims& m, int layer, const float* kc, const floa
 
 long long* g_attn_dbg = nullptr;  // optional device buffer of clock64 stamps (profiling aid)
 
+// attention kernel variant: 1 = v12 (four independent quarter streams), 0 = v11 (lock-step heads); -1 = FFD_ATTN_QUARTERS
+// or the default
+#ifndef FFD_ATTN_QUARTERS_DEFAULT
+#define FFD_ATTN_QUARTERS_DEFAULT 0
+#endif
+static int g_attn_quarters_mode = -1;
+void tc_debug_set_attn_quarters(int mode) { g_attn_quarters_mode = mode; }
+static bool attn_quarters_enabled() {
+  int mode = g_attn_quarters_mode;
+  if (mode < 0) {
+    static const int env_mode = [] {
+      const char* e = getenv("FFD_ATTN_QUARTERS");
+      return e ? (e[0] == '1' ? 1 : 0) : FFD_ATTN_QUARTERS_DEFAULT;
+    }();
+    mode = env_mode;
+  }
+  return mode == 1;
+}
+
 template <int DP, int KQ>
 static int launch_attn(const ffd_dims& m, const AttnGeom& g, const uint8_t* wqimg, const uint8_t* kvimg_layer,
                        const float* lnw, const float* lnb, const float* x, float* y, int64_t M, int own,
@@ -1255,6 +1897,21 @@ static int launch_attn(const ffd_dims& m, const AttnGeom& g, const uint8_t* wqim
   const int tps = (m.max_len + tc::TILE_M - 1) / tc::TILE_M;
   const int64_t n_tiles = own ? M / m.max_len * tps : (M + tc::TILE_M - 1) / tc::TILE_M;
   const unsigned grid = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);
+  if (attn_quarters_enabled()) {
+#ifdef FFD_BUILD_ATTN_QUARTERS
+    // v12: four independent quarter streams (same arguments, identical arithmetic per element)
+    FFD_CHECK_CUDA(cudaFuncSetAttribute(tc::attn_quarters_tc_kernel<DP, KQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        sm.total));
+    tc::attn_quarters_tc_kernel<DP, KQ><<<grid, tc::ATT2_THREADS, sm.total, s>>>(
+        x, y, wqimg, wqimg + (size_t)g.QN * DP * 2, kvimg_layer, lnw, lnb, M, m.d_model, m.n_head, g.hd, g.G, g.QN,
+        g.NCH, n_tiles, 1e-5f, own ? m.max_len : 0, tps, g_attn_dbg);
+    FFD_CHECK_LAUNCH("attn_quarters_tc_kernel");
+    return FFD_OK;
+#else
+    set_error("the quarter-stream attention kernel is an experiment: rebuild with -DFFD_BUILD_ATTN_QUARTERS");
+    return FFD_ERR_ARG;
+#endif
+  }
   tc::attn_cached_tc_kernel<DP, KQ><<<grid, tc::ATT_THREADS, sm.total, s>>>(
       x, y, wqimg, wqimg + (size_t)g.QN * DP * 2, kvimg_layer, lnw, lnb, M, m.d_model, m.n_head, g.hd, g.G, g.QN,
       g.NCH, n_tiles, 1e-5f, own ? m.max_len : 0, tps, g_attn_dbg);

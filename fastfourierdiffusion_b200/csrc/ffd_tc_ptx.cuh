@@ -126,6 +126,18 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// bar.sync after which v is re-read from shared memory (volatile): arithmetic that depends on the returned value
+// cannot be scheduled above the barrier by ptxas (a memory clobber orders memory operations only, and an operand the
+// asm text does not mention is no dependency at the PTX level).
+__device__ __forceinline__ float named_bar_sync_reload(int id, int nthreads, const float* v) {
+  float r;
+  asm volatile("bar.sync %1, %2;\n\tld.volatile.shared.f32 %0, [%3];"
+               : "=f"(r) : "r"(id), "r"(nthreads), "r"(smem_u32(v)) : "memory");
+  return r;
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),

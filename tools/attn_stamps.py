@@ -12,7 +12,7 @@ s = F.DiffusionSampler(model, B, use_cache=True, noise="philox")
 model.noise_scheduler.set_timesteps(1000)
 X = s.sample_prior(B); model.cache.reset()
 s.run_steps(X, 0, step_begin=0, step_end=2)
-buf = torch.zeros(512, dtype=torch.int64, device="cuda")
+buf = torch.zeros(2048, dtype=torch.int64, device="cuda")
 lib.ffd_debug_set_attn_stamps.argtypes = [ctypes.c_void_p]
 lib.ffd_debug_set_attn_stamps(buf.data_ptr())
 s.run_steps(X, 0, step_begin=1, step_end=2)
@@ -32,3 +32,12 @@ print("read-out warp 4 per head: o_full seen, o_empty arrive")
 for h in range(NV): print(h, [f(v) for v in t[256+h*2:256+h*2+2]])
 print("tile warp 8 (phase 2): start, finish(1) done, prepare(3) done | prepare(3): x staged, t_full seen")
 print([f(v) for v in t[400:405]])
+
+if os.environ.get("FFD_ATTN_QUARTERS") == "1":
+    NVH = 24
+    for g in range(4):
+        print(f"v12 softmax group {g} (warp {12+4*g}) per virtual head: top, s_full seen, max done, p_full arrive")
+        for h in range(NVH): print(h, [f(v) for v in t[512+(g*32+h)*4:512+(g*32+h)*4+4]])
+    for g in range(4):
+        print(f"v12 MMA warp {g}: before wait, after wait, PV issued, S issued")
+        for h in range(NVH): print(h, [f(v) for v in t[1024+(g*32+h)*4:1024+(g*32+h)*4+4]])
