@@ -405,12 +405,23 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
           const float inv = rcp_fma(acc[7]);
           // the out-projection of the previous tile must have read its operand before the first overwrite
           if (h == 0 && t >= 1) mbar_wait_relaxed(obf_empty, (t - 1) & 1, 60);
+          if ((hd & 1) == 0) {  // even head dim: the head's columns start even, two columns per store
 #pragma unroll
-          for (int j = 0; j < 7; ++j) {
-            if (j < hd) {
-              const int col = h * hd + j;
-              *reinterpret_cast<op16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
-                  to_op(acc[j] * inv);
+            for (int j = 0; j < 6; j += 2) {
+              if (j < hd) {
+                const int col = h * hd + j;
+                *reinterpret_cast<uint32_t*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                    pack_op(acc[j] * inv, acc[j + 1] * inv);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+              if (j < hd) {
+                const int col = h * hd + j;
+                *reinterpret_cast<op16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                    to_op(acc[j] * inv);
+              }
             }
           }
         } else {
@@ -451,12 +462,23 @@ attn_cached_tc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
           }
           const float inv = rcp_fma(acc[HP - 1]);
           if (h == 0 && t >= 1) mbar_wait_relaxed(obf_empty, (t - 1) & 1, 60);
+          if ((hd & 1) == 0) {
 #pragma unroll
-          for (int j = 0; j < HP - 1; ++j) {
-            if (j < hd) {
-              const int col = h * hd + j;
-              *reinterpret_cast<op16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
-                  to_op(acc[j] * inv);
+            for (int j = 0; j < HP - 2; j += 2) {
+              if (j < hd) {
+                const int col = h * hd + j;
+                *reinterpret_cast<uint32_t*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                    pack_op(acc[j] * inv, acc[j + 1] * inv);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < HP - 1; ++j) {
+              if (j < hd) {
+                const int col = h * hd + j;
+                *reinterpret_cast<op16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                    to_op(acc[j] * inv);
+              }
             }
           }
         }
@@ -1050,12 +1072,23 @@ attn_quarters_tc_kernel(const float* __restrict__ x, float* __restrict__ y, cons
           const float inv = rcp_fma(acc[7]);
           // the out-projection of the previous tile must have read its operand before the first overwrite
           if (h == 0 && t >= 1) mbar_wait_relaxed(obf_empty, (t - 1) & 1, 60);
+          if ((hd & 1) == 0) {  // even head dim: the head's columns start even, two columns per store
 #pragma unroll
-          for (int j = 0; j < 7; ++j) {
-            if (j < hd) {
-              const int col = h * hd + j;
-              *reinterpret_cast<op16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
-                  to_op(acc[j] * inv);
+            for (int j = 0; j < 6; j += 2) {
+              if (j < hd) {
+                const int col = h * hd + j;
+                *reinterpret_cast<uint32_t*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                    pack_op(acc[j] * inv, acc[j + 1] * inv);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+              if (j < hd) {
+                const int col = h * hd + j;
+                *reinterpret_cast<op16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                    to_op(acc[j] * inv);
+              }
             }
           }
         } else {
@@ -1096,12 +1129,23 @@ attn_quarters_tc_kernel(const float* __restrict__ x, float* __restrict__ y, cons
           }
           const float inv = rcp_fma(acc[HP - 1]);
           if (h == 0 && t >= 1) mbar_wait_relaxed(obf_empty, (t - 1) & 1, 60);
+          if ((hd & 1) == 0) {
 #pragma unroll
-          for (int j = 0; j < HP - 1; ++j) {
-            if (j < hd) {
-              const int col = h * hd + j;
-              *reinterpret_cast<op16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
-                  to_op(acc[j] * inv);
+            for (int j = 0; j < HP - 2; j += 2) {
+              if (j < hd) {
+                const int col = h * hd + j;
+                *reinterpret_cast<uint32_t*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                    pack_op(acc[j] * inv, acc[j + 1] * inv);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < HP - 1; ++j) {
+              if (j < hd) {
+                const int col = h * hd + j;
+                *reinterpret_cast<op16*>(ob + row_off + (col >> 3) * (TILE_M * 16) + (col & 7) * 2) =
+                    to_op(acc[j] * inv);
+              }
             }
           }
         }

@@ -60,13 +60,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.  try_wait suspends the
-// thread in hardware for a while before returning false, so 2^24 failed polls is seconds of waiting.
+// Bounded wait (-DFFD_WAIT_TRAPS=1, the development build): a protocol bug traps (launch error) instead of hanging
+// the GPU.  try_wait suspends the thread in hardware for a while before returning false, so 2^24 failed polls is
+// seconds of waiting.  The release build polls without the counter: the counter line was 29 % of the warp
+// instructions the FFN kernel executed (round-1 ncu), issue slots the softmax warps of the attention kernel need.
+#ifndef FFD_WAIT_TRAPS
+#define FFD_WAIT_TRAPS 0
+#endif
+#if FFD_WAIT_TRAPS
+#define FFD_POLL_GUARD(polls) do { if (++(polls) > (1u << 24)) __trap(); } while (0)
+#else
+#define FFD_POLL_GUARD(polls) do { (void)(polls); } while (0)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t polls = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++polls > (1u << 24)) __trap();
-  }
+  while (!mbar_try_wait(bar, parity)) FFD_POLL_GUARD(polls);
 }
 // Same for the roles that wait long and are not latency-critical (producers, tile warps): sleep between polls so
 // that they do not compete with the softmax warps for issue slots (the hardware wakes a suspended try_wait on
@@ -75,7 +83,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(sleep_ns);
-    if (++polls > (1u << 24)) __trap();
+    FFD_POLL_GUARD(polls);
   }
 }
 // Wait for several mbarriers AT ONCE: every lane polls its own barrier (shared-memory address + parity; lanes without
@@ -96,7 +104,7 @@ __device__ __forceinline__ void mbar_wait_lanes(uint32_t bar_addr, uint32_t pari
           : "memory");
     }
     if (__all_sync(0xffffffffu, done != 0)) break;
-    if (++polls > (1u << 24)) __trap();
+    FFD_POLL_GUARD(polls);
   }
 }
 
@@ -318,7 +326,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t polls = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++polls > (1u << 24)) __trap();
+    FFD_POLL_GUARD(polls);
   }
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
