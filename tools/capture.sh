@@ -7,7 +7,7 @@ python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/plain_$T.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_$T.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_$T.log 2>&1
 if [ "$2" = "full" ]; then
 python tools/prof_kernels.py --kernel ffn > gpurun_out/plain_ffn_$T.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:ffn_ln_tc2 -s 1 -c 1 -o gpurun_out/prof_ffn_$T -f python tools/prof_kernels.py --kernel ffn > gpurun_out/ncu_ffn_$T.log 2>&1
-python tools/prof_kernels.py --kernel layer > gpurun_out/plain_attn_$T.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:attn_cached_tc -s 12 -c 1 -o gpurun_out/prof_attn_$T -f python tools/prof_kernels.py --kernel layer > gpurun_out/ncu_attn_$T.log 2>&1
+python tools/prof_kernels.py --kernel attn > gpurun_out/plain_attn_$T.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:attn_cached_tc -s 1 -c 1 -o gpurun_out/prof_attn_$T -f python tools/prof_kernels.py --kernel attn > gpurun_out/ncu_attn_$T.log 2>&1
 fi
 echo capture done
 if [ "$2" = "full" ]; then

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Launch one of the dominant kernels a few times on ECG-sized inputs (for ncu captures).
 
-    python tools/prof_kernels.py --kernel ffn|layer [--batch 16384] [--reps 3]
+    python tools/prof_kernels.py --kernel ffn|attn|layer [--batch 16384] [--reps 3]
+
+ffn / attn launch the block's C-ABI entry point directly (attn = the pure-cache attention block on a shared K/V cache);
+layer runs whole sampler steps (step 0 = stock attention in chunks, then pure-cache steps).
 """
 import argparse
 import os
@@ -35,6 +38,17 @@ if a.kernel == "ffn":
     y = torch.empty_like(x)
     for _ in range(a.reps):
         _lib.check(lib.ffd_ffn_ln(model.dims, 1, _lib.ptr(arena), _lib.ptr(packed), 3, _lib.ptr(x), _lib.ptr(y), None, M, st))
+elif a.kernel == "attn":
+    arena, packed = model.device_weights()
+    L, d, H = model.max_len, model.d_model, model.n_head
+    x = torch.randn(M, d, device="cuda")
+    y = torch.empty_like(x)
+    kc = torch.randn(10, H, L, d // H, device="cuda")
+    vc = torch.randn(10, H, L, d // H, device="cuda")
+    ws = model.workspace(a.batch)
+    for _ in range(a.reps):
+        _lib.check(lib.ffd_attn_cached_ln(model.dims, 1, _lib.ptr(arena), _lib.ptr(packed), 3, _lib.ptr(kc), _lib.ptr(vc),
+                                          _lib.ptr(x), _lib.ptr(y), _lib.ptr(ws), ws.numel(), M, st))
 else:
     import fastfourierdiffusion_b200 as F
 
