@@ -34,6 +34,9 @@ def build(force: bool = False, verbose: bool = False, out: str = "") -> str:
     out = out or os.environ.get("FFD_LIB_OUT", "")
     if not out and not force and not needs_build():
         return LIB
+    # The CUDA runtime is linked statically on purpose: the library is loaded next to torch, whose wheel brings its own
+    # libcudart.so.12 of a different minor version (12.8 vs this toolkit's 12.9); a shared runtime would bind our
+    # 12.9-compiled host stubs to whichever copy the process loaded first.
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     cmd += os.environ.get("FFD_NVCC_FLAGS", "").split()
